@@ -1,0 +1,149 @@
+/*
+ * owwb200.h - C ABI of libowwb200.so: the B200 (sm_100a) replacement for the three
+ * inference sessions on openWakeWord's streaming hot path, plus the device-resident
+ * stream state that sits between them.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference/):
+ *   oww_melspectrogram   -> AudioFeatures.melspec_model_predict   openwakeword/utils.py:84-87,202
+ *                           (melspectrogram.onnx; graph spec notebooks/converting_google_speech_embedding_model.ipynb:426-477)
+ *   oww_embed_windows    -> AudioFeatures.embedding_model_predict openwakeword/utils.py:90-93,235,443
+ *                           (embedding_model.onnx; graph spec same notebook :871-951)
+ *   oww_head_predict     -> Model.model_prediction_function[name] openwakeword/model.py:137-138,158-159
+ *                           (<head>.onnx; family openwakeword/train.py:56-83,144-165)
+ *   oww_set_streams / oww_reset / oww_step / oww_step_host
+ *                        -> AudioFeatures buffers + _streaming_features + the per-head window reads of
+ *                           Model.predict                         openwakeword/utils.py:163-178,387-460; model.py:282-302
+ *   oww_embed_clips      -> AudioFeatures.embed_clips             openwakeword/utils.py:358-385
+ *   oww_predict_clips    -> Model.predict_clip over many clips (bulk_predict's inner loop)
+ *                                                                 openwakeword/model.py:388-426; utils.py:467-539
+ *   oww_get_features / oww_get_mel
+ *                        -> AudioFeatures.get_features / .melspectrogram_buffer   openwakeword/utils.py:454-460,165
+ *
+ * Conventions: every function returns 0 (OWW_OK) or a negative code; oww_last_error() gives the
+ * message of the last failure on that handle (or, with NULL, of the last failed oww_create).
+ * No exceptions cross the boundary.  Pointers named d_* are CUDA device addresses on the handle's
+ * device (e.g. torch.Tensor.data_ptr()); h_* are host addresses.  `stream` is a cudaStream_t
+ * passed as void* (NULL = the legacy default stream); all device work of a call is enqueued on it
+ * and the call does not synchronise unless stated.  The caller owns every buffer it passes; the
+ * library owns weights, rings and scratch inside the handle.  A handle is single-producer: one
+ * host thread at a time.
+ */
+#ifndef OWWB200_H
+#define OWWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OWW_OK            0
+#define OWW_EINVAL      (-1)   /* bad argument / wrong call order            */
+#define OWW_ECUDA       (-2)   /* a CUDA runtime call failed                 */
+#define OWW_ENOMEM      (-3)   /* host or device allocation failed           */
+#define OWW_EUNSUPPORTED (-4)  /* graph shape outside what the kernels cover */
+
+#define OWW_SAMPLES_PER_CHUNK 1280   /* 80 ms @ 16 kHz                         */
+#define OWW_MEL_BINS            32
+#define OWW_WINDOW_ROWS         76   /* mel rows per embedding window          */
+#define OWW_EMBEDDING_DIM       96
+#define OWW_INIT_FEATURE_ROWS   41   /* rows AudioFeatures seeds the ring with */
+#define OWW_MAX_HEAD_LAYERS      8
+
+/* embedding-CNN execution modes */
+#define OWW_CNN_FP32_WINDOW       0  /* CUDA-core fp32, full 76-row window per frame (reference-shaped)  */
+#define OWW_CNN_FP32_INCREMENTAL  1  /* CUDA-core fp32, per-stream activation tails: only the 8 new rows */
+#define OWW_CNN_TC_WINDOW         2  /* tcgen05 fp16-operand/fp32-accumulate implicit GEMM, full window  */
+
+typedef struct oww_ctx oww_ctx;
+
+typedef struct oww_config {
+    int32_t device;        /* CUDA device ordinal                                               */
+    int32_t max_chunks;    /* largest n_chunks a single oww_step may carry (>=1)                */
+    int32_t cnn_mode;      /* OWW_CNN_*                                                         */
+    int32_t window_batch;  /* windows per CNN sub-batch in the window modes (0 = default)       */
+    int32_t reserved[4];
+} oww_config;
+
+typedef struct oww_head_desc {
+    int32_t n_in;                              /* embedding frames read per prediction (model_inputs)  */
+    int32_t n_layers;                          /* Linear layers (>=1, <= OWW_MAX_HEAD_LAYERS)          */
+    int32_t dims[OWW_MAX_HEAD_LAYERS + 1];     /* dims[0] = n_in*96, dims[n_layers] = n_out            */
+    int32_t layernorm;                         /* 1: LayerNorm(eps 1e-5) after every hidden Linear     */
+    int32_t final_act;                         /* 0 none, 1 sigmoid, 2 softmax, 3 relu then softmax    */
+} oww_head_desc;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int  oww_create(const oww_config* cfg, oww_ctx** out);
+void oww_destroy(oww_ctx* ctx);
+const char* oww_last_error(const oww_ctx* ctx);
+const char* oww_version(void);
+
+/* ---- weights (host pointers; copied) ------------------------------------------------------ */
+/* window512: the 512-tap analysis window (periodic Hann(400) centred); mel_fb: [257][32] filterbank.
+ * Either may be NULL to use the built-in constants computed in double precision.                */
+int oww_load_mel(oww_ctx* ctx, const float* h_window512, const float* h_mel_fb);
+/* blob layout: openwakeword_b200/weights.py:pack_embedding_blob (20 x {HWIO kernel, scale, bias}). */
+int oww_load_embedding(oww_ctx* ctx, const float* h_blob, size_t n_floats);
+/* blob layout: weights.py:pack_head_blob.  *head_id receives the index; score columns are
+ * appended in head order (head 0's n_out columns first).                                        */
+int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, size_t n_floats, int* head_id);
+int oww_n_heads(const oww_ctx* ctx);
+int oww_n_outputs(const oww_ctx* ctx);          /* total score columns over all heads           */
+
+/* ---- stateless graph calls (drop-in for the three ORT sessions) --------------------------- */
+/* d_pcm [n_clips][n_samples] int16 -> d_mel [n_clips][T][32], T = (n_samples-512)/160+1.
+ * The -80 dB clamp is per clip (the reference's CPU path runs the graph one clip per call).
+ * affine != 0 applies AudioFeatures' x/10+2 (utils.py:180,206).                                 */
+int oww_melspectrogram(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples,
+                       float* d_mel, int affine, void* stream);
+/* d_windows [n][76][32] float32 -> d_emb [n][96] */
+int oww_embed_windows(oww_ctx* ctx, const float* d_windows, int n, float* d_emb, void* stream);
+/* d_feats [n][n_in][96] -> d_out [n][n_out] */
+int oww_head_predict(oww_ctx* ctx, int head_id, const float* d_feats, int n, float* d_out, void* stream);
+
+/* ---- streaming state ----------------------------------------------------------------------- */
+int oww_set_streams(oww_ctx* ctx, int n_streams);    /* (re)allocates rings; implies reset of all */
+int oww_n_streams(const oww_ctx* ctx);
+/* Reset streams to AudioFeatures.__init__/reset() state: empty PCM history, mel ring = ones(76,32),
+ * feature ring = h_feature_init[n_rows][96] (NULL -> zeros(41,96); the reference fills it with
+ * embeddings of unseeded noise, SURVEY.md F6 - pass the same rows to both sides for parity).
+ * h_stream_ids NULL = all streams.  Synchronises.                                              */
+int oww_reset(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows);
+/* One predict() worth of work for every stream: n_chunks*1280 new samples per stream.
+ * d_pcm row b starts at d_pcm + b*pcm_stride (samples).  d_scores [n_streams][oww_n_outputs]:
+ * per head the element-wise max over the n_chunks window positions (model.py:287-298).          */
+int oww_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks,
+             float* d_scores, void* stream);
+/* Same, host buffers: H2D of the PCM and D2H of the scores through pinned staging on the
+ * handle's own stream; returns after the scores have landed in h_scores.                        */
+int oww_step_host(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, float* h_scores);
+/* last n rows of one stream's feature ring, ending `back` rows before the newest -> h_out[n][96];
+ * rows older than the ring holds come back as zeros.  Synchronises.                             */
+int oww_get_features(oww_ctx* ctx, int stream_id, int n, int back, float* h_out);
+int oww_get_mel(oww_ctx* ctx, int stream_id, int n_rows, float* h_out);   /* last n_rows<=76 mel rows */
+
+/* ---- batch paths --------------------------------------------------------------------------- */
+/* d_pcm [n_clips][n_samples] -> d_emb [n_clips][W][96], W = (T-76)/8+1 (utils.py:322).           */
+int oww_embed_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, float* d_emb, void* stream);
+/* predict_clip for n_clips equal-length clips, each from a FRESH state seeded with h_feature_init
+ * (SURVEY.md F9): pad_samples zeros each side, 1280-sample steps, steps = len(range(0, L-1280, 1280)).
+ * d_scores [n_clips][steps][oww_n_outputs].  Raw head outputs (the first-5-zeroing of
+ * model.py:330-333 is label bookkeeping done by the host wrapper).  Uses a private stream set.  */
+int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, int pad_samples,
+                      const float* h_feature_init, int n_rows, float* d_scores, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+uint64_t oww_launch_count(const oww_ctx* ctx);       /* kernels launched by this handle so far   */
+/* n_slots > 0: every following oww_step / oww_step_host brackets its three stages (mel, embedding
+ * CNN + ring append, heads) with CUDA events on the launching stream, step k in slot k % n_slots;
+ * 0 disables.  oww_stage_ms synchronises on the recorded events and returns the per-step AVERAGE
+ * {mel, cnn, heads} milliseconds over the steps recorded since enabling (at most n_slots).      */
+int oww_enable_stage_timing(oww_ctx* ctx, int n_slots);
+int oww_stage_ms(oww_ctx* ctx, float out_ms[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OWWB200_H */

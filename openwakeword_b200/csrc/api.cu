@@ -1,0 +1,517 @@
+// C ABI of libowwb200.so (include/owwb200.h): handle lifetime, weight upload, stream state and the
+// orchestration of one streaming step  PCM -> K1 mel -> K2 embedding CNN -> ring append -> K3 heads.
+#include "oww_internal.h"
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+
+static thread_local std::string g_create_error;
+
+int oww_fail(oww_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+namespace {
+
+const int kLayerTable[OWW_N_CONV][6] = {   // kh kw cin cout pool_t pool_f  
+    {3, 3, 1, 24, 0, 0},
+    {1, 3, 24, 24, 0, 0}, {3, 1, 24, 24, 2, 2},
+    {1, 3, 24, 48, 0, 0}, {3, 1, 48, 48, 0, 0},
+    {1, 3, 48, 48, 0, 0}, {3, 1, 48, 48, 1, 2},
+    {1, 3, 48, 72, 0, 0}, {3, 1, 72, 72, 0, 0},
+    {1, 3, 72, 72, 0, 0}, {3, 1, 72, 72, 2, 2},
+    {1, 3, 72, 96, 0, 0}, {3, 1, 96, 96, 0, 0},
+    {1, 3, 96, 96, 0, 0}, {3, 1, 96, 96, 1, 2},
+    {1, 3, 96, 96, 0, 0}, {3, 1, 96, 96, 0, 0},
+    {1, 3, 96, 96, 0, 0}, {3, 1, 96, 96, 2, 2},
+    {3, 1, 96, 96, 0, 0},
+};
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+__global__ void reset_kernel(const int* ids, int n_ids, int n_streams, int16_t* tail, int* seen, int* mel_count,
+                             int* feat_count, float* mel_ring, int mel_rows, float* feat_ring, int feat_rows,
+                             const float* feat_init, int n_rows) {
+    const int j = blockIdx.x;
+    const int b = ids ? ids[j] : j;
+    if (b < 0 || b >= n_streams) return;
+    for (int i = threadIdx.x; i < OWW_TAIL; i += blockDim.x) tail[(int64_t)b * OWW_TAIL + i] = 0;
+    float* mr = mel_ring + (int64_t)b * mel_rows * 32;
+    for (int i = threadIdx.x; i < mel_rows * 32; i += blockDim.x) mr[i] = 1.0f;     // np.ones((76,32)), utils.py:165
+    float* fr = feat_ring + (int64_t)b * feat_rows * 96;
+    for (int i = threadIdx.x; i < feat_rows * 96; i += blockDim.x)
+        fr[i] = (i < n_rows * 96 && feat_init) ? feat_init[i] : 0.f;
+    if (threadIdx.x == 0) {
+        seen[b] = 0;
+        mel_count[b] = OWW_WINDOW_ROWS;
+        feat_count[b] = n_rows;
+    }
+}
+
+__global__ void gather_chunk_kernel(const int16_t* pcm, int n_clips, int n_samples, int pad, int step, int16_t* out) {
+    const int64_t total = (int64_t)n_clips * OWW_SAMPLES_PER_CHUNK;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i / OWW_SAMPLES_PER_CHUNK), k = (int)(i % OWW_SAMPLES_PER_CHUNK);
+        const int64_t p = (int64_t)step * OWW_SAMPLES_PER_CHUNK + k - pad;
+        out[i] = (p >= 0 && p < n_samples) ? pcm[(int64_t)c * n_samples + p] : (int16_t)0;
+    }
+}
+
+void free_streams(oww_ctx* c) {
+    cudaFree(c->d_tail); cudaFree(c->d_seen); cudaFree(c->d_mel_count); cudaFree(c->d_feat_count);
+    cudaFree(c->d_mel_ring); cudaFree(c->d_feat_ring); cudaFree(c->d_act[0]); cudaFree(c->d_act[1]);
+    cudaFree(c->d_emb_tmp); cudaFree(c->d_tails); cudaFree(c->d_inc_act[0]); cudaFree(c->d_inc_act[1]);
+    cudaFree(c->d_inc_valid);
+    c->d_tail = nullptr; c->d_seen = c->d_mel_count = c->d_feat_count = c->d_inc_valid = nullptr;
+    c->d_mel_ring = c->d_feat_ring = c->d_act[0] = c->d_act[1] = c->d_emb_tmp = c->d_tails = nullptr;
+    c->d_inc_act[0] = c->d_inc_act[1] = nullptr;
+    c->act_floats = c->emb_tmp_floats = c->inc_act_floats = 0;
+    c->n_streams = 0;
+}
+
+int ensure_act(oww_ctx* ctx, size_t floats) {
+    if (ctx->act_floats >= floats) return OWW_OK;
+    cudaFree(ctx->d_act[0]); cudaFree(ctx->d_act[1]);
+    ctx->d_act[0] = ctx->d_act[1] = nullptr; ctx->act_floats = 0;
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_act[0], floats * sizeof(float)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_act[1], floats * sizeof(float)));
+    ctx->act_floats = floats;
+    return OWW_OK;
+}
+
+int ensure_emb_tmp(oww_ctx* ctx, size_t floats) {
+    if (ctx->emb_tmp_floats >= floats) return OWW_OK;
+    cudaFree(ctx->d_emb_tmp); ctx->d_emb_tmp = nullptr; ctx->emb_tmp_floats = 0;
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_emb_tmp, floats * sizeof(float)));
+    ctx->emb_tmp_floats = floats;
+    return OWW_OK;
+}
+
+int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks, float* d_scores, int out_stride,
+              cudaStream_t s) {
+    const int B = ctx->n_streams;
+    if (B <= 0) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
+    if (n_chunks < 1 || n_chunks > ctx->cfg.max_chunks)
+        return oww_fail(ctx, OWW_EINVAL, "n_chunks=%d outside [1,%d]", n_chunks, ctx->cfg.max_chunks);
+    if (!ctx->mel_loaded || !ctx->emb_loaded) return oww_fail(ctx, OWW_EINVAL, "weights not loaded");
+    int rc;
+    cudaEvent_t* ev = ctx->timing ? &ctx->ev[4 * (ctx->ev_steps % ctx->ev_slots)] : nullptr;
+    if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[0], s));
+    MelLaunch m{d_pcm, pcm_stride, n_chunks * OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
+                (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, B, 1, n_chunks};
+    if ((rc = oww_mel_launch(ctx, m, s))) return rc;
+    if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
+    WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, B, n_chunks};
+    if ((rc = oww_cnn_window_fp32(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s))) return rc;
+    if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, n_chunks, s))) return rc;
+    if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
+    for (int i = n_chunks - 1; i >= 0; --i) {
+        FeatSrc fs{ctx->d_feat_ring, (int64_t)ctx->feat_rows * 96, ctx->d_feat_count, ctx->feat_rows - 1, i};
+        if ((rc = oww_heads_launch(ctx, -1, fs, B, d_scores, out_stride, 0, i != n_chunks - 1, s))) return rc;
+    }
+    if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[3], s)); ctx->ev_steps++; }
+    return OWW_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* oww_version(void) { return "owwb200 0.1 (sm_100a)"; }
+
+const char* oww_last_error(const oww_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int oww_create(const oww_config* cfg, oww_ctx** out) {
+    if (!cfg || !out) return oww_fail(nullptr, OWW_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return oww_fail(nullptr, OWW_ECUDA, "no CUDA device: %s", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return oww_fail(nullptr, OWW_EINVAL, "device %d out of range", cfg->device);
+    if (cfg->cnn_mode != OWW_CNN_FP32_WINDOW)
+        return oww_fail(nullptr, OWW_EUNSUPPORTED, "cnn_mode %d not built in this version", cfg->cnn_mode);
+    oww_ctx* ctx = new (std::nothrow) oww_ctx();
+    if (!ctx) return oww_fail(nullptr, OWW_ENOMEM, "out of host memory");
+    ctx->cfg = *cfg;
+    if (ctx->cfg.max_chunks < 1) ctx->cfg.max_chunks = 1;
+    ctx->device = cfg->device;
+    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : 512;
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) {
+        oww_fail(nullptr, OWW_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+        delete ctx; return OWW_ECUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        oww_fail(nullptr, OWW_EUNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+        delete ctx; return OWW_EUNSUPPORTED;
+    }
+    cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        ConvLayer& L = ctx->conv[li];
+        L.kh = kLayerTable[li][0]; L.kw = kLayerTable[li][1]; L.cin = kLayerTable[li][2]; L.cout = kLayerTable[li][3];
+        L.pool_t = kLayerTable[li][4]; L.pool_f = kLayerTable[li][5];
+        L.d_w = L.d_scale = L.d_bias = nullptr;
+    }
+    *out = ctx;
+    return OWW_OK;
+}
+
+void oww_destroy(oww_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->clip_ctx) { oww_ctx* c = ctx->clip_ctx; ctx->clip_ctx = nullptr; free_streams(c);
+        cudaStreamDestroy(c->own_stream);
+        cudaFree(c->d_pcm_stage); delete c; }
+    free_streams(ctx);
+    cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
+    cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob);
+    for (auto& h : ctx->heads) cudaFree(h.d_blob);
+    cudaFreeHost(ctx->h_pcm_pinned); cudaFreeHost(ctx->h_scores_pinned);
+    cudaFree(ctx->d_pcm_stage); cudaFree(ctx->d_scores_stage);
+    for (auto e : ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int oww_load_embedding(oww_ctx* ctx, const float* h_blob, size_t n_floats) {
+    if (!ctx || !h_blob) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    size_t need = 0;
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        const ConvLayer& L = ctx->conv[li];
+        need += (size_t)L.kh * L.kw * L.cin * L.cout + 2 * (size_t)L.cout;
+    }
+    if (n_floats != need)
+        return oww_fail(ctx, OWW_EINVAL, "embedding blob has %zu floats, the reference CNN needs %zu", n_floats, need);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_emb_blob) OWW_CUDA(ctx, cudaMalloc(&ctx->d_emb_blob, need * sizeof(float)));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_emb_blob, h_blob, need * sizeof(float), cudaMemcpyHostToDevice));
+    size_t off = 0;
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        ConvLayer& L = ctx->conv[li];
+        L.d_w = ctx->d_emb_blob + off; off += (size_t)L.kh * L.kw * L.cin * L.cout;
+        L.d_scale = ctx->d_emb_blob + off; off += L.cout;
+        L.d_bias = ctx->d_emb_blob + off; off += L.cout;
+    }
+    ctx->emb_loaded = true;
+    return OWW_OK;
+}
+
+int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, size_t n_floats, int* head_id) {
+    if (!ctx || !desc || !h_blob) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (desc->n_layers < 1 || desc->n_layers > OWW_MAX_HEAD_LAYERS)
+        return oww_fail(ctx, OWW_EUNSUPPORTED, "head has %d Linear layers (1..%d supported)", desc->n_layers, OWW_MAX_HEAD_LAYERS);
+    if (desc->n_in < 1 || desc->dims[0] != desc->n_in * OWW_EMBEDDING_DIM)
+        return oww_fail(ctx, OWW_EINVAL, "dims[0]=%d must equal n_in*96=%d", desc->dims[0], desc->n_in * OWW_EMBEDDING_DIM);
+    if (desc->final_act < 0 || desc->final_act > 3) return oww_fail(ctx, OWW_EINVAL, "bad final_act");
+    if (ctx->heads.size() >= 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 heads per handle");
+    Head h;
+    h.desc = *desc;
+    size_t off = 0;
+    for (int l = 0; l < desc->n_layers; ++l) {
+        const int din = desc->dims[l], dout = desc->dims[l + 1];
+        if (dout < 1 || dout > 256) return oww_fail(ctx, OWW_EUNSUPPORTED, "layer width %d outside 1..256", dout);
+        h.w_off.push_back(off); off += (size_t)din * dout;
+        h.b_off.push_back(off); off += dout;
+        if (desc->layernorm && l < desc->n_layers - 1) {
+            h.g_off.push_back(off); off += dout;
+            h.h_off.push_back(off); off += dout;
+        } else { h.g_off.push_back(0); h.h_off.push_back(0); }
+    }
+    if (off != n_floats) return oww_fail(ctx, OWW_EINVAL, "head blob has %zu floats, descriptor needs %zu", n_floats, off);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaMalloc(&h.d_blob, off * sizeof(float)));
+    OWW_CUDA(ctx, cudaMemcpy(h.d_blob, h_blob, off * sizeof(float), cudaMemcpyHostToDevice));
+    h.n_out = desc->dims[desc->n_layers];
+    h.col0 = ctx->n_out_total;
+    ctx->n_out_total += h.n_out;
+    ctx->max_n_in = std::max(ctx->max_n_in, desc->n_in);
+    ctx->heads.push_back(h);
+    if (head_id) *head_id = (int)ctx->heads.size() - 1;
+    return OWW_OK;
+}
+
+int oww_n_heads(const oww_ctx* ctx) { return ctx ? (int)ctx->heads.size() : 0; }
+int oww_n_outputs(const oww_ctx* ctx) { return ctx ? ctx->n_out_total : 0; }
+int oww_n_streams(const oww_ctx* ctx) { return ctx ? ctx->n_streams : 0; }
+uint64_t oww_launch_count(const oww_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int oww_melspectrogram(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, float* d_mel, int affine, void* stream) {
+    if (!ctx || !d_pcm || !d_mel) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (n_samples < OWW_FFT_N) return oww_fail(ctx, OWW_EINVAL, "need at least 512 samples, got %d", n_samples);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int T = (n_samples - OWW_FFT_N) / OWW_HOP + 1;
+    MelLaunch m{d_pcm, (int64_t)n_samples, n_samples, nullptr, nullptr, d_mel, (int64_t)T * 32, -1, nullptr, n_clips,
+                affine, 0};
+    return oww_mel_launch(ctx, m, (cudaStream_t)stream);
+}
+
+int oww_embed_windows(oww_ctx* ctx, const float* d_windows, int n, float* d_emb, void* stream) {
+    if (!ctx || !d_windows || !d_emb) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_act(ctx, (size_t)std::min(n, ctx->window_batch) * 74 * 32 * 24);
+    if (rc) return rc;
+    WindowSrc src{d_windows, (int64_t)OWW_WINDOW_ROWS * 32, nullptr, -1, 0, 0};
+    return oww_cnn_window_fp32(ctx, src, n, d_emb, (cudaStream_t)stream);
+}
+
+int oww_head_predict(oww_ctx* ctx, int head_id, const float* d_feats, int n, float* d_out, void* stream) {
+    if (!ctx || !d_feats || !d_out) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (head_id < 0 || head_id >= (int)ctx->heads.size()) return oww_fail(ctx, OWW_EINVAL, "bad head_id %d", head_id);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const Head& h = ctx->heads[head_id];
+    FeatSrc fs{d_feats, (int64_t)h.desc.n_in * 96, nullptr, -1, 0};
+    return oww_heads_launch(ctx, head_id, fs, n, d_out, h.n_out, 0, 0, (cudaStream_t)stream);
+}
+
+int oww_set_streams(oww_ctx* ctx, int n_streams) {
+    if (!ctx || n_streams < 1) return oww_fail(ctx, OWW_EINVAL, "n_streams must be >= 1");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaDeviceSynchronize());
+    free_streams(ctx);
+    const int B = n_streams, mc = ctx->cfg.max_chunks;
+    ctx->mel_rows = next_pow2(OWW_WINDOW_ROWS + 8 * mc);
+    ctx->feat_rows = next_pow2(120 + mc);             // the reference keeps <=120 rows (utils.py:170)
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_tail, (size_t)B * OWW_TAIL * sizeof(int16_t)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_seen, (size_t)B * sizeof(int)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_mel_count, (size_t)B * sizeof(int)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_feat_count, (size_t)B * sizeof(int)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_mel_ring, (size_t)B * ctx->mel_rows * 32 * sizeof(float)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_feat_ring, (size_t)B * ctx->feat_rows * 96 * sizeof(float)));
+    ctx->n_streams = B;
+    int rc = ensure_act(ctx, (size_t)std::min(B * mc, ctx->window_batch) * 74 * 32 * 24);
+    if (rc) return rc;
+    if ((rc = ensure_emb_tmp(ctx, (size_t)B * mc * 96))) return rc;
+    return oww_reset(ctx, nullptr, B, nullptr, OWW_INIT_FEATURE_ROWS);
+}
+
+int oww_reset(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows) {
+    if (!ctx) return OWW_EINVAL;
+    if (ctx->n_streams <= 0) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
+    if (n_rows < 0 || n_rows > ctx->feat_rows) return oww_fail(ctx, OWW_EINVAL, "n_rows=%d outside [0,%d]", n_rows, ctx->feat_rows);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!h_stream_ids) n = ctx->n_streams;
+    if (n <= 0) return OWW_OK;
+    OWW_CUDA(ctx, cudaDeviceSynchronize());
+    int* d_ids = nullptr; float* d_init = nullptr;
+    if (h_stream_ids) {
+        for (int i = 0; i < n; ++i)
+            if (h_stream_ids[i] < 0 || h_stream_ids[i] >= ctx->n_streams)
+                return oww_fail(ctx, OWW_EINVAL, "stream id %d out of range", h_stream_ids[i]);
+        OWW_CUDA(ctx, cudaMalloc(&d_ids, (size_t)n * sizeof(int)));
+        OWW_CUDA(ctx, cudaMemcpy(d_ids, h_stream_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (h_feature_init && n_rows > 0) {
+        OWW_CUDA(ctx, cudaMalloc(&d_init, (size_t)n_rows * 96 * sizeof(float)));
+        OWW_CUDA(ctx, cudaMemcpy(d_init, h_feature_init, (size_t)n_rows * 96 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    reset_kernel<<<n, 256>>>(d_ids, n, ctx->n_streams, ctx->d_tail, ctx->d_seen, ctx->d_mel_count, ctx->d_feat_count,
+                             ctx->d_mel_ring, ctx->mel_rows, ctx->d_feat_ring, ctx->feat_rows, d_init, n_rows);
+    ctx->launches++;
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_ids); cudaFree(d_init);
+    if (e != cudaSuccess) return oww_fail(ctx, OWW_ECUDA, "reset failed: %s", cudaGetErrorString(e));
+    return OWW_OK;
+}
+
+int oww_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks, float* d_scores, void* stream) {
+    if (!ctx || !d_pcm || !d_scores) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    return step_core(ctx, d_pcm, pcm_stride, n_chunks, d_scores, ctx->n_out_total, (cudaStream_t)stream);
+}
+
+int oww_step_host(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, float* h_scores) {
+    if (!ctx || !h_pcm || !h_scores) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = ctx->n_streams;
+    if (B <= 0) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
+    const size_t row = (size_t)n_chunks * OWW_SAMPLES_PER_CHUNK;
+    const size_t pcm_bytes = (size_t)B * row * sizeof(int16_t);
+    const size_t sc_bytes = (size_t)B * std::max(ctx->n_out_total, 1) * sizeof(float);
+    if (ctx->h_pcm_bytes < pcm_bytes) {
+        cudaFreeHost(ctx->h_pcm_pinned); cudaFree(ctx->d_pcm_stage); ctx->h_pcm_pinned = nullptr; ctx->d_pcm_stage = nullptr;
+        OWW_CUDA(ctx, cudaMallocHost(&ctx->h_pcm_pinned, pcm_bytes));
+        OWW_CUDA(ctx, cudaMalloc(&ctx->d_pcm_stage, pcm_bytes));
+        ctx->h_pcm_bytes = ctx->d_pcm_bytes = pcm_bytes;
+    }
+    if (ctx->h_scores_bytes < sc_bytes) {
+        cudaFreeHost(ctx->h_scores_pinned); cudaFree(ctx->d_scores_stage); ctx->h_scores_pinned = nullptr; ctx->d_scores_stage = nullptr;
+        OWW_CUDA(ctx, cudaMallocHost(&ctx->h_scores_pinned, sc_bytes));
+        OWW_CUDA(ctx, cudaMalloc(&ctx->d_scores_stage, sc_bytes));
+        ctx->h_scores_bytes = ctx->d_scores_bytes = sc_bytes;
+    }
+    // pack rows into the pinned buffer (pcm_stride may exceed the row length)
+    if (pcm_stride == (int64_t)row) {
+        std::memcpy(ctx->h_pcm_pinned, h_pcm, pcm_bytes);
+    } else {
+        for (int b = 0; b < B; ++b)
+            std::memcpy(ctx->h_pcm_pinned + (size_t)b * row, h_pcm + (size_t)b * pcm_stride, row * sizeof(int16_t));
+    }
+    cudaStream_t s = ctx->own_stream;
+    OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcm_stage, ctx->h_pcm_pinned, pcm_bytes, cudaMemcpyHostToDevice, s));
+    int rc = step_core(ctx, ctx->d_pcm_stage, (int64_t)row, n_chunks, ctx->d_scores_stage, ctx->n_out_total, s);
+    if (rc) return rc;
+    if (ctx->n_out_total > 0)
+        OWW_CUDA(ctx, cudaMemcpyAsync(ctx->h_scores_pinned, ctx->d_scores_stage, (size_t)B * ctx->n_out_total * sizeof(float),
+                                      cudaMemcpyDeviceToHost, s));
+    OWW_CUDA(ctx, cudaStreamSynchronize(s));
+    if (ctx->n_out_total > 0) std::memcpy(h_scores, ctx->h_scores_pinned, (size_t)B * ctx->n_out_total * sizeof(float));
+    return OWW_OK;
+}
+
+int oww_get_features(oww_ctx* ctx, int stream_id, int n, int back, float* h_out) {
+    if (!ctx || !h_out) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (stream_id < 0 || stream_id >= ctx->n_streams) return oww_fail(ctx, OWW_EINVAL, "bad stream id");
+    if (n < 0 || back < 0 || n + back > ctx->feat_rows) return oww_fail(ctx, OWW_EINVAL, "n+back exceeds the ring (%d rows)", ctx->feat_rows);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaDeviceSynchronize());
+    int count = 0;
+    OWW_CUDA(ctx, cudaMemcpy(&count, ctx->d_feat_count + stream_id, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<float> ring((size_t)ctx->feat_rows * 96);
+    OWW_CUDA(ctx, cudaMemcpy(ring.data(), ctx->d_feat_ring + (size_t)stream_id * ctx->feat_rows * 96,
+                             ring.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const int r = count - back - n + i;
+        if (r < 0 || r < count - ctx->feat_rows) std::memset(h_out + (size_t)i * 96, 0, 96 * sizeof(float));
+        else std::memcpy(h_out + (size_t)i * 96, ring.data() + (size_t)(r & (ctx->feat_rows - 1)) * 96, 96 * sizeof(float));
+    }
+    return OWW_OK;
+}
+
+int oww_get_mel(oww_ctx* ctx, int stream_id, int n_rows, float* h_out) {
+    if (!ctx || !h_out) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (stream_id < 0 || stream_id >= ctx->n_streams) return oww_fail(ctx, OWW_EINVAL, "bad stream id");
+    if (n_rows < 0 || n_rows > OWW_WINDOW_ROWS) return oww_fail(ctx, OWW_EINVAL, "n_rows must be <= 76");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaDeviceSynchronize());
+    int count = 0;
+    OWW_CUDA(ctx, cudaMemcpy(&count, ctx->d_mel_count + stream_id, sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<float> ring((size_t)ctx->mel_rows * 32);
+    OWW_CUDA(ctx, cudaMemcpy(ring.data(), ctx->d_mel_ring + (size_t)stream_id * ctx->mel_rows * 32,
+                             ring.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n_rows; ++i) {
+        const int r = count - n_rows + i;
+        std::memcpy(h_out + (size_t)i * 32, ring.data() + (size_t)(r & (ctx->mel_rows - 1)) * 32, 32 * sizeof(float));
+    }
+    return OWW_OK;
+}
+
+int oww_embed_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, float* d_emb, void* stream) {
+    if (!ctx || !d_pcm || !d_emb) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (n_samples < OWW_FFT_N) return oww_fail(ctx, OWW_EINVAL, "need at least 512 samples");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int T = (n_samples - OWW_FFT_N) / OWW_HOP + 1;
+    if (T < OWW_WINDOW_ROWS)
+        return oww_fail(ctx, OWW_EINVAL, "Embedding model requires the input melspectrograms to have at least 76 frames");
+    const int W = (T - OWW_WINDOW_ROWS) / 8 + 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    // slabs bounded by the activation scratch (~512 windows' worth of layer-1 output)
+    const size_t per_clip = (size_t)(T - 2) * 32 * 24;
+    int rc = ensure_act(ctx, std::max(ctx->act_floats, std::max(per_clip, (size_t)ctx->window_batch * 74 * 32 * 24)));
+    if (rc) return rc;
+    const int slab = (int)std::max<size_t>(1, ctx->act_floats / per_clip);
+    float* d_mel = nullptr;
+    OWW_CUDA(ctx, cudaMallocAsync(&d_mel, (size_t)std::min(slab, n_clips) * T * 32 * sizeof(float), s));
+    for (int c0 = 0; c0 < n_clips; c0 += slab) {
+        const int m = std::min(slab, n_clips - c0);
+        MelLaunch ml{d_pcm + (size_t)c0 * n_samples, (int64_t)n_samples, n_samples, nullptr, nullptr, d_mel, (int64_t)T * 32,
+                     -1, nullptr, m, 1, 0};
+        if ((rc = oww_mel_launch(ctx, ml, s))) break;
+        if ((rc = oww_cnn_clip_fp32(ctx, d_mel, m, T, d_emb + (size_t)c0 * W * 96, s))) break;
+    }
+    cudaFreeAsync(d_mel, s);
+    return rc;
+}
+
+int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, int pad_samples,
+                      const float* h_feature_init, int n_rows, float* d_scores, void* stream) {
+    if (!ctx || !d_pcm || !d_scores) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (n_clips < 1 || n_samples < 1 || pad_samples < 0) return oww_fail(ctx, OWW_EINVAL, "bad clip geometry");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t L = (int64_t)n_samples + 2 * (int64_t)pad_samples;
+    const int steps = L > OWW_SAMPLES_PER_CHUNK ? (int)((L - OWW_SAMPLES_PER_CHUNK + OWW_SAMPLES_PER_CHUNK - 1) / OWW_SAMPLES_PER_CHUNK) : 0;
+    if (steps == 0) return OWW_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int slab_max = 16384;
+    // the private stream set shares this handle's weights (shallow copy, non-owning)
+    if (!ctx->clip_ctx) {
+        oww_ctx* c = new (std::nothrow) oww_ctx();
+        if (!c) return oww_fail(ctx, OWW_ENOMEM, "out of host memory");
+        c->cfg = ctx->cfg; c->cfg.max_chunks = 1; c->device = ctx->device; c->sm_count = ctx->sm_count;
+        c->window_batch = ctx->window_batch;
+        cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+        ctx->clip_ctx = c;
+    }
+    oww_ctx* c = ctx->clip_ctx;
+    c->mel_loaded = ctx->mel_loaded; c->d_window = ctx->d_window; c->d_twiddle = ctx->d_twiddle;
+    c->d_mel_start = ctx->d_mel_start; c->d_mel_len = ctx->d_mel_len; c->d_mel_w = ctx->d_mel_w; c->mel_kmax = ctx->mel_kmax;
+    c->emb_loaded = ctx->emb_loaded;
+    for (int li = 0; li < OWW_N_CONV; ++li) c->conv[li] = ctx->conv[li];
+    c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in;
+    int rc = OWW_OK;
+    for (int c0 = 0; c0 < n_clips && rc == OWW_OK; c0 += slab_max) {
+        const int m = std::min(slab_max, n_clips - c0);
+        if (c->n_streams != m) { if ((rc = oww_set_streams(c, m))) { ctx->err = c->err; break; } }
+        if ((rc = oww_reset(c, nullptr, m, h_feature_init, h_feature_init ? n_rows : OWW_INIT_FEATURE_ROWS))) { ctx->err = c->err; break; }
+        const size_t stage_bytes = (size_t)m * OWW_SAMPLES_PER_CHUNK * sizeof(int16_t);
+        if (c->d_pcm_bytes < stage_bytes) {
+            cudaFree(c->d_pcm_stage); c->d_pcm_stage = nullptr;
+            OWW_CUDA(ctx, cudaMalloc(&c->d_pcm_stage, stage_bytes));
+            c->d_pcm_bytes = stage_bytes;
+        }
+        for (int st = 0; st < steps; ++st) {
+            unsigned grid = (unsigned)std::min<int64_t>(((int64_t)m * OWW_SAMPLES_PER_CHUNK + 255) / 256, (int64_t)ctx->sm_count * 32);
+            gather_chunk_kernel<<<grid, 256, 0, s>>>(d_pcm + (size_t)c0 * n_samples, m, n_samples, pad_samples, st, c->d_pcm_stage);
+            c->launches++;
+            rc = step_core(c, c->d_pcm_stage, OWW_SAMPLES_PER_CHUNK, 1,
+                           d_scores + ((size_t)c0 * steps + st) * ctx->n_out_total, steps * ctx->n_out_total, s);
+            if (rc) { ctx->err = c->err; break; }
+        }
+    }
+    ctx->launches += c->launches; c->launches = 0;
+    c->heads.clear();   // do not let the child free shared blobs
+    return rc;
+}
+
+int oww_enable_stage_timing(oww_ctx* ctx, int n_slots) {
+    if (!ctx) return OWW_EINVAL;
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->timing = n_slots > 0;
+    ctx->ev_steps = 0;
+    if (n_slots > 4096) n_slots = 4096;
+    while ((int)ctx->ev.size() < 4 * n_slots) {
+        cudaEvent_t e;
+        OWW_CUDA(ctx, cudaEventCreate(&e));
+        ctx->ev.push_back(e);
+    }
+    if (n_slots > 0) ctx->ev_slots = n_slots;
+    return OWW_OK;
+}
+
+int oww_stage_ms(oww_ctx* ctx, float out_ms[3]) {
+    if (!ctx || !out_ms) return OWW_EINVAL;
+    if (!ctx->timing || ctx->ev_steps == 0) return oww_fail(ctx, OWW_EINVAL, "no timed step recorded");
+    const long n = ctx->ev_steps < ctx->ev_slots ? ctx->ev_steps : ctx->ev_slots;
+    double acc[3] = {0, 0, 0};
+    for (long k = 0; k < n; ++k) {
+        cudaEvent_t* ev = &ctx->ev[4 * k];
+        OWW_CUDA(ctx, cudaEventSynchronize(ev[3]));
+        for (int i = 0; i < 3; ++i) {
+            float ms = 0.f;
+            OWW_CUDA(ctx, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            acc[i] += ms;
+        }
+    }
+    for (int i = 0; i < 3; ++i) out_ms[i] = (float)(acc[i] / n);
+    return OWW_OK;
+}
+
+}  // extern "C"

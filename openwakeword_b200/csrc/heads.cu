@@ -1,0 +1,216 @@
+// K3: wake-word classifier heads, one CTA per (tile of 32 streams, head).
+//
+// Replaces the per-head onnxruntime sessions of the reference
+// (/root/reference/openwakeword/model.py:137-138,153-159,287-302) for the DNN family of
+// /root/reference/openwakeword/train.py:56-83,144-165: Flatten([n_in,96]) -> Linear -> [LayerNorm]
+// -> ReLU -> n x (Linear -> [LayerNorm] -> ReLU) -> Linear -> Sigmoid | (ReLU+)Softmax.
+// The input window is gathered straight from the per-stream feature ring (AudioFeatures.get_features,
+// utils.py:454-460), so predict() needs no host copy of the embeddings.  All loaded heads run in the
+// same launch (blockIdx.y = head), each reading the same ring rows - "one embedding, every head".
+#include "oww_internal.h"
+
+namespace {
+
+constexpr int TB = 32;          // samples per CTA
+constexpr int KC = 32;          // K chunk of the first (wide) layer
+constexpr int NTHREADS = 256;
+constexpr int HMAX = 256;       // widest hidden / output layer supported
+
+struct HeadDev {
+    const float* blob;
+    int n_in, n_layers, layernorm, final_act;
+    int dims[OWW_MAX_HEAD_LAYERS + 1];
+    int w_off[OWW_MAX_HEAD_LAYERS], b_off[OWW_MAX_HEAD_LAYERS], g_off[OWW_MAX_HEAD_LAYERS], h_off[OWW_MAX_HEAD_LAYERS];
+    int col0;
+};
+struct HeadsArgs {
+    HeadDev head[16];
+    FeatSrc src;
+    int n; float* out; int out_stride; int combine_max;
+};
+
+__device__ __forceinline__ int next_pow2_32(int d) { int p = 32; while (p < d) p <<= 1; return p; }
+
+// acc[i] holds output (row = rgrp + R*i, col = d) for this thread; DP = padded layer width.
+template <int DP>
+__device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& src, int s0, int n, float (*xs)[KC + 1],
+                                             float* ws, float* acc) {
+    constexpr int R = NTHREADS / DP, NR = TB / R;
+    const int tid = threadIdx.x, d = tid % DP, rgrp = tid / DP;
+    const int D = H.dims[1], K = H.dims[0];
+    const float* W = H.blob + H.w_off[0];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int frow = k0 / 96, fcol = k0 % 96;
+        for (int q = tid; q < TB * KC; q += NTHREADS) {
+            const int tb = q / KC, kk = q % KC;
+            const int s = s0 + tb;
+            float v = 0.f;
+            if (s < n) {
+                if (src.count) {
+                    const int r = src.count[s] - src.back - H.n_in + frow;
+                    v = r >= 0 ? __ldg(src.base + (int64_t)s * src.stride + (int64_t)(r & src.rows_mask) * 96 + fcol + kk)
+                               : 0.f;
+                } else {
+                    v = __ldg(src.base + (int64_t)s * src.stride + (int64_t)frow * 96 + fcol + kk);
+                }
+            }
+            xs[tb][kk] = v;
+        }
+        for (int q = tid; q < KC * D; q += NTHREADS) ws[q] = __ldg(W + (int64_t)k0 * D + q);
+        __syncthreads();
+        if (d < D) {
+#pragma unroll 8
+            for (int kk = 0; kk < KC; ++kk) {
+                const float w = ws[kk * D + d];
+#pragma unroll
+                for (int i = 0; i < NR; ++i) acc[i] = fmaf(xs[rgrp + R * i][kk], w, acc[i]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int DP>
+__device__ __forceinline__ void dense_smem(const float* __restrict__ W, int K, int D, const float (*hin)[HMAX + 1],
+                                           float* acc) {
+    constexpr int R = NTHREADS / DP, NR = TB / R;
+    const int tid = threadIdx.x, d = tid % DP, rgrp = tid / DP;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+    if (d < D) {
+        for (int k = 0; k < K; ++k) {
+            const float w = __ldg(W + (int64_t)k * D + d);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) acc[i] = fmaf(hin[rgrp + R * i][k], w, acc[i]);
+        }
+    }
+}
+
+template <int DP>
+__device__ __forceinline__ void store_acc(const float* acc, const float* bias, int D, float (*hout)[HMAX + 1]) {
+    constexpr int R = NTHREADS / DP, NR = TB / R;
+    const int tid = threadIdx.x, d = tid % DP, rgrp = tid / DP;
+    if (d < D) {
+        const float b = __ldg(bias + d);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) hout[rgrp + R * i][d] = acc[i] + b;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
+    extern __shared__ __align__(16) float smem_dyn[];
+    float (*xs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(smem_dyn);
+    float* ws = smem_dyn + TB * (KC + 1);
+    float (*hA)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + KC * HMAX);
+    float (*hB)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + KC * HMAX + TB * (HMAX + 1));
+    const HeadDev& H = a.head[blockIdx.y];
+    const int s0 = blockIdx.x * TB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float acc[32];
+
+    float (*cur)[HMAX + 1] = hA;
+    float (*nxt)[HMAX + 1] = hB;
+    for (int l = 0; l < H.n_layers; ++l) {
+        const int D = H.dims[l + 1], K = H.dims[l];
+        const int DP = next_pow2_32(D);
+        if (l == 0) {
+            switch (DP) {
+                case 32: dense_gather<32>(H, a.src, s0, a.n, xs, ws, acc); store_acc<32>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 64: dense_gather<64>(H, a.src, s0, a.n, xs, ws, acc); store_acc<64>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 128: dense_gather<128>(H, a.src, s0, a.n, xs, ws, acc); store_acc<128>(acc, H.blob + H.b_off[0], D, cur); break;
+                default: dense_gather<256>(H, a.src, s0, a.n, xs, ws, acc); store_acc<256>(acc, H.blob + H.b_off[0], D, cur); break;
+            }
+        } else {
+            const float* W = H.blob + H.w_off[l];
+            switch (DP) {
+                case 32: dense_smem<32>(W, K, D, cur, acc); store_acc<32>(acc, H.blob + H.b_off[l], D, nxt); break;
+                case 64: dense_smem<64>(W, K, D, cur, acc); store_acc<64>(acc, H.blob + H.b_off[l], D, nxt); break;
+                case 128: dense_smem<128>(W, K, D, cur, acc); store_acc<128>(acc, H.blob + H.b_off[l], D, nxt); break;
+                default: dense_smem<256>(W, K, D, cur, acc); store_acc<256>(acc, H.blob + H.b_off[l], D, nxt); break;
+            }
+            float (*t)[HMAX + 1] = cur; cur = nxt; nxt = t;
+        }
+        __syncthreads();
+        const bool last = l == H.n_layers - 1;
+        if (!last) {
+            // [LayerNorm] + ReLU, one warp per row
+            for (int r = warp; r < TB; r += NTHREADS / 32) {
+                if (H.layernorm) {
+                    float sum = 0.f;
+                    for (int d = lane; d < D; d += 32) sum += cur[r][d];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float mu = sum / (float)D;
+                    float sq = 0.f;
+                    for (int d = lane; d < D; d += 32) { const float c = cur[r][d] - mu; sq = fmaf(c, c, sq); }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    const float rstd = 1.0f / sqrtf(sq / (float)D + 1e-5f);
+                    const float* g = H.blob + H.g_off[l];
+                    const float* hb = H.blob + H.h_off[l];
+                    for (int d = lane; d < D; d += 32)
+                        cur[r][d] = fmaxf((cur[r][d] - mu) * rstd * __ldg(g + d) + __ldg(hb + d), 0.f);
+                } else {
+                    for (int d = lane; d < D; d += 32) cur[r][d] = fmaxf(cur[r][d], 0.f);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // final activation + store: one thread per row
+    const int n_out = H.dims[H.n_layers];
+    if (tid < TB && s0 + tid < a.n) {
+        float* row = cur[tid];
+        if (H.final_act == 1) {
+            for (int d = 0; d < n_out; ++d) row[d] = 1.0f / (1.0f + expf(-row[d]));
+        } else if (H.final_act == 2 || H.final_act == 3) {
+            float m = -INFINITY;
+            for (int d = 0; d < n_out; ++d) {
+                if (H.final_act == 3) row[d] = fmaxf(row[d], 0.f);
+                m = fmaxf(m, row[d]);
+            }
+            float sum = 0.f;
+            for (int d = 0; d < n_out; ++d) { row[d] = expf(row[d] - m); sum += row[d]; }
+            for (int d = 0; d < n_out; ++d) row[d] = row[d] / sum;
+        }
+        float* o = a.out + (int64_t)(s0 + tid) * a.out_stride + H.col0;
+        for (int d = 0; d < n_out; ++d) o[d] = a.combine_max ? fmaxf(o[d], row[d]) : row[d];
+    }
+}
+
+}  // namespace
+
+// head_id < 0: all heads (blockIdx.y = head), score columns at each head's col0 (+out_col0).
+int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float* d_out, int out_stride,
+                     int out_col0, int combine_max, cudaStream_t s) {
+    if (n <= 0) return OWW_OK;
+    const int nh = head_id < 0 ? (int)ctx->heads.size() : 1;
+    if (nh == 0) return OWW_OK;
+    if (nh > 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 heads per launch");
+    HeadsArgs a;
+    for (int i = 0; i < nh; ++i) {
+        const Head& h = ctx->heads[head_id < 0 ? i : head_id];
+        HeadDev& d = a.head[i];
+        d.blob = h.d_blob;
+        d.n_in = h.desc.n_in; d.n_layers = h.desc.n_layers; d.layernorm = h.desc.layernorm; d.final_act = h.desc.final_act;
+        for (int l = 0; l <= h.desc.n_layers; ++l) d.dims[l] = h.desc.dims[l];
+        for (int l = 0; l < h.desc.n_layers; ++l) {
+            d.w_off[l] = (int)h.w_off[l]; d.b_off[l] = (int)h.b_off[l];
+            d.g_off[l] = (int)h.g_off[l]; d.h_off[l] = (int)h.h_off[l];
+        }
+        d.col0 = (head_id < 0 ? h.col0 : 0) + out_col0;
+    }
+    a.src = src; a.n = n; a.out = d_out; a.out_stride = out_stride; a.combine_max = combine_max;
+    dim3 grid((n + TB - 1) / TB, nh);
+    constexpr size_t kSmem = sizeof(float) * (TB * (KC + 1) + KC * HMAX + 2 * TB * (HMAX + 1));
+    static bool attr_set = false;
+    if (!attr_set) {
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+        attr_set = true;
+    }
+    heads_kernel<<<grid, NTHREADS, kSmem, s>>>(a);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}

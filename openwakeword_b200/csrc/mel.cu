@@ -1,0 +1,251 @@
+// K1: int16 PCM -> log-mel rows, one CTA per (stream, call).
+//
+// Replaces the melspectrogram.onnx session of the reference
+// (/root/reference/openwakeword/utils.py:84-87,180-208; graph spec
+// notebooks/converting_google_speech_embedding_model.ipynb:426-477): frames of 512 samples every
+// 160, periodic Hann(400) zero-padded to 512, |rFFT|^2, 32 Slaney mel filters (60-3800 Hz),
+// 10*log10(max(.,1e-10)), clamp at (max over the call) - 80 dB, then x/10+2.
+//
+// The reference graph evaluates the STFT as a dense 512x514 conv; here each warp runs a 256-point
+// complex radix-4 Stockham FFT in shared memory on the even/odd-packed real frame and unpacks only
+// the bins the filterbank touches.  One CTA owns one call of one stream, so the per-call dB
+// maximum is a block reduction; the CTA also advances the stream's PCM tail and mel
+// ring, so the whole frontend is one launch with no host round trip.
+#include "oww_internal.h"
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+struct MelDev {
+    const float* window;       // [512]
+    const float2* twiddle;     // [512]
+    const int* mel_start;      // [32]
+    const int* mel_len;        // [32]
+    const float* mel_w;        // [32][OWW_MEL_MAXSUPPORT]
+    int kmax;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+__global__ void __launch_bounds__(kThreads) mel_kernel(MelLaunch p, MelDev c) {
+    __shared__ float2 s_buf[kWarps][2][256];
+    __shared__ float2 s_tw[512];
+    __shared__ float s_win[512];
+    __shared__ float s_pow[kWarps][264];
+    __shared__ float s_red[kWarps];
+
+    const int clip = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < 512; i += kThreads) { s_tw[i] = c.twiddle[i]; s_win[i] = c.window[i]; }
+
+    const bool streaming = p.tail != nullptr;
+    const int prefix = streaming ? OWW_TAIL : 0;
+    const bool fresh = streaming && p.seen[clip] == 0;
+    const int total = prefix + p.n_body;
+    const int T = (total - OWW_FFT_N) / OWW_HOP + 1;
+    const int f0 = fresh ? 3 : 0;                 // frames 0..2 would read the (absent) prefix
+    const int16_t* body = p.body + (int64_t)clip * p.body_stride;
+    const int16_t* tail = streaming ? p.tail + (int64_t)clip * OWW_TAIL : nullptr;
+    const int row0 = p.out_count ? p.out_count[clip] : 0;
+    float* out = p.out + (int64_t)clip * p.out_stride;
+    __syncthreads();
+
+    const int my_start = c.mel_start[lane];
+    const int my_len = c.mel_len[lane];
+    const float* my_w = c.mel_w + lane * OWW_MEL_MAXSUPPORT;
+    float vmax = -INFINITY;
+
+    for (int f = f0 + warp; f < T; f += kWarps) {
+        float2* a = s_buf[warp][0];
+        float2* b = s_buf[warp][1];
+        // windowed frame, packed z[n] = x[2n] + i x[2n+1]
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = lane + 32 * j;
+            const int s0 = f * OWW_HOP + 2 * n;
+            float x0, x1;
+            if (s0 + 1 < prefix) { x0 = (float)tail[s0]; x1 = (float)tail[s0 + 1]; }
+            else if (s0 >= prefix) { x0 = (float)__ldg(body + (s0 - prefix)); x1 = (float)__ldg(body + (s0 + 1 - prefix)); }
+            else { x0 = (float)tail[s0]; x1 = (float)__ldg(body); }
+            a[n] = make_float2(x0 * s_win[2 * n], x1 * s_win[2 * n + 1]);
+        }
+        __syncwarp();
+        // 256-point complex FFT, radix-4 Stockham autosort, 4 passes
+#pragma unroll
+        for (int Ns = 1; Ns < 256; Ns *= 4) {
+            const int tstep = 128 / Ns;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int j = lane + 32 * jj;
+                const int k = j & (Ns - 1);
+                float2 v0 = a[j];
+                float2 v1 = cmul(a[j + 64], s_tw[k * tstep]);
+                float2 v2 = cmul(a[j + 128], s_tw[2 * k * tstep]);
+                float2 v3 = cmul(a[j + 192], s_tw[3 * k * tstep]);
+                float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+                float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+                float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+                float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
+                float2 a3 = make_float2(d.y, -d.x);          // -i * (v1 - v3)
+                const int dst = (j / Ns) * Ns * 4 + k;
+                b[dst] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                b[dst + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                b[dst + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                b[dst + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+            }
+            __syncwarp();
+            float2* t = a; a = b; b = t;
+        }
+        // unpack the real spectrum, power of the bins the filterbank reads
+        for (int k = lane; k < c.kmax; k += 32) {
+            float pw;
+            if (k == 256) {
+                const float x = a[0].x - a[0].y;
+                pw = x * x;
+            } else {
+                const float2 zk = a[k & 255];
+                const float2 zc = a[(256 - k) & 255];
+                const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+                const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);   // Zk - conj(Zc')
+                const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);  // -i/2 * dd
+                const float2 t2 = cmul(s_tw[k], xo);
+                const float re = xe.x + t2.x, im = xe.y + t2.y;
+                pw = re * re + im * im;
+            }
+            s_pow[warp][k] = pw;
+        }
+        __syncwarp();
+        float acc = 0.f;
+        for (int i = 0; i < my_len; ++i) acc = fmaf(s_pow[warp][my_start + i], my_w[i], acc);
+        const float db = 10.0f * logf(fmaxf(acc, 1e-10f)) / logf(10.0f);
+        vmax = fmaxf(vmax, db);
+        const int r = f - f0;
+        const int slot = p.out_rows_mask >= 0 ? ((row0 + r) & p.out_rows_mask) : r;
+        out[(int64_t)slot * OWW_MEL_BINS + lane] = db;
+        __syncwarp();
+    }
+    // per-call maximum -> clamp -> affine
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) s_red[warp] = vmax;
+    __syncthreads();
+    float m = s_red[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) m = fmaxf(m, s_red[w]);
+    const float floor_db = m - 80.0f;
+    const int nrows = T - f0;
+    for (int i = tid; i < nrows * OWW_MEL_BINS; i += kThreads) {
+        const int r = i >> 5, col = i & 31;
+        const int slot = p.out_rows_mask >= 0 ? ((row0 + r) & p.out_rows_mask) : r;
+        float* q = out + (int64_t)slot * OWW_MEL_BINS + col;
+        float v = fmaxf(__ldcg(q), floor_db);
+        if (p.affine) v = v / 10.0f + 2.0f;
+        *q = v;
+    }
+    if (streaming) {
+        __syncthreads();                       // every frame has read the old tail
+        int16_t* tw = p.tail + (int64_t)clip * OWW_TAIL;
+        for (int i = tid; i < OWW_TAIL; i += kThreads) tw[i] = __ldg(body + (p.n_body - OWW_TAIL + i));
+        if (tid == 0) {
+            p.out_count[clip] = row0 + nrows;
+            const int sn = p.seen[clip] + p.n_chunks;
+            p.seen[clip] = sn > (1 << 30) ? (1 << 30) : sn;
+        }
+    }
+}
+
+// ---- host-side constants (double precision), SURVEY.md Appendix A ---------------------------
+double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+}  // namespace
+
+int oww_mel_launch(oww_ctx* ctx, const MelLaunch& p, cudaStream_t s) {
+    if (!ctx->mel_loaded) return oww_fail(ctx, OWW_EINVAL, "mel constants not loaded");
+    const int prefix = p.tail ? OWW_TAIL : 0;
+    if (prefix + p.n_body < OWW_FFT_N) return oww_fail(ctx, OWW_EINVAL, "clip shorter than 512 samples");
+    if (p.n_clips <= 0) return OWW_OK;
+    MelDev c{ctx->d_window, ctx->d_twiddle, ctx->d_mel_start, ctx->d_mel_len, ctx->d_mel_w, ctx->mel_kmax};
+    mel_kernel<<<p.n_clips, kThreads, 0, s>>>(p, c);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+extern "C" int oww_load_mel(oww_ctx* ctx, const float* h_window512, const float* h_mel_fb) {
+    if (!ctx) return OWW_EINVAL;
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double kPi = 3.14159265358979323846;
+    std::vector<float> win(512, 0.f);
+    if (h_window512) {
+        std::memcpy(win.data(), h_window512, 512 * sizeof(float));
+    } else {
+        for (int n = 0; n < 400; ++n) win[56 + n] = (float)(0.5 - 0.5 * std::cos(2.0 * kPi * n / 400.0));
+    }
+    std::vector<float2> tw(512);
+    for (int k = 0; k < 512; ++k) {
+        const double a = -2.0 * kPi * k / 512.0;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    std::vector<float> fb(OWW_N_BINS * OWW_MEL_BINS);
+    if (h_mel_fb) {
+        std::memcpy(fb.data(), h_mel_fb, fb.size() * sizeof(float));
+    } else {
+        const int n_mels = OWW_MEL_BINS;
+        std::vector<double> mel_f(n_mels + 2);
+        const double m0 = hz_to_mel(60.0), m1 = hz_to_mel(3800.0);
+        for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(m0 + (m1 - m0) * i / (n_mels + 1));
+        for (int k = 0; k < OWW_N_BINS; ++k) {
+            const double ff = 8000.0 * k / 256.0;
+            for (int i = 0; i < n_mels; ++i) {
+                const double lower = (ff - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+                const double upper = (mel_f[i + 2] - ff) / (mel_f[i + 2] - mel_f[i + 1]);
+                double w = lower < upper ? lower : upper;
+                if (w < 0) w = 0;
+                w *= 2.0 / (mel_f[i + 2] - mel_f[i]);
+                fb[k * n_mels + i] = (float)w;
+            }
+        }
+    }
+    std::vector<int> st(OWW_MEL_BINS, 0), ln(OWW_MEL_BINS, 0);
+    std::vector<float> mw(OWW_MEL_BINS * OWW_MEL_MAXSUPPORT, 0.f);
+    int kmax = 0;
+    for (int i = 0; i < OWW_MEL_BINS; ++i) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < OWW_N_BINS; ++k)
+            if (fb[k * OWW_MEL_BINS + i] != 0.f) { if (lo < 0) lo = k; hi = k; }
+        if (lo < 0) { st[i] = 0; ln[i] = 0; continue; }
+        if (hi - lo + 1 > OWW_MEL_MAXSUPPORT)
+            return oww_fail(ctx, OWW_EUNSUPPORTED, "mel filter %d spans %d FFT bins (max %d)", i, hi - lo + 1,
+                            OWW_MEL_MAXSUPPORT);
+        st[i] = lo; ln[i] = hi - lo + 1;
+        for (int k = lo; k <= hi; ++k) mw[i * OWW_MEL_MAXSUPPORT + (k - lo)] = fb[k * OWW_MEL_BINS + i];
+        if (hi + 1 > kmax) kmax = hi + 1;
+    }
+    ctx->mel_kmax = kmax;
+    auto up = [&](void** d, const void* h, size_t bytes) -> cudaError_t {
+        if (!*d) { cudaError_t e = cudaMalloc(d, bytes); if (e != cudaSuccess) return e; }
+        return cudaMemcpy(*d, h, bytes, cudaMemcpyHostToDevice);
+    };
+    OWW_CUDA(ctx, up((void**)&ctx->d_window, win.data(), 512 * sizeof(float)));
+    OWW_CUDA(ctx, up((void**)&ctx->d_twiddle, tw.data(), 512 * sizeof(float2)));
+    OWW_CUDA(ctx, up((void**)&ctx->d_mel_start, st.data(), OWW_MEL_BINS * sizeof(int)));
+    OWW_CUDA(ctx, up((void**)&ctx->d_mel_len, ln.data(), OWW_MEL_BINS * sizeof(int)));
+    OWW_CUDA(ctx, up((void**)&ctx->d_mel_w, mw.data(), mw.size() * sizeof(float)));
+    ctx->mel_loaded = true;
+    return OWW_OK;
+}

@@ -1,0 +1,153 @@
+// Internal declarations shared by the .cu translation units of libowwb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "owwb200.h"
+
+#define OWW_N_CONV 20
+#define OWW_FFT_N 512
+#define OWW_N_BINS 257
+#define OWW_HOP 160
+#define OWW_TAIL 480
+#define OWW_MEL_MAXSUPPORT 32
+
+struct ConvLayer {
+    int kh, kw, cin, cout, pool_t, pool_f;
+    int t_in, f_in;      // input extent for the 76-row window
+    int t_out, f_out;    // conv output extent (before pool)
+    float* d_w;          // [kh*kw*cin][cout]
+    float* d_scale;      // [cout]
+    float* d_bias;       // [cout]
+};
+
+struct Head {
+    oww_head_desc desc;
+    int n_out;
+    int col0;            // first score column
+    float* d_blob;       // packed weights (layout of pack_head_blob)
+    std::vector<size_t> w_off, b_off, g_off, h_off;   // float offsets per layer
+};
+
+struct oww_ctx {
+    oww_config cfg;
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    uint64_t launches = 0;
+
+    // mel constants
+    bool mel_loaded = false;
+    float* d_window = nullptr;       // [512]
+    float2* d_twiddle = nullptr;     // [512] exp(-2 pi i k/512)
+    int* d_mel_start = nullptr;      // [32]
+    int* d_mel_len = nullptr;        // [32]
+    float* d_mel_w = nullptr;        // [32][OWW_MEL_MAXSUPPORT]
+    int mel_kmax = 0;                // highest FFT bin any filter touches (+1)
+
+    // embedding CNN
+    bool emb_loaded = false;
+    ConvLayer conv[OWW_N_CONV];
+    float* d_emb_blob = nullptr;
+
+    std::vector<Head> heads;
+    int n_out_total = 0;
+    int max_n_in = 0;
+
+    // streaming state
+    int n_streams = 0;
+    int mel_rows = 128;              // ring rows (power of two)
+    int feat_rows = 128;
+    int16_t* d_tail = nullptr;       // [B][480]
+    int* d_seen = nullptr;           // [B] chunks seen since reset (saturating)
+    int* d_mel_count = nullptr;      // [B] rows ever written (ring slot = count & (mel_rows-1))
+    int* d_feat_count = nullptr;     // [B]
+    float* d_mel_ring = nullptr;     // [B][mel_rows][32]
+    float* d_feat_ring = nullptr;    // [B][feat_rows][96]
+
+    // scratch for the window-mode CNN
+    int window_batch = 256;
+    float* d_act[2] = {nullptr, nullptr};
+    size_t act_floats = 0;           // per buffer
+    float* d_emb_tmp = nullptr;      // [max_chunks*B][96]
+    size_t emb_tmp_floats = 0;
+
+    // incremental-mode state
+    float* d_tails = nullptr;        // per-stream cached rows (layout in cnn_incremental.cu)
+    float* d_inc_act[2] = {nullptr, nullptr};
+    size_t inc_act_floats = 0;
+    int* d_inc_valid = nullptr;      // [B] 1 = tails hold a consistent pyramid
+
+    // host staging for oww_step_host
+    cudaStream_t own_stream = nullptr;
+    int16_t* h_pcm_pinned = nullptr; size_t h_pcm_bytes = 0;
+    int16_t* d_pcm_stage = nullptr;  size_t d_pcm_bytes = 0;
+    float* h_scores_pinned = nullptr; size_t h_scores_bytes = 0;
+    float* d_scores_stage = nullptr;  size_t d_scores_bytes = 0;
+
+    // stage timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;     // 4 events per slot; step k uses slot k % ev_slots
+    int ev_slots = 0;
+    long ev_steps = 0;               // timed steps recorded since timing was enabled
+
+    // private stream set for oww_predict_clips
+    oww_ctx* clip_ctx = nullptr;
+};
+
+int oww_fail(oww_ctx* ctx, int code, const char* fmt, ...);
+#define OWW_CUDA(ctx, call)                                                                    \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return oww_fail((ctx), OWW_ECUDA, "%s failed: %s (%s:%d)", #call,                  \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+#define OWW_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess)                                                                \
+            return oww_fail((ctx), OWW_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+    } while (0)
+
+// ---- mel.cu ----
+// Log-mel of n_clips virtual clips.  Clip c = [prefix (prefix_len samples, may be 0) | body (n_body samples)].
+// Streaming: prefix = d_tail row, out rows go to the mel ring at the stream's count; fresh streams
+// (seen==0) have no prefix and skip the frames that would touch it.
+struct MelLaunch {
+    const int16_t* body; int64_t body_stride; int n_body;
+    int16_t* tail;                 // [n_clips][480] or nullptr (stateless)
+    int* seen;                     // [n_clips] or nullptr
+    float* out; int64_t out_stride; int out_rows_mask;   // ring: mask = rows-1 ; linear: mask = -1
+    int* out_count;                // ring row counters or nullptr
+    int n_clips; int affine; int n_chunks;
+};
+int oww_mel_launch(oww_ctx* ctx, const MelLaunch& p, cudaStream_t s);
+
+// ---- cnn_fp32.cu ----
+// Window-mode embedding CNN on n windows.  Source of window j:
+//   stateless: src + j*76*32
+//   ring     : stream b = j % n_streams, chunk i = j / n_streams (i=0 oldest): rows
+//              [count[b] - 8*(n_chunks-1-i) - 76, +76) of the ring.
+struct WindowSrc {
+    const float* base; int64_t stride;  // per-window (or per-stream) stride in floats
+    const int* count; int rows_mask;    // ring addressing (count==nullptr -> linear)
+    int n_streams; int n_chunks;
+};
+int oww_cnn_window_fp32(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s);
+// Fully-convolutional pass over linear mel [n][T][32] -> [n][(T-76)/8+1][96].
+int oww_cnn_clip_fp32(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s);
+int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s);
+
+// ---- heads.cu ----
+struct FeatSrc {
+    const float* base; int64_t stride;   // per-sample stride in floats
+    const int* count; int rows_mask;     // ring addressing (nullptr -> linear [n][n_in][96])
+    int back;                            // ring: window ends `back` rows before the newest
+};
+int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float* d_out, int out_stride,
+                     int out_col0, int combine_max, cudaStream_t s);

@@ -1,0 +1,47 @@
+"""StreamEngine: the batched, dictionary-free face of the streaming hot path.
+
+``Model`` mirrors the reference's per-call dict API; the engine is what a serving loop (and
+bench.py) drives: B streams, one ``step`` = every stream consumes n_chunks*1280 samples and yields
+``float32[B, n_cols]`` raw head outputs.  ``step`` takes device-resident PCM (torch int16 tensor)
+and enqueues on the current CUDA stream with no synchronisation; ``step_host`` takes a host array
+and includes the H2D/D2H copies (pinned staging inside the library)."""
+import numpy as np
+
+from . import _native
+from . import weights as _weights
+from .utils import load_embedding_weights, _torch
+
+
+class StreamEngine:
+    def __init__(self, heads, n_streams, embedding="synthetic:0", feature_init=None, device_index=0,
+                 max_chunks=1, cnn_mode=_native.CNN_FP32_WINDOW, window_batch=0):
+        """heads: list of head dicts (weights.synthetic_head / load_head)."""
+        self.ctx = _native.Context(device=device_index, max_chunks=max_chunks, cnn_mode=cnn_mode,
+                                   window_batch=window_batch)
+        self.ctx.load_mel()
+        self.ctx.load_embedding(_weights.pack_embedding_blob(load_embedding_weights(embedding)))
+        for h in heads:
+            n_in, dims, ln, fin = _weights.head_desc(h)
+            self.ctx.add_head(n_in, dims, ln, fin, _weights.pack_head_blob(h))
+        self.n_streams = n_streams
+        self.n_cols = self.ctx.n_outputs
+        self.device_index = device_index
+        self.ctx.set_streams(n_streams)
+        self.reset(feature_init)
+
+    def reset(self, feature_init=None, stream_ids=None):
+        fi = np.zeros((41, 96), np.float32) if feature_init is None else feature_init
+        self.ctx.reset(stream_ids, fi)
+
+    def step(self, d_pcm, n_chunks=1, out=None):
+        torch = _torch()
+        if out is None:
+            out = torch.empty((self.n_streams, self.n_cols), dtype=torch.float32, device=d_pcm.device)
+        self.ctx.step(d_pcm, d_pcm.stride(0), n_chunks, out, torch.cuda.current_stream(d_pcm.device).cuda_stream)
+        return out
+
+    def step_host(self, pcm, n_chunks=1, out=None):
+        if out is None:
+            out = np.empty((self.n_streams, self.n_cols), np.float32)
+        self.ctx.step_host(pcm, n_chunks, out)
+        return out

@@ -1,0 +1,297 @@
+"""B200 mirror of the reference's ``openwakeword.utils`` surface for the inference hot path.
+
+``AudioFeatures`` keeps the reference's constructor / call / attribute surface
+(/root/reference/openwakeword/utils.py:33-463) but owns a libowwb200 ``Context``: the PCM tail,
+mel ring and embedding ring live in HBM and one ``__call__`` is one C-ABI step for every stream.
+``bulk_predict`` keeps the reference signature (utils.py:467-539) and runs clips through
+``oww_predict_clips`` with fresh state per clip.  Host code here only moves arguments, shapes and
+errors; all arithmetic is in the CUDA library.
+"""
+import functools
+import os
+import wave
+
+import numpy as np
+
+from . import _native
+from . import weights as _weights
+
+CHUNK = 1280
+_MODELS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "resources", "models")
+
+
+def re_arg(kwarg_map):
+    """Rename deprecated keyword arguments (same role as the reference's ``re_arg`` shim,
+    utils.py:677-688, used for ``wakeword_model_paths`` -> ``wakeword_models``)."""
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            renamed = {kwarg_map.get(k, k): v for k, v in kwargs.items()}
+            return fn(*args, **renamed)
+        return wrapped
+    return deco
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def load_embedding_weights(path):
+    """'' -> resources/models/embedding_model.npz ; 'synthetic[:seed]' -> seeded synthetic weights;
+    '*.npz' -> weights.load_embedding.  (.onnx ingestion: SURVEY.md Appendix E, next round.)"""
+    if isinstance(path, dict):
+        return path
+    if path.startswith("synthetic"):
+        seed = int(path.split(":")[1]) if ":" in path else 0
+        return _weights.synthetic_embedding(seed)
+    if path == "":
+        path = os.path.join(_MODELS_DIR, "embedding_model.npz")
+    if ".tflite" in path:
+        raise ValueError("The b200 inference framework is selected, but tflite models were provided!")
+    if not os.path.exists(path):
+        raise ValueError(
+            f"Embedding model file '{path}' not found. The reference's released weights are download-only; "
+            "convert them with openwakeword_b200.weights.save_embedding or pass embedding_model_path='synthetic:0'.")
+    return _weights.load_embedding(path)
+
+
+class AudioFeatures:
+    """PCM -> log-mel -> speech-embedding features, streaming and batch, on one B200.
+
+    Extra keywords over the reference: ``n_streams`` (independent audio streams packed on the batch
+    axis; 1 behaves exactly like the reference object), ``feature_init`` ([rows,96] initial content
+    of the embedding ring - the reference fills it from unseeded noise; default is
+    the embeddings of ``np.random.randint(-1000,1000,64000)`` computed on the GPU, as the reference
+    does), ``max_chunks`` (largest multiple of 1280 samples one call may carry), ``cnn_mode``.
+    """
+
+    def __init__(self, melspec_model_path="", embedding_model_path="", sr=16000, ncpu=1,
+                 inference_framework="b200", device="gpu", n_streams=1, feature_init=None,
+                 max_chunks=8, cnn_mode=_native.CNN_FP32_WINDOW, window_batch=0, device_index=0):
+        if inference_framework != "b200":
+            raise ValueError(f"openwakeword_b200 only provides inference_framework='b200' (got '{inference_framework}')")
+        if sr != 16000:
+            raise ValueError("only 16 kHz audio is supported")
+        self.ctx = _native.Context(device=device_index, max_chunks=max_chunks, cnn_mode=cnn_mode,
+                                   window_batch=window_batch)
+        if melspec_model_path not in ("", "builtin"):
+            z = np.load(melspec_model_path)
+            self.ctx.load_mel(z["window"], z["mel_fb"])
+        else:
+            self.ctx.load_mel()
+        self.embedding_weights = load_embedding_weights(embedding_model_path)
+        self.ctx.load_embedding(_weights.pack_embedding_blob(self.embedding_weights))
+        self.n_streams = int(n_streams)
+        self.max_chunks = max_chunks
+        self.device_index = device_index
+        self.onnx_execution_provider = "B200ExecutionProvider"
+        self.melspectrogram_max_len = 10 * 97
+        self.feature_buffer_max_len = 120
+        self._feature_init = None if feature_init is None else np.asarray(feature_init, np.float32)
+        self._streams_ready = False
+        # the three session callables of the reference (utils.py:87,93), numpy in / numpy out
+        self.melspec_model_predict = self._melspec_model_predict
+        self.embedding_model_predict = self._embedding_model_predict
+
+    # ---- lazily allocate the stream state (heads must be registered on ctx first) ----
+    def _ensure_streams(self):
+        if not self._streams_ready:
+            self.ctx.set_streams(self.n_streams)
+            self._streams_ready = True
+            self.reset()
+
+    def reset(self, feature_init=None, stream_ids=None):
+        """Reset buffers (utils.py:172-178).  ``feature_init`` overrides the ring content."""
+        if not self._streams_ready:
+            self.ctx.set_streams(self.n_streams)
+            self._streams_ready = True
+        fi = feature_init if feature_init is not None else self._feature_init
+        if fi is None:
+            noise = np.random.randint(-1000, 1000, 16000 * 4).astype(np.int16)
+            fi = self._get_embeddings(noise)
+        self.ctx.reset(stream_ids, np.asarray(fi, np.float32))
+        if stream_ids is None:
+            self._pending = np.zeros((self.n_streams, 0), np.int16)
+            self.accumulated_samples = 0
+
+    # ---- session-shaped calls ----
+    def _melspec_model_predict(self, x):
+        """float32/int16 [B,n] -> [array [B,1,T,32]] raw dB (what melspectrogram.onnx returns)."""
+        x = np.asarray(x)
+        x = x[None] if x.ndim == 1 else x
+        return [self._mel_device(x.astype(np.int16), affine=False).cpu().numpy()[:, None]]
+
+    def _embedding_model_predict(self, x):
+        """float32 [N,76,32,1] -> squeezed [N,96] ([96] for N=1), as utils.py:93."""
+        torch = _torch()
+        x = np.ascontiguousarray(np.asarray(x, np.float32).reshape(-1, 76, 32))
+        d = torch.from_numpy(x).to(f"cuda:{self.device_index}")
+        out = torch.empty((x.shape[0], 96), dtype=torch.float32, device=d.device)
+        self.ctx.embed_windows(d, x.shape[0], out, torch.cuda.current_stream(d.device).cuda_stream)
+        return out.cpu().numpy().squeeze()
+
+    def _mel_device(self, x_int16, affine=True):
+        torch = _torch()
+        x = np.ascontiguousarray(x_int16)
+        n, s = x.shape
+        if s < 512:
+            raise ValueError("The number of input frames must be at least 512 samples for the mel model")
+        d = torch.from_numpy(x).to(f"cuda:{self.device_index}")
+        T = (s - 512) // 160 + 1
+        out = torch.empty((n, T, 32), dtype=torch.float32, device=d.device)
+        self.ctx.melspectrogram(d, n, s, out, affine, torch.cuda.current_stream(d.device).cuda_stream)
+        return out
+
+    def _get_melspectrogram(self, x, melspec_transform=None):
+        """utils.py:180-208: int16 (or list) -> mel [T,32] (or [B,T,32]) after x/10+2."""
+        x = np.array(x).astype(np.int16) if isinstance(x, list) else np.asarray(x)
+        if x.dtype != np.int16:
+            raise ValueError("Input data must be 16-bit integers (i.e., 16-bit PCM audio)."
+                             f"You provided {x.dtype} data.")
+        x = x[None] if x.ndim < 2 else x
+        if melspec_transform is None:
+            return np.squeeze(self._mel_device(x, affine=True).cpu().numpy())
+        return melspec_transform(np.squeeze(self._mel_device(x, affine=False).cpu().numpy()))
+
+    def _get_embeddings_from_melspec(self, melspec):
+        melspec = np.asarray(melspec, np.float32)
+        if melspec.shape[0] != 1:
+            melspec = melspec[None]
+        return self._embedding_model_predict(melspec)
+
+    def _get_embeddings(self, x, window_size=76, step_size=8, **kwargs):
+        """utils.py:225-236: whole-clip mel, 76-row windows every 8 rows -> [W,96]."""
+        x = np.asarray(x)
+        if x.dtype != np.int16:
+            raise ValueError(f"Input data must be 16-bit integers. You provided {x.dtype} data.")
+        return self.embed_clips(x[None])[0]
+
+    def get_embedding_shape(self, audio_length, sr=16000):
+        n = int(audio_length * sr)
+        T = (n - 512) // 160 + 1
+        return ((T - 76) // 8 + 1, 96)
+
+    def _get_melspectrogram_batch(self, x, batch_size=128, ncpu=1):
+        return self._mel_device(np.asarray(x, np.int16), affine=True).cpu().numpy()
+
+    def _get_embeddings_batch(self, x, batch_size=128, ncpu=1):
+        x = np.asarray(x, np.float32)
+        if x.ndim == 4:
+            x = x[..., 0]
+        if x.shape[1] < 76:
+            raise ValueError("Embedding model requires the input melspectrograms to have at least 76 frames")
+        n_w = (x.shape[1] - 76) // 8 + 1
+        wins = np.stack([x[:, 8 * i:8 * i + 76] for i in range(n_w)], axis=1).reshape(-1, 76, 32)
+        return np.atleast_2d(self._embedding_model_predict(wins)).reshape(x.shape[0], n_w, 96)
+
+    def embed_clips(self, x, batch_size=128, ncpu=1):
+        """utils.py:358-385: int16 [N,samples] -> float32 [N,(T-76)//8+1,96]; one device call."""
+        torch = _torch()
+        x = np.ascontiguousarray(np.asarray(x))
+        if x.dtype != np.int16:
+            raise ValueError(f"Input data must be 16-bit integers. You provided {x.dtype} data.")
+        n, s = x.shape
+        T = (s - 512) // 160 + 1 if s >= 512 else 0
+        if T < 76:
+            raise ValueError("Embedding model requires the input melspectrograms to have at least 76 frames")
+        W = (T - 76) // 8 + 1
+        d = torch.from_numpy(x).to(f"cuda:{self.device_index}")
+        out = torch.empty((n, W, 96), dtype=torch.float32, device=d.device)
+        self.ctx.embed_clips(d, n, s, out, torch.cuda.current_stream(d.device).cuda_stream)
+        return out.cpu().numpy()
+
+    # ---- streaming ----
+    def _coerce(self, x):
+        x = np.asarray(x)
+        if x.dtype != np.int16:
+            x = x.astype(np.int16)          # the reference's list->int16 truncation (utils.py:194)
+        if x.ndim == 1:
+            x = x[None]
+        if x.shape[0] != self.n_streams:
+            raise ValueError(f"expected audio for {self.n_streams} stream(s), got {x.shape[0]}")
+        return x
+
+    def _streaming_features(self, x, scores_out=None):
+        """Chunk accumulation of utils.py:409-452, shared by all streams (same lengths).
+        Returns (n_prepared_samples, n_chunks_run).  Scores land in scores_out when a step ran."""
+        self._ensure_streams()
+        x = self._coerce(x)
+        buf = np.concatenate((self._pending, x), axis=1) if self._pending.shape[1] else x
+        total = buf.shape[1]
+        if total >= CHUNK:
+            rem = total % CHUNK
+            ready = buf[:, :total - rem]
+            self._pending = buf[:, total - rem:].copy()
+        else:
+            self._pending = buf.copy()
+            self.accumulated_samples = total
+            return total, 0
+        n_chunks = ready.shape[1] // CHUNK
+        if n_chunks > self.max_chunks:
+            raise ValueError(f"{ready.shape[1]} samples in one call exceeds max_chunks={self.max_chunks}*1280")
+        if scores_out is None:
+            scores_out = np.empty((self.n_streams, max(self.ctx.n_outputs, 1)), np.float32)
+        self.ctx.step_host(np.ascontiguousarray(ready), n_chunks, scores_out)
+        self.accumulated_samples = 0
+        self._last_scores = scores_out
+        return ready.shape[1], n_chunks
+
+    def __call__(self, x):
+        return self._streaming_features(x)[0]
+
+    def get_features(self, n_feature_frames=16, start_ndx=-1, stream=0):
+        """utils.py:454-460 on the device ring -> float32 [1,n,96]."""
+        self._ensure_streams()
+        n = int(n_feature_frames)
+        if start_ndx != -1:
+            if start_ndx >= 0:
+                raise ValueError("only negative start_ndx (relative to the newest row) is supported on the device ring")
+            back = -start_ndx - n
+            if back < 0:
+                n, back = -start_ndx, 0
+            return self.ctx.get_features(stream, n, back)[None]
+        return self.ctx.get_features(stream, n, 0)[None]
+
+    @property
+    def feature_buffer(self):
+        self._ensure_streams()
+        return self.ctx.get_features(0, 120, 0)
+
+    @property
+    def melspectrogram_buffer(self):
+        self._ensure_streams()
+        return self.ctx.get_mel(0, 76)
+
+
+def _read_wav(path):
+    with wave.open(path, mode="rb") as f:
+        if f.getframerate() != 16000 or f.getnchannels() != 1 or f.getsampwidth() != 2:
+            raise ValueError(f"{path}: expected 16-bit, 16 khz, single-channel WAV")
+        return np.frombuffer(f.readframes(f.getnframes()), dtype=np.int16)
+
+
+def bulk_predict(file_paths, wakeword_models, prediction_function="predict_clip", ncpu=1,
+                 inference_framework="b200", **kwargs):
+    """Reference signature (utils.py:467-539).  ``ncpu`` is accepted and ignored: clips are batched on
+    the GPU instead of forked across processes.  Each clip starts from a fresh state (the
+    reference bleeds state across the clips of one worker).  Returns {path: list of dicts}."""
+    from .model import Model
+    if prediction_function != "predict_clip":
+        raise ValueError("the b200 bulk path implements prediction_function='predict_clip'")
+    import inspect
+    init_names = set(inspect.signature(Model.__init__).parameters) | set(inspect.signature(AudioFeatures.__init__).parameters)
+    init_kw = {k: v for k, v in kwargs.items() if k in init_names}
+    clip_kw = {k: v for k, v in kwargs.items() if k not in init_names}
+    mdl = Model(wakeword_models=wakeword_models, inference_framework=inference_framework, **init_kw)
+    clips = [_read_wav(p) for p in file_paths]
+    out = {}
+    by_len = {}
+    for p, c in zip(file_paths, clips):
+        by_len.setdefault(c.shape[0], []).append(p)
+    lookup = dict(zip(file_paths, clips))
+    for _, paths in by_len.items():
+        res = mdl.predict_clips(np.stack([lookup[p] for p in paths]), **clip_kw)
+        for p, r in zip(paths, res):
+            out[p] = r
+    return out

@@ -1,0 +1,157 @@
+"""not-gpu tests: the C-ABI library loads and exports every symbol of include/owwb200.h; weight
+packing; registry; and the host-side Model logic driven through a fake (oracle-backed) context
+against the golden vectors made from the reference plumbing."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import openwakeword_b200 as owb
+from openwakeword_b200 import _native, weights as W, registry
+from openwakeword_b200.utils import re_arg
+from helpers import emb_weights, head, class_mapping, golden_cases, load_case, TIMER_MAP
+import fake_backend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    hdr = open(os.path.join(ROOT, "include", "owwb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(oww_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no prototypes found"
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert b"sm_100a" in built_library.oww_version()
+
+
+def test_create_fails_loudly_without_gpu(built_library):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeError):
+        _native.Context()
+    with pytest.raises(_native.NativeError):      # no silent CPU fallback behind the public API either
+        owb.Model(wakeword_models=[{"name": "a", "head": head("alexa_v0.1")}], embedding_model_path="synthetic:0")
+
+
+def test_embedding_blob_layout_and_param_count():
+    w = emb_weights()
+    n_conv = sum(a.size for a in w["conv"])
+    n_bn = sum(4 * p[0].size for p in w["bn"])
+    assert n_conv == 326808 and n_conv + n_bn == W.N_EMBEDDING_PARAMS        # nb/conv:859
+    blob = W.pack_embedding_blob(w)
+    assert blob.dtype == np.float32 and blob.size == n_conv + 2 * sum(l[3] for l in W.EMBEDDING_LAYERS)
+    back = fake_backend.unpack_embedding_blob(blob)
+    from oracle import embedding
+    x = np.random.default_rng(0).normal(8, 2, (2, 76, 32)).astype(np.float32)
+    np.testing.assert_allclose(embedding.embed_windows(back, x), embedding.embed_windows(w, x), atol=1e-4)
+
+
+def test_head_blob_roundtrip(tmp_path):
+    for name in ("alexa_v0.1", "timer_v0.1", "big_v0.1"):
+        h = head(name)
+        n_in, dims, ln, fin = W.head_desc(h)
+        assert dims[0] == n_in * 96
+        back = fake_backend.unpack_head_blob(n_in, dims, ln, fin, W.pack_head_blob(h))
+        from oracle import heads
+        f = np.random.default_rng(1).normal(0, 1, (3, n_in, 96)).astype(np.float32)
+        np.testing.assert_array_equal(heads.forward(back, f), heads.forward(h, f))
+        p = str(tmp_path / (name + ".npz"))
+        W.save_head(p, h, TIMER_MAP if name.startswith("timer") else None)
+        h2, cm = W.load_head(p)
+        np.testing.assert_array_equal(heads.forward(h2, f), heads.forward(h, f))
+        assert (cm == TIMER_MAP) if name.startswith("timer") else cm is None
+
+
+def test_registry_matches_reference_names():
+    assert list(registry.MODELS) == ["alexa", "hey_mycroft", "hey_jarvis", "hey_rhasspy", "timer", "weather"]
+    assert registry.model_class_mappings["timer"]["6"] == "1_hour_timer"
+    assert len(owb.get_pretrained_model_paths()) == 6
+
+
+def test_re_arg():
+    @re_arg({"old": "new"})
+    def f(new=1):
+        return new
+    assert f(old=5) == 5 and f(new=6) == 6
+
+
+@pytest.fixture
+def fake_ctx(monkeypatch):
+    monkeypatch.setattr(_native, "Context", fake_backend.FakeContext)
+    yield
+
+
+def _model(c, **kw):
+    specs = [{"name": n, "head": head(n), "class_mapping": class_mapping([n]).get(n)} for n in c["names"]]
+    return owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(int(c["emb_seed"])),
+                     feature_init=c["feature_init"], max_chunks=8, **kw)
+
+
+@pytest.mark.parametrize("tag", golden_cases("predict_clip"))
+def test_model_host_logic_on_golden(fake_ctx, tag):
+    c = load_case(tag)
+    m = _model(c)
+    res = m.predict_clip(c["pcm"], padding=int(c["padding"]), chunk_size=int(c["chunk"]), **c["kw"])
+    assert list(res[0].keys()) == c["labels"]
+    got = np.array([[r[l] for l in c["labels"]] for r in res], dtype=np.float32)
+    np.testing.assert_allclose(got, c["scores"], atol=1e-5)
+
+
+def test_model_stream_mixed(fake_ctx):
+    c = load_case("stream_mixed")
+    c["emb_seed"] = 0
+    m = _model(c)
+    pos, rows = 0, []
+    for n in c["lens"]:
+        r = m.predict(c["pcm"][pos:pos + n])
+        pos += n
+        rows.append([r[l] for l in c["labels"]])
+    np.testing.assert_allclose(np.array(rows, np.float32), c["scores"], atol=1e-5)
+    np.testing.assert_allclose(m.preprocessor.melspectrogram_buffer, c["mel_tail"], atol=1e-4)
+    np.testing.assert_allclose(m.preprocessor.get_features(34)[0], c["feat_tail"], atol=1e-4)
+    assert len(m.prediction_buffer[c["labels"][0]]) == len(c["lens"])
+
+
+def test_model_errors_match_reference(fake_ctx):
+    c = load_case("alexa_c1280")
+    m = _model(c)
+    with pytest.raises(ValueError):
+        m.predict([0] * 1280)                                  # model.py:262-263
+    with pytest.raises(ValueError):
+        m.predict(np.zeros(1280), patience={"alexa_v0.1": 3})   # model.py:341-343
+    with pytest.raises(ValueError):
+        m.predict(np.zeros(1280, np.int16), patience={"alexa_v0.1": 3}, threshold={"alexa_v0.1": 0.5}, debounce_time=1.0)
+    with pytest.raises(ValueError):
+        owb.Model(wakeword_models=["no such model"], embedding_model_path="synthetic:0")   # model.py:96-97
+    with pytest.raises(ValueError):
+        owb.Model(wakeword_models=[{"name": "a", "head": head("alexa_v0.1")}], inference_framework="onnx")
+    with pytest.raises(ValueError):
+        m.preprocessor._get_melspectrogram(np.zeros(1280, np.float32))     # utils.py:195-197
+    r = m.predict(np.zeros(1280))                              # float64 zeros accepted (tests/test_models.py:302-316)
+    assert set(r) == {"alexa_v0.1"}
+    r, t = m.predict(np.zeros(1280, np.int16), timing=True)
+    assert "preprocessor" in t["models"] and "alexa_v0.1" in t["models"]
+    assert m.get_parent_model_from_label("alexa_v0.1") == "alexa_v0.1"
+
+
+def test_multi_stream_batch_equals_singles(fake_ctx):
+    rng = np.random.default_rng(0)
+    names = ["alexa_v0.1", "timer_v0.1"]
+    specs = [{"name": n, "head": head(n), "class_mapping": class_mapping([n]).get(n)} for n in names]
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    pcm = rng.integers(-3000, 3000, (3, 1280 * 7)).astype(np.int16)
+    mb = owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(), feature_init=fi, n_streams=3)
+    singles = [owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(), feature_init=fi) for _ in range(3)]
+    for s in range(7):
+        rb = mb.predict(pcm[:, s * 1280:(s + 1) * 1280])
+        for b in range(3):
+            r1 = singles[b].predict(pcm[b, s * 1280:(s + 1) * 1280])
+            for k in r1:
+                assert abs(r1[k] - rb[k][b]) < 1e-6
+    assert "1_hour_timer" in rb and rb["alexa_v0.1"].shape == (3,)
