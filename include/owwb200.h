@@ -134,6 +134,12 @@ int oww_embed_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sampl
 int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, int pad_samples,
                       const float* h_feature_init, int n_rows, float* d_scores, void* stream);
 
+/* ---- parity instrumentation --------------------------------------------------------------- */
+/* Runs the embedding CNN on d_windows [n][76][32] (n <= window_batch) up to and including conv
+ * layer `layer` (0..18) and its max-pool, and writes that activation as NHWC float32
+ * [n][T][F][C] to d_out - used by the tests to localise a mismatch layer by layer.             */
+int oww_debug_layer(oww_ctx* ctx, const float* d_windows, int n, int layer, float* d_out, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 uint64_t oww_launch_count(const oww_ctx* ctx);       /* kernels launched by this handle so far   */
 /* n_slots > 0: every following oww_step / oww_step_host brackets its three stages (mel, embedding

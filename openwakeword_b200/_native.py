@@ -52,6 +52,7 @@ _SIGNATURES = {
     "oww_get_mel": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "oww_embed_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "oww_predict_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
+    "oww_debug_layer": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "oww_launch_count": (C.c_uint64, [_P]),
     "oww_enable_stage_timing": (C.c_int, [_P, C.c_int]),
     "oww_stage_ms": (C.c_int, [_P, _P]),
@@ -204,6 +205,9 @@ class Context:
         fi = None if feature_init is None else np.ascontiguousarray(feature_init, np.float32)
         self._check(self.lib.oww_predict_clips(self.h, _ptr(d_pcm), n_clips, n_samples, pad_samples, _ptr(fi),
                                                41 if fi is None else fi.shape[0], _ptr(d_scores), stream))
+
+    def debug_layer(self, d_windows, n, layer, d_out, stream=None):
+        self._check(self.lib.oww_debug_layer(self.h, _ptr(d_windows), n, layer, _ptr(d_out), stream))
 
     # ---- introspection ----
     def enable_stage_timing(self, n_slots=1):

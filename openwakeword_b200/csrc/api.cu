@@ -76,6 +76,18 @@ void free_streams(oww_ctx* c) {
 }
 
 int ensure_act(oww_ctx* ctx, size_t floats) {
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW) {
+        const size_t units = oww_tc_act_units(ctx, ctx->window_batch);
+        if (ctx->tc_act_units < units) {
+            cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]);
+            ctx->d_tc_act[0] = ctx->d_tc_act[1] = nullptr; ctx->tc_act_units = 0;
+            for (int i = 0; i < 2; ++i) {
+                OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_act[i], units * 16));
+                OWW_CUDA(ctx, cudaMemset(ctx->d_tc_act[i], 0, units * 16));
+            }
+            ctx->tc_act_units = units;
+        }
+    }
     if (ctx->act_floats >= floats) return OWW_OK;
     cudaFree(ctx->d_act[0]); cudaFree(ctx->d_act[1]);
     ctx->d_act[0] = ctx->d_act[1] = nullptr; ctx->act_floats = 0;
@@ -108,7 +120,7 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
     if ((rc = oww_mel_launch(ctx, m, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
     WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, B, n_chunks};
-    if ((rc = oww_cnn_window_fp32(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s))) return rc;
+    if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s))) return rc;
     if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, n_chunks, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
     for (int i = n_chunks - 1; i >= 0; --i) {
@@ -135,14 +147,14 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     if (e != cudaSuccess || ndev == 0)
         return oww_fail(nullptr, OWW_ECUDA, "no CUDA device: %s", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return oww_fail(nullptr, OWW_EINVAL, "device %d out of range", cfg->device);
-    if (cfg->cnn_mode != OWW_CNN_FP32_WINDOW)
+    if (cfg->cnn_mode != OWW_CNN_FP32_WINDOW && cfg->cnn_mode != OWW_CNN_TC_WINDOW)
         return oww_fail(nullptr, OWW_EUNSUPPORTED, "cnn_mode %d not built in this version", cfg->cnn_mode);
     oww_ctx* ctx = new (std::nothrow) oww_ctx();
     if (!ctx) return oww_fail(nullptr, OWW_ENOMEM, "out of host memory");
     ctx->cfg = *cfg;
     if (ctx->cfg.max_chunks < 1) ctx->cfg.max_chunks = 1;
     ctx->device = cfg->device;
-    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : 512;
+    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : (cfg->cnn_mode == OWW_CNN_TC_WINDOW ? 256 : 512);
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) {
         oww_fail(nullptr, OWW_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
         delete ctx; return OWW_ECUDA;
@@ -170,10 +182,12 @@ void oww_destroy(oww_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->clip_ctx) { oww_ctx* c = ctx->clip_ctx; ctx->clip_ctx = nullptr; free_streams(c);
         cudaStreamDestroy(c->own_stream);
+        cudaFree(c->d_tc_act[0]); cudaFree(c->d_tc_act[1]);
         cudaFree(c->d_pcm_stage); delete c; }
     free_streams(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
-    cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob);
+    cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
+    cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]);
     for (auto& h : ctx->heads) cudaFree(h.d_blob);
     cudaFreeHost(ctx->h_pcm_pinned); cudaFreeHost(ctx->h_scores_pinned);
     cudaFree(ctx->d_pcm_stage); cudaFree(ctx->d_scores_stage);
@@ -202,7 +216,7 @@ int oww_load_embedding(oww_ctx* ctx, const float* h_blob, size_t n_floats) {
         L.d_bias = ctx->d_emb_blob + off; off += L.cout;
     }
     ctx->emb_loaded = true;
-    return OWW_OK;
+    return oww_tc_pack_weights(ctx, h_blob);
 }
 
 int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, size_t n_floats, int* head_id) {
@@ -260,7 +274,7 @@ int oww_embed_windows(oww_ctx* ctx, const float* d_windows, int n, float* d_emb,
     int rc = ensure_act(ctx, (size_t)std::min(n, ctx->window_batch) * 74 * 32 * 24);
     if (rc) return rc;
     WindowSrc src{d_windows, (int64_t)OWW_WINDOW_ROWS * 32, nullptr, -1, 0, 0};
-    return oww_cnn_window_fp32(ctx, src, n, d_emb, (cudaStream_t)stream);
+    return oww_cnn_window(ctx, src, n, d_emb, (cudaStream_t)stream);
 }
 
 int oww_head_predict(oww_ctx* ctx, int head_id, const float* d_feats, int n, float* d_out, void* stream) {
@@ -454,7 +468,8 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     c->mel_loaded = ctx->mel_loaded; c->d_window = ctx->d_window; c->d_twiddle = ctx->d_twiddle;
     c->d_mel_start = ctx->d_mel_start; c->d_mel_len = ctx->d_mel_len; c->d_mel_w = ctx->d_mel_w; c->mel_kmax = ctx->mel_kmax;
     c->emb_loaded = ctx->emb_loaded;
-    for (int li = 0; li < OWW_N_CONV; ++li) c->conv[li] = ctx->conv[li];
+    for (int li = 0; li < OWW_N_CONV; ++li) { c->conv[li] = ctx->conv[li]; c->tc_w_off[li] = ctx->tc_w_off[li]; c->tc_sb_off[li] = ctx->tc_sb_off[li]; }
+    c->d_tc_w = ctx->d_tc_w; c->d_tc_sb = ctx->d_tc_sb;
     c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in;
     int rc = OWW_OK;
     for (int c0 = 0; c0 < n_clips && rc == OWW_OK; c0 += slab_max) {
@@ -479,6 +494,18 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     ctx->launches += c->launches; c->launches = 0;
     c->heads.clear();   // do not let the child free shared blobs
     return rc;
+}
+
+int oww_debug_layer(oww_ctx* ctx, const float* d_windows, int n, int layer, float* d_out, void* stream) {
+    if (!ctx || !d_windows || !d_out) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (layer < 0 || layer >= OWW_N_CONV - 1) return oww_fail(ctx, OWW_EINVAL, "layer must be in [0,18]");
+    if (n < 1 || n > ctx->window_batch) return oww_fail(ctx, OWW_EINVAL, "n must be in [1, window_batch]");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_act(ctx, (size_t)std::min(n, ctx->window_batch) * 74 * 32 * 24);
+    if (rc) return rc;
+    WindowSrc src{d_windows, (int64_t)OWW_WINDOW_ROWS * 32, nullptr, -1, 0, 0};
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW) return oww_cnn_tc_pyramid(ctx, src, n, nullptr, layer, d_out, (cudaStream_t)stream);
+    return oww_cnn_fp32_pyramid(ctx, src, n, nullptr, layer, d_out, (cudaStream_t)stream);
 }
 
 int oww_enable_stage_timing(oww_ctx* ctx, int n_slots) {

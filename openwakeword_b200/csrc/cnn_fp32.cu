@@ -281,7 +281,8 @@ int dispatch_conv(oww_ctx* ctx, const ConvLayer& L, const ConvArgs& a, cudaStrea
 }
 
 // Runs layers 0..19 on n samples whose mel source has t_mel rows; result [n][W][96] in d_out.
-int run_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, int t_mel, float* d_out, cudaStream_t s) {
+int run_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, int t_mel, float* d_out, cudaStream_t s, int stop_layer = -1,
+                float* d_dbg = nullptr) {
     float* bufs[2] = {ctx->d_act[0], ctx->d_act[1]};
     int cur = 0;
     int t = t_mel, f = 32;
@@ -319,13 +320,21 @@ int run_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, int t_mel, float* d_o
             OWW_LAUNCH_CHECK(ctx);
             t = t2; f = f2; stride_in = so; cur ^= 1;
         }
+        if (li == stop_layer && !last) {
+            OWW_CUDA(ctx, cudaMemcpyAsync(d_dbg, bufs[cur ^ 1], (size_t)n * stride_in * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            return OWW_OK;
+        }
     }
     return OWW_OK;
 }
 
 }  // namespace
 
-int oww_cnn_window_fp32(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s) {
+int oww_cnn_fp32_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s) {
+    return run_pyramid(ctx, src, n, OWW_WINDOW_ROWS, d_emb, s, stop_layer, d_dbg);
+}
+
+int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s) {
     if (!ctx->emb_loaded) return oww_fail(ctx, OWW_EINVAL, "embedding weights not loaded");
     const int wb = ctx->window_batch;
     int w0 = 0;
@@ -348,7 +357,9 @@ int oww_cnn_window_fp32(oww_ctx* ctx, const WindowSrc& src, int n_windows, float
         } else {
             sub.base = src.base + (int64_t)w0 * src.stride;
         }
-        int rc = run_pyramid(ctx, sub, n, OWW_WINDOW_ROWS, d_emb + (int64_t)w0 * OWW_EMBEDDING_DIM, s);
+        float* o = d_emb + (int64_t)w0 * OWW_EMBEDDING_DIM;
+        int rc = ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW ? oww_cnn_tc_pyramid(ctx, sub, n, o, -1, nullptr, s)
+                                                       : run_pyramid(ctx, sub, n, OWW_WINDOW_ROWS, o, s);
         if (rc) return rc;
         w0 += n;
     }

@@ -1,0 +1,542 @@
+// K2 (tensor-core path): the speech-embedding CNN as tcgen05 implicit GEMMs for sm_100a.
+//
+// Same graph as cnn_fp32.cu (reference: embedding_model.onnx, /root/reference/openwakeword/utils.py:90-93;
+// spec notebooks/converting_google_speech_embedding_model.ipynb:871-951).  Layers 1..19 are dense
+// (1,3)/(3,1) convolutions: M = output positions, N = Cout, K = 3 taps x Cin.
+//
+// Layout.  Activations live in HBM/L2 as fp16 "channel-group planes": plane g holds channels
+// 8g..8g+7 of every position as one 16-byte unit, positions ordered (window, t, f) with ONE zero pad
+// column per row (f = W), i.e. exactly the canonical no-swizzle K-major UMMA core-matrix order
+// (8 consecutive positions x 16 B = one 8x8 core matrix, SBO = 128 B, LBO = plane pitch).  Hence
+//   * an A tile (128 positions + halo, all planes) is CG contiguous runs -> CG 1-D bulk copies
+//     (cp.async.bulk, mbarrier complete_tx), no im2col, no tensor map;
+//   * a conv tap is just a 16-byte-granular shift of the A descriptor's start address:
+//     (1,3) taps shift by -1/0/+1 positions (the pad column supplies the "same" zeros),
+//     (3,1) taps shift by 0/Wp/2Wp positions; one smem tile feeds all three taps.
+// Weights are pre-packed per layer as fp16 [tap][plane][n][8] (same core-matrix order, K-major B).
+// D accumulates in TMEM (fp32, 128 lanes x N columns, two stages); the epilogue warps read their
+// lane quarter with tcgen05.ld, apply folded BN + leaky + clamp in fp32 and write the next layer's
+// fp16 planes directly (16-byte coalesced stores).  Warp roles: 0 = bulk-copy producer,
+// 1 = TMEM allocator + single-thread MMA issuer, 2..5 = epilogue.  Persistent CTAs, grid = #SMs.
+#include "oww_internal.h"
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr float kLeak = 0.20000000298023224f;
+constexpr float kFloor = -0.4000000059604645f;
+constexpr int kGuard = 8;          // 16-byte units of zero guard in front of every plane
+constexpr int kGuardBack = 384;    // readable units behind the last position
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;
+constexpr int kTcThreads = 192;
+
+__device__ __forceinline__ float act(float v) {
+    v = fmaxf(kLeak * v, v);
+    return fmaxf(v, kFloor);
+}
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 26)) { printf("owwb200: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// ---------------------------------------------------------------- layer 0 (CUDA cores) -> fp16 planes
+struct Tc0Args {
+    WindowSrc src;
+    int n_windows;
+    const float* w; const float* scale; const float* bias;
+    __half* out; int64_t plane;       // units per plane
+};
+
+__global__ void __launch_bounds__(256) tc_conv0_kernel(Tc0Args a) {
+    __shared__ float s_w[9 * 24];
+    __shared__ float s_s[24], s_b[24];
+    for (int i = threadIdx.x; i < 9 * 24; i += 256) s_w[i] = a.w[i];
+    if (threadIdx.x < 24) { s_s[threadIdx.x] = a.scale[threadIdx.x]; s_b[threadIdx.x] = a.bias[threadIdx.x]; }
+    __syncthreads();
+    constexpr int T = 74, Wp = 33;
+    const int64_t total = (int64_t)a.n_windows * T * Wp;
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
+        const int f = (int)(p % Wp);
+        const int64_t r = p / Wp;
+        const int t = (int)(r % T);
+        const int j = (int)(r / T);
+        uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + p;
+        if (p == 0) { const uint4 z = make_uint4(0, 0, 0, 0); o[-1] = z; o[a.plane - 1] = z; o[2 * a.plane - 1] = z; }
+        if (f == 32) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            o[0] = z; o[a.plane] = z; o[2 * a.plane] = z;
+            continue;
+        }
+        const float* base; int row0, mask;
+        if (a.src.count) {
+            const int b = j % a.src.n_streams, i = j / a.src.n_streams;
+            base = a.src.base + (int64_t)b * a.src.stride;
+            row0 = a.src.count[b] - 8 * (a.src.n_chunks - 1 - i) - OWW_WINDOW_ROWS;
+            mask = a.src.rows_mask;
+        } else {
+            base = a.src.base + (int64_t)j * a.src.stride; row0 = 0; mask = -1;
+        }
+        float x[9];
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+            int row = row0 + t + dt;
+            if (mask >= 0) row &= mask;
+            const float* rp = base + (int64_t)row * 32;
+#pragma unroll
+            for (int df = 0; df < 3; ++df) {
+                const int ff = f + df - 1;
+                x[dt * 3 + df] = (ff >= 0 && ff < 32) ? __ldg(rp + ff) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            __half2 h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float v2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = g * 8 + u * 2 + e;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acc = fmaf(x[k], s_w[k * 24 + c], acc);
+                    acc = fmaxf(acc, 0.f);
+                    v2[e] = act(fmaf(acc, s_s[c], s_b[c]));
+                }
+                h[u] = __floats2half2_rn(v2[0], v2[1]);
+            }
+            o[g * a.plane] = *reinterpret_cast<uint4*>(h);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- tcgen05 conv layer
+struct TcConvArgs {
+    const __half* in; int64_t in_plane;     // units (16 B) per input plane, guard included
+    __half* out; int64_t out_plane;
+    float* out_f32;                         // final layer: [n][96] fp32 instead of planes
+    const __half* w;                        // packed [3][CGP][NP][8]
+    const float* scale; const float* bias;  // [NP]
+    int n, T, W, T_out;                     // input extent per window, W excludes the pad column
+    int tap_off[3];                         // tile-row offset of each tap
+    int lo;                                 // tile starts `lo` positions before its first output
+    int rows;                               // tile rows incl. halo (multiple of 8)
+    int cg_in;                              // real input planes
+    int cg_out;                             // real output planes (Cout/8)
+    int apply_act;
+    int64_t p_in;                           // n*T*(W+1)
+    int n_tiles;
+};
+
+template <int CGP, int NP>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int W_BYTES = 3 * CGP * NP * 16;
+    uint8_t* w_smem = smem;
+    const int stage_bytes = CGP * a.rows * 16;
+    uint8_t* a_smem = smem + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + kStages * stage_bytes);
+    // bars: [0..S) full, [S..2S) empty, [2S..2S+A) tmem_full, [..+A) tmem_empty, then w_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + kAccStages + s); };
+    const uint32_t wfull_bar = bar0 + 8u * (2 * kStages + 2 * kAccStages);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        mbar_init(wfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // zero the pad planes of every A stage once (never overwritten by the bulk copies)
+    if (a.cg_in < CGP) {
+        for (int s = 0; s < kStages; ++s) {
+            uint4* pz = reinterpret_cast<uint4*>(a_smem + s * stage_bytes + a.cg_in * a.rows * 16);
+            for (int i = threadIdx.x; i < (CGP - a.cg_in) * a.rows; i += kTcThreads) pz[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: weights once, then one A tile per stage =====================
+        if (lane == 0) {
+            mbar_expect_tx(wfull_bar, W_BYTES);
+            bulk_g2s(smem_u32(w_smem), a.w, W_BYTES, wfull_bar);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t plane_bytes = (uint32_t)a.rows * 16u;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                mbar_expect_tx(full_bar(stage), plane_bytes * a.cg_in);
+                const int64_t u0 = kGuard + (int64_t)tile * 128 - a.lo;
+                for (int g = 0; g < a.cg_in; ++g)
+                    bulk_g2s(smem_u32(a_smem + stage * stage_bytes + g * plane_bytes),
+                             reinterpret_cast<const uint4*>(a.in) + g * a.in_plane + u0, plane_bytes, full_bar(stage));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            mbar_wait(wfull_bar, 0);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t w_addr = smem_u32(w_smem);
+            const uint32_t lbo_a = (uint32_t)a.rows * 16u;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(a_smem + stage * stage_bytes);
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+                uint32_t accumulate = 0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                    for (int q = 0; q < CGP / 2; ++q) {
+                        const uint64_t ad = make_desc(a_addr + (uint32_t)(2 * q * a.rows + a.tap_off[j]) * 16u, lbo_a, 128u);
+                        const uint64_t bd = make_desc(w_addr + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
+                        tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                tc_commit(empty_bar(stage));
+                tc_commit(tfull_bar(acc));
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: 4 warps, one TMEM lane quarter each =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int Wp = a.W + 1;
+        const int per_in = a.T * Wp;
+        const int per_out = a.T_out * Wp;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            uint32_t v[NP];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u;
+#pragma unroll
+            for (int c = 0; c < NP; c += 16) tmem_ld16(taddr + c, v + c);
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+
+            const int64_t m = (int64_t)tile * 128 + row;
+            if (m >= a.p_in) continue;
+            const int n = (int)(m / per_in);
+            const int rem = (int)(m - (int64_t)n * per_in);
+            const int t = rem / Wp, f = rem - t * Wp;
+            if (t >= a.T_out) continue;
+            if (a.out_f32) {
+                if (f != 0) continue;
+                float* o = a.out_f32 + (int64_t)n * 96;
+#pragma unroll
+                for (int c = 0; c < 96 && c < NP; c += 4) {
+                    float4 r4;
+                    r4.x = fmaf(__uint_as_float(v[c + 0]), __ldg(a.scale + c + 0), __ldg(a.bias + c + 0));
+                    r4.y = fmaf(__uint_as_float(v[c + 1]), __ldg(a.scale + c + 1), __ldg(a.bias + c + 1));
+                    r4.z = fmaf(__uint_as_float(v[c + 2]), __ldg(a.scale + c + 2), __ldg(a.bias + c + 2));
+                    r4.w = fmaf(__uint_as_float(v[c + 3]), __ldg(a.scale + c + 3), __ldg(a.bias + c + 3));
+                    reinterpret_cast<float4*>(o)[c >> 2] = r4;
+                }
+                continue;
+            }
+            const int64_t po = (int64_t)n * per_out + (int64_t)t * Wp + f;
+            uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + po;
+            const bool pad = f == a.W;
+#pragma unroll
+            for (int g = 0; g < NP / 8; ++g) {
+                __half2 h[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = g * 8 + u * 2;
+                    float y0 = fmaf(__uint_as_float(v[c]), __ldg(a.scale + c), __ldg(a.bias + c));
+                    float y1 = fmaf(__uint_as_float(v[c + 1]), __ldg(a.scale + c + 1), __ldg(a.bias + c + 1));
+                    if (a.apply_act) { y0 = act(y0); y1 = act(y1); }
+                    h[u] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(y0, y1);
+                }
+                if (g < a.cg_out) {
+                    o[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
+                    if (po == 0) o[(int64_t)g * a.out_plane - 1] = make_uint4(0, 0, 0, 0);   // front guard (position -1)
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
+// ---------------------------------------------------------------- max-pool on fp16 planes
+__global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t in_plane, __half* out, int64_t out_plane,
+                                                      int n, int t_in, int w_in, int cg, int pt, int pf) {
+    const int t_out = t_in / pt, w_out = w_in / pf;
+    const int wp_in = w_in + 1, wp_out = w_out + 1;
+    const int64_t per_out = (int64_t)t_out * wp_out;
+    const int64_t total = (int64_t)n * per_out * cg;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t p = i % ((int64_t)n * per_out);
+        const int g = (int)(i / ((int64_t)n * per_out));
+        const int f = (int)(p % wp_out);
+        const int64_t r = p / wp_out;
+        const int t = (int)(r % t_out);
+        const int64_t s = r / t_out;
+        uint4 res = make_uint4(0, 0, 0, 0);
+        if (f < w_out) {
+            __half2 m[4];
+            bool first = true;
+            for (int da = 0; da < pt; ++da)
+                for (int db = 0; db < pf; ++db) {
+                    const int64_t pi = s * (int64_t)t_in * wp_in + (int64_t)(t * pt + da) * wp_in + (f * pf + db);
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + (int64_t)g * in_plane + kGuard + pi);
+                    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) m[u] = first ? hv[u] : __hmax2(m[u], hv[u]);
+                    first = false;
+                }
+            res = *reinterpret_cast<uint4*>(m);
+        }
+        reinterpret_cast<uint4*>(out)[(int64_t)g * out_plane + kGuard + p] = res;
+        if (p == 0) reinterpret_cast<uint4*>(out)[(int64_t)g * out_plane + kGuard - 1] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// planes -> NHWC fp32 (debug / parity only)
+__global__ void tc_unpack_kernel(const __half* in, int64_t plane, float* out, int n, int t, int w, int c) {
+    const int wp = w + 1;
+    const int64_t total = (int64_t)n * t * w * c;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        int64_t r = i / c;
+        const int f = (int)(r % w); r /= w;
+        const int tt = (int)(r % t);
+        const int64_t s = r / t;
+        const int64_t p = s * (int64_t)t * wp + (int64_t)tt * wp + f;
+        out[i] = __half2float(in[((int64_t)(ch >> 3) * plane + kGuard + p) * 8 + (ch & 7)]);
+    }
+}
+
+struct TcLayerGeom { int T, W, cg, cgp, np, T_out, rows, lo, tap_off[3]; };
+
+inline int round8(int v) { return (v + 7) & ~7; }
+
+template <int CGP, int NP>
+int launch_tc(oww_ctx* ctx, const TcConvArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)3 * CGP * NP * 16 + (size_t)kStages * CGP * a.rows * 16 + 8 * (2 * kStages + 2 * kAccStages + 1) + 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        OWW_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<CGP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
+    tc_conv_kernel<CGP, NP><<<grid, kTcThreads, smem, s>>>(a);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+}  // namespace
+
+// Host-side packing: fp16 weights [3][CGP][NP][8] + padded scale/bias per layer 1..19.
+int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob) {
+    size_t off = 0, total_h = 0, total_f = 0;
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        const ConvLayer& L = ctx->conv[li];
+        if (li > 0) {
+            const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
+            total_h += (size_t)3 * cgp * np * 8;
+            total_f += 2 * (size_t)np;
+        }
+    }
+    std::vector<__half> hw(total_h);
+    std::vector<float> hf(total_f);
+    size_t oh = 0, of = 0;
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        const ConvLayer& L = ctx->conv[li];
+        const size_t nw = (size_t)L.kh * L.kw * L.cin * L.cout;
+        const float* w = h_blob + off; const float* sc = w + nw; const float* bi = sc + L.cout;
+        off += nw + 2 * (size_t)L.cout;
+        if (li == 0) continue;
+        const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
+        ctx->tc_w_off[li] = oh; ctx->tc_sb_off[li] = of;
+        for (int j = 0; j < 3; ++j)
+            for (int g = 0; g < cgp; ++g)
+                for (int n = 0; n < np; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = g * 8 + e;
+                        const float v = (c < L.cin && n < L.cout) ? w[((size_t)j * L.cin + c) * L.cout + n] : 0.f;
+                        hw[oh + (((size_t)j * cgp + g) * np + n) * 8 + e] = __float2half_rn(v);
+                    }
+        oh += (size_t)3 * cgp * np * 8;
+        for (int n = 0; n < np; ++n) { hf[of + n] = n < L.cout ? sc[n] : 0.f; hf[of + np + n] = n < L.cout ? bi[n] : 0.f; }
+        of += 2 * (size_t)np;
+    }
+    if (!ctx->d_tc_w) OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_w, total_h * sizeof(__half)));
+    if (!ctx->d_tc_sb) OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_sb, total_f * sizeof(float)));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_tc_w, hw.data(), total_h * sizeof(__half), cudaMemcpyHostToDevice));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_tc_sb, hf.data(), total_f * sizeof(float), cudaMemcpyHostToDevice));
+    return OWW_OK;
+}
+
+size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows) {
+    // largest footprint over all layer outputs: planes * plane pitch, in 16-byte units
+    size_t best = 0;
+    int T = 76, W = 32;
+    auto upd = [&](int t, int w, int c) {
+        const size_t plane = ((size_t)kGuard + (size_t)n_windows * t * (w + 1) + kGuardBack + 7) & ~(size_t)7;
+        const size_t tot = (size_t)(c / 8) * plane;
+        if (tot > best) best = tot;
+    };
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        const ConvLayer& L = ctx->conv[li];
+        T -= (L.kh - 1);
+        upd(T, W, L.cout);
+        if (L.pool_t) { T /= L.pool_t; W /= L.pool_f; upd(T, W, L.cout); }
+    }
+    return best + 64;
+}
+
+// Runs the pyramid in tensor-core mode on n windows (n <= ctx->window_batch); d_emb [n][96] fp32.
+// stop_layer >= 0: stop after that layer (and its pool) and unpack it to NHWC fp32 in d_dbg.
+int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s) {
+    __half* bufs[2] = {reinterpret_cast<__half*>(ctx->d_tc_act[0]), reinterpret_cast<__half*>(ctx->d_tc_act[1])};
+    int cur = 0;
+    int T = 76, W = 32;
+    auto plane_units = [&](int t, int w) { return (int64_t)((kGuard + (int64_t)n * t * (w + 1) + kGuardBack + 7) & ~7LL); };
+    int64_t in_plane = 0;
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        const ConvLayer& L = ctx->conv[li];
+        const int T_out = T - (L.kh - 1);
+        const bool last = li == OWW_N_CONV - 1;
+        const int64_t out_plane = plane_units(T_out, W);
+        if (li == 0) {
+            Tc0Args a{src, n, L.d_w, L.d_scale, L.d_bias, bufs[cur], out_plane};
+            const int64_t total = (int64_t)n * 74 * 33;
+            unsigned grid = (unsigned)((total + 255) / 256);
+            if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
+            tc_conv0_kernel<<<grid, 256, 0, s>>>(a);
+            OWW_LAUNCH_CHECK(ctx);
+        } else {
+            const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
+            const int Wp = W + 1;
+            TcConvArgs a;
+            a.in = bufs[cur ^ 1]; a.in_plane = in_plane;
+            a.out = bufs[cur]; a.out_plane = out_plane;
+            a.out_f32 = last ? d_emb : nullptr;
+            a.w = reinterpret_cast<const __half*>(ctx->d_tc_w) + ctx->tc_w_off[li];
+            a.scale = ctx->d_tc_sb + ctx->tc_sb_off[li]; a.bias = a.scale + np;
+            a.n = n; a.T = T; a.W = W; a.T_out = T_out;
+            if (L.kw == 3) { a.lo = 1; a.tap_off[0] = 0; a.tap_off[1] = 1; a.tap_off[2] = 2; a.rows = round8(128 + 2); }
+            else { a.lo = 0; a.tap_off[0] = 0; a.tap_off[1] = Wp; a.tap_off[2] = 2 * Wp; a.rows = round8(128 + 2 * Wp); }
+            a.cg_in = cg; a.cg_out = L.cout / 8; a.apply_act = last ? 0 : 1;
+            a.p_in = (int64_t)n * T * Wp;
+            a.n_tiles = (int)((a.p_in + 127) / 128);
+            int rc;
+            if (cgp == 4 && np == 32) rc = launch_tc<4, 32>(ctx, a, s);
+            else if (cgp == 4 && np == 48) rc = launch_tc<4, 48>(ctx, a, s);
+            else if (cgp == 6 && np == 48) rc = launch_tc<6, 48>(ctx, a, s);
+            else if (cgp == 6 && np == 80) rc = launch_tc<6, 80>(ctx, a, s);
+            else if (cgp == 10 && np == 80) rc = launch_tc<10, 80>(ctx, a, s);
+            else if (cgp == 10 && np == 96) rc = launch_tc<10, 96>(ctx, a, s);
+            else if (cgp == 12 && np == 96) rc = launch_tc<12, 96>(ctx, a, s);
+            else rc = oww_fail(ctx, OWW_EUNSUPPORTED, "no tcgen05 conv instance for cgp=%d np=%d", cgp, np);
+            if (rc) return rc;
+        }
+        T = T_out; in_plane = out_plane; cur ^= 1;
+        if (L.pool_t && !last) {
+            const int T2 = T / L.pool_t, W2 = W / L.pool_f;
+            const int64_t op = plane_units(T2, W2);
+            const int cgo = L.cout / 8;
+            const int64_t total = (int64_t)n * T2 * (W2 + 1) * cgo;
+            unsigned grid = (unsigned)((total + 255) / 256);
+            if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
+            tc_pool_kernel<<<grid, 256, 0, s>>>(bufs[cur ^ 1], in_plane, bufs[cur], op, n, T, W, cgo, L.pool_t, L.pool_f);
+            OWW_LAUNCH_CHECK(ctx);
+            T = T2; W = W2; in_plane = op; cur ^= 1;
+        }
+        if (li == stop_layer && !last) {
+            const int64_t total = (int64_t)n * T * W * L.cout;
+            tc_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bufs[cur ^ 1], in_plane, d_dbg, n, T, W, L.cout);
+            OWW_LAUNCH_CHECK(ctx);
+            return OWW_OK;
+        }
+    }
+    return OWW_OK;
+}

@@ -74,6 +74,14 @@ struct oww_ctx {
     float* d_emb_tmp = nullptr;      // [max_chunks*B][96]
     size_t emb_tmp_floats = 0;
 
+    // tensor-core path (cnn_tc.cu)
+    void* d_tc_w = nullptr;          // packed fp16 weights, all layers
+    float* d_tc_sb = nullptr;        // padded scale/bias per layer
+    size_t tc_w_off[OWW_N_CONV] = {0};
+    size_t tc_sb_off[OWW_N_CONV] = {0};
+    void* d_tc_act[2] = {nullptr, nullptr};   // fp16 channel-group planes, ping-pong
+    size_t tc_act_units = 0;
+
     // incremental-mode state
     float* d_tails = nullptr;        // per-stream cached rows (layout in cnn_incremental.cu)
     float* d_inc_act[2] = {nullptr, nullptr};
@@ -138,10 +146,18 @@ struct WindowSrc {
     const int* count; int rows_mask;    // ring addressing (count==nullptr -> linear)
     int n_streams; int n_chunks;
 };
-int oww_cnn_window_fp32(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s);
 // Fully-convolutional pass over linear mel [n][T][32] -> [n][(T-76)/8+1][96].
 int oww_cnn_clip_fp32(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s);
 int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s);
+// mode dispatch (fp32 window / tcgen05 window) with sub-batching over ctx->window_batch
+int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s);
+
+// ---- cnn_tc.cu ----
+int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob);
+size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows);
+int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
+// fp32 pyramid with an optional early stop that leaves NHWC fp32 [n][T][W][C] of `stop_layer` in d_dbg
+int oww_cnn_fp32_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
 
 // ---- heads.cu ----
 struct FeatSrc {

@@ -1,0 +1,84 @@
+"""-m gpu: the tcgen05 embedding-CNN path (cnn_mode = OWW_CNN_TC_WINDOW) against the oracle, layer by
+layer (fp16 operands: activations and weights are rounded to fp16, accumulation is fp32), then end to
+end on embeddings and scores (1e-3 gate)."""
+import numpy as np
+import pytest
+
+from helpers import emb_weights, head
+
+pytestmark = pytest.mark.gpu
+TC = 2
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch
+
+
+def _ctx(mode, window_batch=0):
+    from openwakeword_b200 import _native, weights as W
+    ctx = _native.Context(cnn_mode=mode, window_batch=window_batch)
+    ctx.load_mel()
+    ctx.load_embedding(W.pack_embedding_blob(emb_weights()))
+    return ctx
+
+
+def _windows(rng, n):
+    from oracle import mel
+    out = []
+    for i in range(n):
+        amp = [300, 3000, 12000][i % 3]
+        x = np.clip(rng.normal(0, amp, 12400 + 512), -32768, 32767).astype(np.int16)
+        out.append(mel.melspectrogram(x)[:76])
+    return np.stack(out).astype(np.float32)
+
+
+@pytest.mark.parametrize("n", [3, 130])
+def test_tc_layers_vs_oracle(torch_cuda, built_library, n):
+    torch = torch_cuda
+    from oracle import embedding
+    rng = np.random.default_rng(5)
+    wins = _windows(rng, n)
+    _, ref_layers = embedding.forward(emb_weights(), wins, return_all=True)
+    ctx = _ctx(TC)
+    d = torch.from_numpy(wins).cuda()
+    worst_rel = 0.0
+    for li in range(19):
+        ref = ref_layers[li]
+        out = torch.empty(ref.shape, dtype=torch.float32, device="cuda")
+        ctx.debug_layer(d, n, li, out)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        err = np.abs(got - ref)
+        scale = np.abs(ref).max()
+        print(f"layer {li:2d} shape {ref.shape} max|ref| {scale:7.3f} max err {err.max():.4e} mean err {err.mean():.3e}")
+        assert np.isfinite(got).all(), f"layer {li} has non-finite values"
+        assert err.max() < 2e-2 * max(scale, 1.0), f"layer {li}: max err {err.max()}"
+        worst_rel = max(worst_rel, err.max() / max(scale, 1.0))
+    emb = torch.empty((n, 96), dtype=torch.float32, device="cuda")
+    ctx.embed_windows(d, n, emb)
+    torch.cuda.synchronize()
+    e = np.abs(emb.cpu().numpy() - embedding.embed_windows(emb_weights(), wins))
+    print("embedding max err", e.max(), "worst relative layer err", worst_rel)
+    assert e.max() < 3e-2
+
+
+def test_tc_scores_vs_fp32_and_oracle(torch_cuda, built_library):
+    from openwakeword_b200.engine import StreamEngine
+    rng = np.random.default_rng(9)
+    B, steps = 300, 6
+    hs = [head("alexa_v0.1"), head("hey_mycroft_v0.1"), head("timer_v0.1"), head("big_v0.1")]
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    pcm = np.clip(rng.normal(0, 2500, (B, steps * 1280)), -32768, 32767).astype(np.int16)
+    pcm[::3] = rng.integers(-1000, 1000, (len(pcm[::3]), steps * 1280))
+    res = {}
+    for mode in (0, TC):
+        eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=mode)
+        res[mode] = np.stack([eng.step_host(np.ascontiguousarray(pcm[:, s * 1280:(s + 1) * 1280]), 1).copy()
+                              for s in range(steps)], 1)
+    d = np.abs(res[0] - res[TC])
+    print("max |score_tc - score_fp32| =", d.max(), " mean", d.mean())
+    assert d.max() < 1e-3
