@@ -154,7 +154,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     ctx->cfg = *cfg;
     if (ctx->cfg.max_chunks < 1) ctx->cfg.max_chunks = 1;
     ctx->device = cfg->device;
-    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : (cfg->cnn_mode == OWW_CNN_TC_WINDOW ? 256 : 512);
+    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : (cfg->cnn_mode == OWW_CNN_TC_WINDOW ? 1024 : 512);
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) {
         oww_fail(nullptr, OWW_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
         delete ctx; return OWW_ECUDA;

@@ -11,7 +11,6 @@
 
 namespace {
 
-constexpr int TB = 32;          // samples per CTA
 constexpr int KC = 32;          // K chunk of the first (wide) layer
 constexpr int NTHREADS = 256;
 constexpr int HMAX = 256;       // widest hidden / output layer supported
@@ -32,7 +31,7 @@ struct HeadsArgs {
 __device__ __forceinline__ int next_pow2_32(int d) { int p = 32; while (p < d) p <<= 1; return p; }
 
 // acc[i] holds output (row = rgrp + R*i, col = d) for this thread; DP = padded layer width.
-template <int DP>
+template <int TB, int DP>
 __device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& src, int s0, int n, float (*xs)[KC + 1],
                                              float* ws, float* acc) {
     constexpr int R = NTHREADS / DP, NR = TB / R;
@@ -72,7 +71,7 @@ __device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& sr
     }
 }
 
-template <int DP>
+template <int TB, int DP>
 __device__ __forceinline__ void dense_smem(const float* __restrict__ W, int K, int D, const float (*hin)[HMAX + 1],
                                            float* acc) {
     constexpr int R = NTHREADS / DP, NR = TB / R;
@@ -88,7 +87,7 @@ __device__ __forceinline__ void dense_smem(const float* __restrict__ W, int K, i
     }
 }
 
-template <int DP>
+template <int TB, int DP>
 __device__ __forceinline__ void store_acc(const float* acc, const float* bias, int D, float (*hout)[HMAX + 1]) {
     constexpr int R = NTHREADS / DP, NR = TB / R;
     const int tid = threadIdx.x, d = tid % DP, rgrp = tid / DP;
@@ -99,6 +98,7 @@ __device__ __forceinline__ void store_acc(const float* acc, const float* bias, i
     }
 }
 
+template <int TB>
 __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
     extern __shared__ __align__(16) float smem_dyn[];
     float (*xs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(smem_dyn);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
     const HeadDev& H = a.head[blockIdx.y];
     const int s0 = blockIdx.x * TB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float acc[32];
+    float acc[TB];
 
     float (*cur)[HMAX + 1] = hA;
     float (*nxt)[HMAX + 1] = hB;
@@ -117,18 +117,18 @@ __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
         const int DP = next_pow2_32(D);
         if (l == 0) {
             switch (DP) {
-                case 32: dense_gather<32>(H, a.src, s0, a.n, xs, ws, acc); store_acc<32>(acc, H.blob + H.b_off[0], D, cur); break;
-                case 64: dense_gather<64>(H, a.src, s0, a.n, xs, ws, acc); store_acc<64>(acc, H.blob + H.b_off[0], D, cur); break;
-                case 128: dense_gather<128>(H, a.src, s0, a.n, xs, ws, acc); store_acc<128>(acc, H.blob + H.b_off[0], D, cur); break;
-                default: dense_gather<256>(H, a.src, s0, a.n, xs, ws, acc); store_acc<256>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 32: dense_gather<TB, 32>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 32>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 64: dense_gather<TB, 64>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 64>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 128: dense_gather<TB, 128>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 128>(acc, H.blob + H.b_off[0], D, cur); break;
+                default: dense_gather<TB, 256>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 256>(acc, H.blob + H.b_off[0], D, cur); break;
             }
         } else {
             const float* W = H.blob + H.w_off[l];
             switch (DP) {
-                case 32: dense_smem<32>(W, K, D, cur, acc); store_acc<32>(acc, H.blob + H.b_off[l], D, nxt); break;
-                case 64: dense_smem<64>(W, K, D, cur, acc); store_acc<64>(acc, H.blob + H.b_off[l], D, nxt); break;
-                case 128: dense_smem<128>(W, K, D, cur, acc); store_acc<128>(acc, H.blob + H.b_off[l], D, nxt); break;
-                default: dense_smem<256>(W, K, D, cur, acc); store_acc<256>(acc, H.blob + H.b_off[l], D, nxt); break;
+                case 32: dense_smem<TB, 32>(W, K, D, cur, acc); store_acc<TB, 32>(acc, H.blob + H.b_off[l], D, nxt); break;
+                case 64: dense_smem<TB, 64>(W, K, D, cur, acc); store_acc<TB, 64>(acc, H.blob + H.b_off[l], D, nxt); break;
+                case 128: dense_smem<TB, 128>(W, K, D, cur, acc); store_acc<TB, 128>(acc, H.blob + H.b_off[l], D, nxt); break;
+                default: dense_smem<TB, 256>(W, K, D, cur, acc); store_acc<TB, 256>(acc, H.blob + H.b_off[l], D, nxt); break;
             }
             float (*t)[HMAX + 1] = cur; cur = nxt; nxt = t;
         }
@@ -203,14 +203,22 @@ int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float
         d.col0 = (head_id < 0 ? h.col0 : 0) + out_col0;
     }
     a.src = src; a.n = n; a.out = d_out; a.out_stride = out_stride; a.combine_max = combine_max;
-    dim3 grid((n + TB - 1) / TB, nh);
-    constexpr size_t kSmem = sizeof(float) * (TB * (KC + 1) + KC * HMAX + 2 * TB * (HMAX + 1));
+    // small batches: 8 samples per CTA so that the grid still covers the SMs
+    const bool small = (n + 31) / 32 * nh < 2 * ctx->sm_count;
+    auto smem_of = [](int tb) { return sizeof(float) * (size_t)(tb * (KC + 1) + KC * HMAX + 2 * tb * (HMAX + 1)); };
     static bool attr_set = false;
     if (!attr_set) {
-        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(32)));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(8)));
         attr_set = true;
     }
-    heads_kernel<<<grid, NTHREADS, kSmem, s>>>(a);
+    if (small) {
+        dim3 grid((n + 7) / 8, nh);
+        heads_kernel<8><<<grid, NTHREADS, smem_of(8), s>>>(a);
+    } else {
+        dim3 grid((n + 31) / 32, nh);
+        heads_kernel<32><<<grid, NTHREADS, smem_of(32), s>>>(a);
+    }
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }

@@ -211,7 +211,7 @@ def test_full_size_properties(torch_cuda, built_library):
     assert np.array_equal(runs[0], runs[1])                           # bitwise deterministic
     first = {}
     for b in range(B):
-        key = pcm[b, :64].tobytes()
+        key = pcm[b].tobytes()
         if key in first:
             assert np.array_equal(runs[0][b], runs[0][first[key]])    # position in the batch does not matter
         else:
