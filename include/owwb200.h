@@ -53,8 +53,10 @@ extern "C" {
 
 /* embedding-CNN execution modes */
 #define OWW_CNN_FP32_WINDOW       0  /* CUDA-core fp32, full 76-row window per frame (reference-shaped)  */
-#define OWW_CNN_FP32_INCREMENTAL  1  /* CUDA-core fp32, per-stream activation tails: only the 8 new rows */
 #define OWW_CNN_TC_WINDOW         2  /* tcgen05 fp16-operand/fp32-accumulate implicit GEMM, full window  */
+#define OWW_CNN_TC_INCREMENTAL    3  /* tcgen05, fused 20-layer kernel on the 8 new mel rows per stream
+                                        (per-stream activation tails in HBM); first step after a reset and
+                                        the stateless/batch calls use the full-window tcgen05 kernels      */
 
 typedef struct oww_ctx oww_ctx;
 
@@ -139,6 +141,11 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
  * layer `layer` (0..18) and its max-pool, and writes that activation as NHWC float32
  * [n][T][F][C] to d_out - used by the tests to localise a mismatch layer by layer.             */
 int oww_debug_layer(oww_ctx* ctx, const float* d_windows, int n, int layer, float* d_out, void* stream);
+
+/* Geometry plan of the fused incremental CNN kernel for groups of `group` streams, as raw int32
+ * (struct IncPlan of csrc/oww_internal.h); returns the number of ints written (> 0) or an error.
+ * Pure host computation (usable without a GPU): tests/test_inc_plan.py replays it in NumPy.          */
+int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int max_ints);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 uint64_t oww_launch_count(const oww_ctx* ctx);       /* kernels launched by this handle so far   */

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "oww_embed_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "oww_predict_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "oww_debug_layer": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "oww_debug_inc_plan": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
     "oww_launch_count": (C.c_uint64, [_P]),
     "oww_enable_stage_timing": (C.c_int, [_P, C.c_int]),
     "oww_stage_ms": (C.c_int, [_P, _P]),

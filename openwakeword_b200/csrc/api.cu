@@ -33,6 +33,15 @@ const int kLayerTable[OWW_N_CONV][6] = {   // kh kw cin cout pool_t pool_f  (SUR
     {3, 1, 96, 96, 0, 0},
 };
 
+void fill_layer_table(oww_ctx* ctx) {
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        ConvLayer& L = ctx->conv[li];
+        L.kh = kLayerTable[li][0]; L.kw = kLayerTable[li][1]; L.cin = kLayerTable[li][2]; L.cout = kLayerTable[li][3];
+        L.pool_t = kLayerTable[li][4]; L.pool_f = kLayerTable[li][5];
+        L.d_w = L.d_scale = L.d_bias = nullptr;
+    }
+}
+
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 __global__ void reset_kernel(const int* ids, int n_ids, int n_streams, int16_t* tail, int* seen, int* mel_count,
@@ -66,17 +75,17 @@ __global__ void gather_chunk_kernel(const int16_t* pcm, int n_clips, int n_sampl
 void free_streams(oww_ctx* c) {
     cudaFree(c->d_tail); cudaFree(c->d_seen); cudaFree(c->d_mel_count); cudaFree(c->d_feat_count);
     cudaFree(c->d_mel_ring); cudaFree(c->d_feat_ring); cudaFree(c->d_act[0]); cudaFree(c->d_act[1]);
-    cudaFree(c->d_emb_tmp); cudaFree(c->d_tails); cudaFree(c->d_inc_act[0]); cudaFree(c->d_inc_act[1]);
-    cudaFree(c->d_inc_valid);
-    c->d_tail = nullptr; c->d_seen = c->d_mel_count = c->d_feat_count = c->d_inc_valid = nullptr;
-    c->d_mel_ring = c->d_feat_ring = c->d_act[0] = c->d_act[1] = c->d_emb_tmp = c->d_tails = nullptr;
-    c->d_inc_act[0] = c->d_inc_act[1] = nullptr;
-    c->act_floats = c->emb_tmp_floats = c->inc_act_floats = 0;
+    cudaFree(c->d_emb_tmp); cudaFree(c->d_inc_tails[0]); cudaFree(c->d_inc_tails[1]);
+    c->d_tail = nullptr; c->d_seen = c->d_mel_count = c->d_feat_count = nullptr;
+    c->d_mel_ring = c->d_feat_ring = c->d_act[0] = c->d_act[1] = c->d_emb_tmp = nullptr;
+    c->d_inc_tails[0] = c->d_inc_tails[1] = nullptr;
+    c->inc_primed = false;
+    c->act_floats = c->emb_tmp_floats = 0;
     c->n_streams = 0;
 }
 
 int ensure_act(oww_ctx* ctx, size_t floats) {
-    if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW) {
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW || ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL) {
         const size_t units = oww_tc_act_units(ctx, ctx->window_batch);
         if (ctx->tc_act_units < units) {
             cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]);
@@ -120,7 +129,15 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
     if ((rc = oww_mel_launch(ctx, m, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
     WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, B, n_chunks};
-    if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s))) return rc;
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && ctx->inc_primed) {
+        // steady state: one fused launch per chunk on the 8 new mel rows
+        for (int i = 0; i < n_chunks; ++i)
+            if ((rc = oww_cnn_inc_step(ctx, 8 * (n_chunks - 1 - i), ctx->d_emb_tmp + (size_t)i * B * 96, s))) return rc;
+    } else {
+        const bool prime = ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL;
+        if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s, prime))) return rc;
+        if (prime) ctx->inc_primed = true;
+    }
     if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, n_chunks, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
     for (int i = n_chunks - 1; i >= 0; --i) {
@@ -147,14 +164,14 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     if (e != cudaSuccess || ndev == 0)
         return oww_fail(nullptr, OWW_ECUDA, "no CUDA device: %s", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return oww_fail(nullptr, OWW_EINVAL, "device %d out of range", cfg->device);
-    if (cfg->cnn_mode != OWW_CNN_FP32_WINDOW && cfg->cnn_mode != OWW_CNN_TC_WINDOW)
+    if (cfg->cnn_mode != OWW_CNN_FP32_WINDOW && cfg->cnn_mode != OWW_CNN_TC_WINDOW && cfg->cnn_mode != OWW_CNN_TC_INCREMENTAL)
         return oww_fail(nullptr, OWW_EUNSUPPORTED, "cnn_mode %d not built in this version", cfg->cnn_mode);
     oww_ctx* ctx = new (std::nothrow) oww_ctx();
     if (!ctx) return oww_fail(nullptr, OWW_ENOMEM, "out of host memory");
     ctx->cfg = *cfg;
     if (ctx->cfg.max_chunks < 1) ctx->cfg.max_chunks = 1;
     ctx->device = cfg->device;
-    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : (cfg->cnn_mode == OWW_CNN_TC_WINDOW ? 1024 : 512);
+    ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : (cfg->cnn_mode == OWW_CNN_FP32_WINDOW ? 512 : 1024);
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) {
         oww_fail(nullptr, OWW_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
         delete ctx; return OWW_ECUDA;
@@ -167,12 +184,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
         delete ctx; return OWW_EUNSUPPORTED;
     }
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
-    for (int li = 0; li < OWW_N_CONV; ++li) {
-        ConvLayer& L = ctx->conv[li];
-        L.kh = kLayerTable[li][0]; L.kw = kLayerTable[li][1]; L.cin = kLayerTable[li][2]; L.cout = kLayerTable[li][3];
-        L.pool_t = kLayerTable[li][4]; L.pool_f = kLayerTable[li][5];
-        L.d_w = L.d_scale = L.d_bias = nullptr;
-    }
+    fill_layer_table(ctx);
     *out = ctx;
     return OWW_OK;
 }
@@ -187,7 +199,7 @@ void oww_destroy(oww_ctx* ctx) {
     free_streams(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
     cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
-    cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]);
+    cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w);
     for (auto& h : ctx->heads) cudaFree(h.d_blob);
     cudaFreeHost(ctx->h_pcm_pinned); cudaFreeHost(ctx->h_scores_pinned);
     cudaFree(ctx->d_pcm_stage); cudaFree(ctx->d_scores_stage);
@@ -216,7 +228,9 @@ int oww_load_embedding(oww_ctx* ctx, const float* h_blob, size_t n_floats) {
         L.d_bias = ctx->d_emb_blob + off; off += L.cout;
     }
     ctx->emb_loaded = true;
-    return oww_tc_pack_weights(ctx, h_blob);
+    int rc = oww_tc_pack_weights(ctx, h_blob);
+    if (rc) return rc;
+    return oww_inc_setup(ctx, h_blob);
 }
 
 int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, size_t n_floats, int* head_id) {
@@ -304,6 +318,7 @@ int oww_set_streams(oww_ctx* ctx, int n_streams) {
     int rc = ensure_act(ctx, (size_t)std::min(B * mc, ctx->window_batch) * 74 * 32 * 24);
     if (rc) return rc;
     if ((rc = ensure_emb_tmp(ctx, (size_t)B * mc * 96))) return rc;
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && (rc = oww_inc_alloc_streams(ctx))) return rc;
     return oww_reset(ctx, nullptr, B, nullptr, OWW_INIT_FEATURE_ROWS);
 }
 
@@ -330,6 +345,7 @@ int oww_reset(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_f
     reset_kernel<<<n, 256>>>(d_ids, n, ctx->n_streams, ctx->d_tail, ctx->d_seen, ctx->d_mel_count, ctx->d_feat_count,
                              ctx->d_mel_ring, ctx->mel_rows, ctx->d_feat_ring, ctx->feat_rows, d_init, n_rows);
     ctx->launches++;
+    ctx->inc_primed = false;          // a fresh stream's next window shifts by 5 rows, not 8: re-prime from a full window
     cudaError_t e = cudaDeviceSynchronize();
     cudaFree(d_ids); cudaFree(d_init);
     if (e != cudaSuccess) return oww_fail(ctx, OWW_ECUDA, "reset failed: %s", cudaGetErrorString(e));
@@ -469,7 +485,7 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     c->d_mel_start = ctx->d_mel_start; c->d_mel_len = ctx->d_mel_len; c->d_mel_w = ctx->d_mel_w; c->mel_kmax = ctx->mel_kmax;
     c->emb_loaded = ctx->emb_loaded;
     for (int li = 0; li < OWW_N_CONV; ++li) { c->conv[li] = ctx->conv[li]; c->tc_w_off[li] = ctx->tc_w_off[li]; c->tc_sb_off[li] = ctx->tc_sb_off[li]; }
-    c->d_tc_w = ctx->d_tc_w; c->d_tc_sb = ctx->d_tc_sb;
+    c->d_tc_w = ctx->d_tc_w; c->d_tc_sb = ctx->d_tc_sb; c->d_inc_w = ctx->d_inc_w;
     c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in;
     int rc = OWW_OK;
     for (int c0 = 0; c0 < n_clips && rc == OWW_OK; c0 += slab_max) {
@@ -506,6 +522,19 @@ int oww_debug_layer(oww_ctx* ctx, const float* d_windows, int n, int layer, floa
     WindowSrc src{d_windows, (int64_t)OWW_WINDOW_ROWS * 32, nullptr, -1, 0, 0};
     if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW) return oww_cnn_tc_pyramid(ctx, src, n, nullptr, layer, d_out, (cudaStream_t)stream);
     return oww_cnn_fp32_pyramid(ctx, src, n, nullptr, layer, d_out, (cudaStream_t)stream);
+}
+
+int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int max_ints) {
+    if (!out) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    oww_ctx local;                       // ctx may be NULL: the plan depends only on the fixed layer table
+    if (!ctx) { fill_layer_table(&local); ctx = &local; }
+    IncPlan P;
+    int rc = oww_inc_build_plan(ctx, group, n_streams, &P);
+    if (rc) return rc;
+    const int n = (int)(sizeof(IncPlan) / sizeof(int32_t));
+    if (max_ints < n) return oww_fail(ctx, OWW_EINVAL, "need room for %d ints", n);
+    std::memcpy(out, &P, sizeof(IncPlan));
+    return n;
 }
 
 int oww_enable_stage_timing(oww_ctx* ctx, int n_slots) {

@@ -334,7 +334,7 @@ int oww_cnn_fp32_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb
     return run_pyramid(ctx, src, n, OWW_WINDOW_ROWS, d_emb, s, stop_layer, d_dbg);
 }
 
-int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s) {
+int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s, bool capture_tails) {
     if (!ctx->emb_loaded) return oww_fail(ctx, OWW_EINVAL, "embedding weights not loaded");
     const int wb = ctx->window_batch;
     int w0 = 0;
@@ -358,8 +358,23 @@ int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_e
             sub.base = src.base + (int64_t)w0 * src.stride;
         }
         float* o = d_emb + (int64_t)w0 * OWW_EMBEDDING_DIM;
-        int rc = ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW ? oww_cnn_tc_pyramid(ctx, sub, n, o, -1, nullptr, s)
-                                                       : run_pyramid(ctx, sub, n, OWW_WINDOW_ROWS, o, s);
+        int rc;
+        if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW || ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL) {
+            TailCapture cap{0, 0, 0};
+            if (capture_tails && src.count) {
+                // windows of the newest chunk (global chunk index n_chunks-1) inside this sub-batch
+                const int b0 = w0 % src.n_streams, i0 = w0 / src.n_streams;
+                if (b0 == 0 && n >= src.n_streams) {
+                    const int k = n / src.n_streams;
+                    if (i0 + k == src.n_chunks) cap = TailCapture{(k - 1) * src.n_streams, src.n_streams, 0};
+                } else if (i0 == src.n_chunks - 1) {
+                    cap = TailCapture{0, n, b0};
+                }
+            }
+            rc = oww_cnn_tc_pyramid_cap(ctx, sub, n, o, cap.n_win ? &cap : nullptr, s);
+        } else {
+            rc = run_pyramid(ctx, sub, n, OWW_WINDOW_ROWS, o, s);
+        }
         if (rc) return rc;
         w0 += n;
     }

@@ -19,83 +19,9 @@
 // fp16 planes directly (16-byte coalesced stores).  Warp roles: 0 = bulk-copy producer,
 // 1 = TMEM allocator + single-thread MMA issuer, 2..5 = epilogue.  Persistent CTAs, grid = #SMs.
 #include "oww_internal.h"
-#include <cuda_fp16.h>
+#include "tc_common.cuh"
 
 namespace {
-
-constexpr float kLeak = 0.20000000298023224f;
-constexpr float kFloor = -0.4000000059604645f;
-constexpr int kGuard = 8;          // 16-byte units of zero guard in front of every plane
-constexpr int kGuardBack = 384;    // readable units behind the last position
-constexpr int kStages = 4;
-constexpr int kAccStages = 2;
-constexpr int kTcThreads = 192;
-
-__device__ __forceinline__ float act(float v) {
-    v = fmaxf(kLeak * v, v);
-    return fmaxf(v, kFloor);
-}
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must abort the kernel, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 26)) { printf("owwb200: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
 
 // ---------------------------------------------------------------- layer 0 (CUDA cores) -> fp16 planes
 struct Tc0Args {
@@ -475,7 +401,16 @@ size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows) {
 
 // Runs the pyramid in tensor-core mode on n windows (n <= ctx->window_batch); d_emb [n][96] fp32.
 // stop_layer >= 0: stop after that layer (and its pool) and unpack it to NHWC fp32 in d_dbg.
+int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg,
+                            const TailCapture* cap, cudaStream_t s);
 int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s) {
+    return oww_cnn_tc_pyramid_impl(ctx, src, n, d_emb, stop_layer, d_dbg, nullptr, s);
+}
+int oww_cnn_tc_pyramid_cap(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, const TailCapture* cap, cudaStream_t s) {
+    return oww_cnn_tc_pyramid_impl(ctx, src, n, d_emb, -1, nullptr, cap, s);
+}
+int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg,
+                            const TailCapture* cap, cudaStream_t s) {
     __half* bufs[2] = {reinterpret_cast<__half*>(ctx->d_tc_act[0]), reinterpret_cast<__half*>(ctx->d_tc_act[1])};
     int cur = 0;
     int T = 76, W = 32;
@@ -530,6 +465,11 @@ int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, 
             tc_pool_kernel<<<grid, 256, 0, s>>>(bufs[cur ^ 1], in_plane, bufs[cur], op, n, T, W, cgo, L.pool_t, L.pool_f);
             OWW_LAUNCH_CHECK(ctx);
             T = T2; W = W2; in_plane = op; cur ^= 1;
+        }
+        if (cap && cap->n_win > 0 && !last) {
+            // the tensor just produced feeds layer li+1; if that is a (3,1) conv its last two rows are the tails
+            int rc = oww_inc_capture(ctx, li, bufs[cur ^ 1], in_plane, T, W, cap->win0, cap->n_win, cap->stream0, s);
+            if (rc) return rc;
         }
         if (li == stop_layer && !last) {
             const int64_t total = (int64_t)n * T * W * L.cout;

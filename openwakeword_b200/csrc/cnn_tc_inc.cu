@@ -1,0 +1,525 @@
+// K2 (incremental tensor-core path): ONE persistent kernel runs all 20 layers of the speech-embedding
+// CNN for the 8 new mel rows of every stream, with every activation in shared memory / TMEM.
+//
+// Why this is exact.  The CNN (reference embedding_model.onnx, /root/reference/openwakeword/utils.py:90-93,
+// spec notebooks/converting_google_speech_embedding_model.ipynb:871-951) is fully convolutional along
+// time with total stride 8, and the reference evaluates it on a 76-row window that slides by exactly
+// 8 rows per 80 ms chunk (utils.py:437-443).  So the newest window's activations are
+// the previous window's shifted by 8/4/2/1 rows per level: only the LAST 8/4/2/1 rows of each layer
+// are new, and a (3,1) convolution needs just the last two rows of its input from the previous step
+// ("tails", 10 small tensors per stream, kept in HBM between steps).  The first step after a reset
+// (5 mel rows) is computed with the full-window kernels (cnn_tc.cu), which also prime
+// the tails.
+//
+// Mapping.  A CTA owns a group of G streams.  Positions are ordered (t, stream, f) with one zero pad
+// column, stored as fp16 channel-group planes (16-byte units) in two smem buffers X/Y, exactly the
+// no-swizzle K-major UMMA core-matrix order.  For layer l the A operand is read IN PLACE from the
+// previous layer's output planes: a conv tap is a shift of the descriptor start address
+// ((1,3): -1/0/+1 units; (3,1): 0/GWp/2GWp units), so there is no im2col and no copy.  Weights
+// (+ folded BN scale/bias) of layer l+1 stream into a double buffer by cp.async.bulk while layer l
+// computes.  D lives in TMEM (4 x 128 columns); 8 epilogue warps (2 per lane quarter) apply
+// BN + leaky + clamp, write the next layer's planes to smem, and spill the new tails to HBM.
+// Max-pools are an smem->smem pass of the same warps.  Warp 8 = weight producer, warp 9 = MMA issuer.
+#include "oww_internal.h"
+#include "tc_common.cuh"
+#include <cstring>
+
+namespace {
+
+constexpr int kIncEpiWarps = 8;
+constexpr int kIncThreads = (kIncEpiWarps + 2) * 32;      // 320
+constexpr int kIncAcc = 4;                                // TMEM accumulator stages (4 x 128 columns)
+constexpr int kIncMaxG = 4;
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
+struct IncArgs {
+    IncPlan plan;
+    const float* mel; const int* mel_count; int64_t mel_stride; int mel_mask; int back;
+    const float* w0; const float* s0; const float* b0;       // layer 0 (fp32, CUDA cores)
+    const uint8_t* wblob;                                     // packed per layer: fp16 [3][CGP][NP][8] | scale[NP] | bias[NP]
+    const uint4* tails_in; uint4* tails_out;                  // [n_groups][tail_units]
+    float* emb;                                               // [B][96]
+    int B;
+};
+
+__global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_constant__ IncArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const IncPlan& P = a.plan;
+    const int G = P.G;
+    // [0, 2048): barriers, TMEM slot, layer-0 weights.  Activations grow from 2048 up; the per-layer weight
+    // slots sit at the top of the arena (offsets in the plan, checked against the activation extents).
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kIncAcc);
+    float* s_l0 = reinterpret_cast<float*>(smem + 256);              // 9*24 + 24 + 24 floats
+    uint4* bufX = reinterpret_cast<uint4*>(smem + 2048);
+    uint4* bufY = bufX + P.x_units;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto wfull = [&](int i) { return bar0 + 8u * i; };
+    auto wempty = [&](int i) { return bar0 + 8u * (2 + i); };
+    auto tfull = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto tempty = [&](int s) { return bar0 + 8u * (4 + kIncAcc + s); };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), 1); }
+        for (int s = 0; s < kIncAcc; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), kIncEpiWarps * 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 9 * 24; i += kIncThreads) s_l0[i] = a.w0[i];
+    if (threadIdx.x < 24) { s_l0[216 + threadIdx.x] = a.s0[threadIdx.x]; s_l0[240 + threadIdx.x] = a.b0[threadIdx.x]; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == kIncEpiWarps + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == kIncEpiWarps) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            uint32_t par[2] = {0, 0};
+            for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+                for (int l = 1; l < OWW_N_CONV; ++l) {
+                    const int i = l & 1;
+                    mbar_wait(wempty(i), par[i] ^ 1);
+                    mbar_expect_tx(wfull(i), (uint32_t)P.L[l].w_bytes);
+                    bulk_g2s(smem_u32(smem + P.L[l].w_smem), a.wblob + P.L[l].w_off, (uint32_t)P.L[l].w_bytes, wfull(i));
+                    par[i] ^= 1;
+                }
+            }
+        }
+    } else if (warp == kIncEpiWarps + 1) {
+        // ===================== MMA issuer =====================
+        uint32_t wpar[2] = {0, 0};
+        int acc = 0; uint32_t acc_par = 0;
+        bool have_prev = false; int prev_i = 0;
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+            for (int l = 1; l < OWW_N_CONV; ++l) {
+                const IncLayer& L = P.L[l];
+                named_bar_sync(1, (kIncEpiWarps + 1) * 32);       // layer l-1 output complete and fenced
+                tc_fence_after();
+                if (lane == 0) {
+                    // layer l-1's epilogue (which reads scale/bias from its weight slot) is done: free that slot
+                    if (have_prev) mbar_arrive(wempty(prev_i));
+                    const int i = l & 1;
+                    mbar_wait(wfull(i), wpar[i]);
+                    wpar[i] ^= 1;
+                    const uint32_t w_addr = smem_u32(smem + L.w_smem);
+                    const uint32_t a_base = smem_u32(L.in_buf ? bufY : bufX);
+                    const uint32_t idesc = (1u << 4) | ((uint32_t)(L.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                    const int n_tiles = (L.M + 127) / 128;
+                    for (int tile = 0; tile < n_tiles; ++tile) {
+                        mbar_wait(tempty(acc), acc_par ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+                        uint32_t accumulate = 0;
+                        for (int j = 0; j < 3; ++j) {
+                            for (int q = 0; q < L.cgp / 2; ++q) {
+                                // K = 16 = two channel-group planes; an odd plane count pairs the last plane with
+                                // itself (LBO 0) against zero weights, so no pad plane has to exist in smem
+                                const uint32_t lbo_a = (2 * q + 1 < L.cg_in) ? (uint32_t)L.in_pitch * 16u : 0u;
+                                const uint64_t ad = make_desc(a_base + (uint32_t)(2 * q * L.in_pitch + 1 + tile * 128 + L.tap[j]) * 16u, lbo_a, 128u);
+                                const uint64_t bd = make_desc(w_addr + (uint32_t)((j * L.cgp + 2 * q) * L.np) * 16u, (uint32_t)L.np * 16u, 128u);
+                                tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        tc_commit(tfull(acc));
+                        if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
+                    }
+                    have_prev = true; prev_i = i;
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue / CUDA-core warps (256 threads) =====================
+        const int et = threadIdx.x;                               // 0..255
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = quarter * 32 + lane;
+        int acc = 0; uint32_t acc_par = 0;
+        uint32_t epar[2] = {0, 0};
+        for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
+            const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
+            uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
+            for (int l = 0; l < OWW_N_CONV; ++l) {
+                const IncLayer& L = P.L[l];
+                uint4* nx = L.nx_buf ? bufY : bufX;
+                // ---- (a) tails of the buffer this phase fills (rows 0..1) and front guards.  In a pool phase that
+                //      buffer is still the conv's INPUT, so this is deferred until the tiles are drained. ----
+                auto fill_tails_and_guards = [&]() {
+                    if (L.nx_tail_off >= 0) {
+                        const int per = 2 * G * L.nx_Wp;
+                        for (int i = et; i < L.cg_out * per; i += kIncEpiWarps * 32) {
+                            const int pl = i / per, u = i - pl * per;
+                            const int g = (u / L.nx_Wp) % G;
+                            const bool live = grp * G + g < a.B;
+                            uint4 v = make_uint4(0, 0, 0, 0);
+                            if (live) v = __ldg(tin + L.nx_tail_off + i);
+                            nx[pl * L.nx_pitch + 1 + u] = v;
+                            if (L.nx_rows_new == 1 && u >= G * L.nx_Wp && live)      // single new row: old tail row 1 becomes row 0
+                                tout[L.nx_tail_off + pl * per + (u - G * L.nx_Wp)] = v;
+                        }
+                    }
+                    if (!L.final && et < L.cg_out) nx[et * L.nx_pitch] = make_uint4(0, 0, 0, 0);
+                };
+                if (!L.pool_t) fill_tails_and_guards();
+                else if (et < L.cg_out) (L.out_buf ? bufY : bufX)[et * L.tmp_pitch] = make_uint4(0, 0, 0, 0);
+
+                if (l == 0) {
+                    // ---- layer 0 on CUDA cores: 8 new rows from the last 10 mel rows of each stream ----
+                    const int Wp = 33;
+                    for (int p = et; p < 8 * G * Wp; p += kIncEpiWarps * 32) {
+                        const int f = p % Wp, tg = p / Wp, g = tg % G, t = tg / G;
+                        const int b = grp * G + g;
+                        uint4* o = nx + 1 + p;
+                        if (f == 32 || b >= a.B) {
+                            const uint4 z = make_uint4(0, 0, 0, 0);
+                            o[0] = z; o[L.nx_pitch] = z; o[2 * L.nx_pitch] = z;
+                            continue;
+                        }
+                        const float* base = a.mel + (int64_t)b * a.mel_stride;
+                        const int row0 = a.mel_count[b] - a.back - 10 + t;
+                        float x[9];
+#pragma unroll
+                        for (int dt = 0; dt < 3; ++dt) {
+                            const float* rp = base + (int64_t)((row0 + dt) & a.mel_mask) * 32;
+#pragma unroll
+                            for (int df = 0; df < 3; ++df) {
+                                const int ff = f + df - 1;
+                                x[dt * 3 + df] = (ff >= 0 && ff < 32) ? __ldg(rp + ff) : 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl) {
+                            __half2 h[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float v2[2];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int c = pl * 8 + u * 2 + e;
+                                    float s = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < 9; ++k) s = fmaf(x[k], s_l0[k * 24 + c], s);
+                                    s = fmaxf(s, 0.f);
+                                    v2[e] = act(fmaf(s, s_l0[216 + c], s_l0[240 + c]));
+                                }
+                                h[u] = __floats2half2_rn(v2[0], v2[1]);
+                            }
+                            o[pl * L.nx_pitch] = *reinterpret_cast<uint4*>(h);
+                        }
+                    }
+                } else {
+                    // ---- tcgen05 layer: drain TMEM tiles ----
+                    mbar_wait(wfull(l & 1), epar[l & 1]);             // weights (and scale/bias) of layer l have landed
+                    epar[l & 1] ^= 1;
+                    const float* sb = reinterpret_cast<const float*>(smem + L.w_smem + 3 * L.cgp * L.np * 16);
+                    const int np8 = L.np / 8;
+                    const int ph = (np8 + 1) / 2;
+                    const int pl0 = half * ph, pl1 = min(np8, pl0 + ph);
+                    uint4* dst = L.pool_t ? (L.out_buf ? bufY : bufX) : nx;
+                    const int dpitch = L.pool_t ? L.tmp_pitch : L.nx_pitch;
+                    const int t_off_units = L.pool_t ? 0 : L.nx_t_off * G * L.Wp;
+                    const int n_tiles = (L.M + 127) / 128;
+                    const int tail_start = (L.T_out - 2) * G * L.Wp;
+                    for (int tile = 0; tile < n_tiles; ++tile) {
+                        mbar_wait(tfull(acc), acc_par);
+                        tc_fence_after();
+                        uint32_t v[6][8];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k)
+                            if (pl0 + k < pl1) tmem_ld8(taddr + (pl0 + k) * 8, v[k]);
+                        tmem_wait_ld();
+                        tc_fence_before();
+                        mbar_arrive(tempty(acc));
+                        if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
+                        const int m = tile * 128 + row;
+                        if (m >= L.M) continue;
+                        const int f = m % L.Wp;
+                        const int g = (m / L.Wp) % G;
+                        const bool live = grp * G + g < a.B;
+                        if (L.final) {
+                            if (f != 0 || !live) continue;
+                            float* o = a.emb + (int64_t)(grp * G + g) * 96;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) {
+                                if (pl0 + k >= pl1) continue;
+                                const int c = (pl0 + k) * 8;
+                                float4 r0, r1;
+                                r0.x = fmaf(__uint_as_float(v[k][0]), sb[c + 0], sb[L.np + c + 0]);
+                                r0.y = fmaf(__uint_as_float(v[k][1]), sb[c + 1], sb[L.np + c + 1]);
+                                r0.z = fmaf(__uint_as_float(v[k][2]), sb[c + 2], sb[L.np + c + 2]);
+                                r0.w = fmaf(__uint_as_float(v[k][3]), sb[c + 3], sb[L.np + c + 3]);
+                                r1.x = fmaf(__uint_as_float(v[k][4]), sb[c + 4], sb[L.np + c + 4]);
+                                r1.y = fmaf(__uint_as_float(v[k][5]), sb[c + 5], sb[L.np + c + 5]);
+                                r1.z = fmaf(__uint_as_float(v[k][6]), sb[c + 6], sb[L.np + c + 6]);
+                                r1.w = fmaf(__uint_as_float(v[k][7]), sb[c + 7], sb[L.np + c + 7]);
+                                reinterpret_cast<float4*>(o + c)[0] = r0;
+                                reinterpret_cast<float4*>(o + c)[1] = r1;
+                            }
+                            continue;
+                        }
+                        const bool pad = f == L.W;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) {
+                            const int pl = pl0 + k;
+                            if (pl >= pl1 || pl >= L.cg_out) continue;
+                            const int c = pl * 8;
+                            __half2 h[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float y0 = act(fmaf(__uint_as_float(v[k][2 * u]), sb[c + 2 * u], sb[L.np + c + 2 * u]));
+                                const float y1 = act(fmaf(__uint_as_float(v[k][2 * u + 1]), sb[c + 2 * u + 1], sb[L.np + c + 2 * u + 1]));
+                                h[u] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(y0, y1);
+                            }
+                            const uint4 pk = *reinterpret_cast<uint4*>(h);
+                            dst[pl * dpitch + 1 + t_off_units + m] = pk;
+                            if (!L.pool_t && L.nx_tail_off >= 0 && m >= tail_start && live)
+                                tout[L.nx_tail_off + pl * (2 * G * L.Wp) + (m - tail_start)] = pk;
+                        }
+                    }
+                    if (L.pool_t) {
+                        // ---- max-pool: tmp (unpooled conv output) -> nx ----
+                        named_bar_sync(2, kIncEpiWarps * 32);          // every tile drained: the conv input buffer is free
+                        fill_tails_and_guards();
+                        const uint4* src = L.out_buf ? bufY : bufX;
+                        const int T2 = L.T_out / L.pool_t;
+                        const int per = T2 * G * L.nx_Wp;
+                        for (int i = et; i < L.cg_out * per; i += kIncEpiWarps * 32) {
+                            const int pl = i / per, p = i - pl * per;
+                            const int f = p % L.nx_Wp, tg = p / L.nx_Wp, g = tg % G, t = tg / G;
+                            uint4 res = make_uint4(0, 0, 0, 0);
+                            if (f < L.nx_W) {
+                                __half2 mx[4];
+                                bool first = true;
+                                for (int da = 0; da < L.pool_t; ++da)
+                                    for (int db = 0; db < L.pool_f; ++db) {
+                                        const uint4 q = src[pl * L.tmp_pitch + 1 + ((t * L.pool_t + da) * G + g) * L.Wp + f * L.pool_f + db];
+                                        const __half2* hv = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) mx[u] = first ? hv[u] : __hmax2(mx[u], hv[u]);
+                                        first = false;
+                                    }
+                                res = *reinterpret_cast<uint4*>(mx);
+                            }
+                            nx[pl * L.nx_pitch + 1 + L.nx_t_off * G * L.nx_Wp + p] = res;
+                            if (L.nx_tail_off >= 0 && grp * G + g < a.B) {
+                                // the pooled rows are the newest rows of a tails-bearing buffer
+                                const int keep = T2 >= 2 ? 2 : 1;
+                                if (t >= T2 - keep)
+                                    tout[L.nx_tail_off + pl * (2 * G * L.nx_Wp) + ((2 - keep + t - (T2 - keep)) * G + g) * L.nx_Wp + f] = res;
+                            }
+                        }
+                    }
+                }
+                // ---- phase done: make generic-proxy smem writes visible to the tensor core ----
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (l < OWW_N_CONV - 1) {
+                    tc_fence_before();
+                    named_bar_sync(1, (kIncEpiWarps + 1) * 32);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kIncEpiWarps + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---- capture of tails from the full-window planes (stream-major positions) ----------------------
+__global__ void __launch_bounds__(256) tc_capture_kernel(const uint4* planes, int64_t plane_pitch, int T, int Wp, int cg,
+                                                         int win0, int n_win, int stream0, int G, int tail_off,
+                                                         int tail_units, uint4* tails) {
+    const int per = 2 * Wp;
+    const int64_t total = (int64_t)n_win * cg * per;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int u = (int)(i % per);
+        const int pl = (int)((i / per) % cg);
+        const int w = (int)(i / ((int64_t)per * cg));
+        const int r = u / Wp, f = u - r * Wp;
+        const int b = stream0 + w, grp = b / G, g = b - grp * G;
+        const uint4 v = planes[(int64_t)pl * plane_pitch + kGuard + (int64_t)(win0 + w) * T * Wp + (int64_t)(T - 2 + r) * Wp + f];
+        tails[(int64_t)grp * tail_units + tail_off + pl * (2 * G * Wp) + (r * G + g) * Wp + f] = v;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Plan: per-layer geometry of the fused kernel for groups of G streams.
+int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
+    if (G < 1 || G > kIncMaxG) return oww_fail(ctx, OWW_EINVAL, "group size must be 1..%d", kIncMaxG);
+    constexpr int kTop = 227 * 1024;     // usable dynamic shared memory per CTA on sm_100
+    constexpr int kActBase = 2048;
+    IncPlan P;
+    std::memset(&P, 0, sizeof(P));
+    P.G = G;
+    P.n_groups = (n_streams + G - 1) / G;
+    int rows_new = 8, W = 32;            // geometry of the tensor produced by the previous phase
+    int tail_units = 0;
+    int x_units = 0, y_units = 0;
+    size_t w_off = 0;
+    auto pitch_of = [&](int rows, int wp) { return (1 + rows * G * wp + 7) & ~7; };
+    auto need = [&](int buf, int units) { if (buf) { if (units > y_units) y_units = units; } else { if (units > x_units) x_units = units; } };
+    int cur_buf = 0;                      // buffer holding the input of the next layer
+    int use_x[OWW_N_CONV] = {0}, use_y[OWW_N_CONV] = {0};   // units of X / Y alive during phase l
+    for (int l = 0; l < OWW_N_CONV; ++l) {
+        const ConvLayer& C = ctx->conv[l];
+        IncLayer& L = P.L[l];
+        L.final = l == OWW_N_CONV - 1;
+        L.kh3 = C.kh == 3 && l > 0;
+        L.W = W; L.Wp = W + 1;
+        L.cg_in = C.cin / 8; L.cgp = (L.cg_in + 1) & ~1; L.np = (C.cout + 15) & ~15; L.cg_out = C.cout / 8;
+        L.pool_t = C.pool_t; L.pool_f = C.pool_f;
+        auto use = [&](int buf, int units) { need(buf, units); int& u = buf ? use_y[l] : use_x[l]; if (units > u) u = units; };
+        if (l == 0) {
+            L.T_out = 8; L.M = 0;
+        } else {
+            L.in_buf = cur_buf;
+            L.rows_in = rows_new + (L.kh3 ? 2 : 0);
+            L.T_out = rows_new;
+            L.M = L.T_out * G * L.Wp;
+            L.in_pitch = P.L[l - 1].nx_pitch;
+            use(L.in_buf, L.in_pitch * L.cg_in);
+            if (L.kh3) { L.tap[0] = 0; L.tap[1] = G * L.Wp; L.tap[2] = 2 * G * L.Wp; }
+            else { L.tap[0] = -1; L.tap[1] = 0; L.tap[2] = 1; }
+            L.w_off = (int)w_off;
+            L.w_bytes = 3 * L.cgp * L.np * 16 + 2 * L.np * 4;
+            w_off += (size_t)((L.w_bytes + 127) & ~127);
+        }
+        // geometry of what this phase leaves for layer l+1
+        const bool next_kh3 = l + 1 < OWW_N_CONV && ctx->conv[l + 1].kh == 3;
+        int nrows = L.T_out, nW = W;
+        if (L.pool_t) { nrows = L.T_out / L.pool_t; nW = W / L.pool_f; }
+        L.nx_W = nW; L.nx_Wp = nW + 1; L.nx_rows_new = nrows;
+        L.nx_t_off = (next_kh3 && !L.final) ? 2 : 0;
+        L.out_buf = l == 0 ? 0 : (cur_buf ^ 1);
+        L.nx_buf = (l == 0) ? 0 : (L.pool_t ? cur_buf : L.out_buf);
+        L.nx_pitch = pitch_of(nrows + L.nx_t_off, L.nx_Wp);
+        if (L.pool_t) { L.tmp_pitch = pitch_of(L.T_out, L.Wp); use(L.out_buf, L.tmp_pitch * L.cg_out); }
+        if (!L.final) use(L.nx_buf, L.nx_pitch * L.cg_out);
+        L.nx_tail_off = -1;
+        if (L.nx_t_off == 2) { L.nx_tail_off = tail_units; tail_units += L.cg_out * 2 * G * L.nx_Wp; }
+        cur_buf = L.nx_buf;
+        rows_new = nrows; W = nW;
+    }
+    P.tail_units = tail_units;
+    P.x_units = (x_units + 7) & ~7; P.y_units = (y_units + 7) & ~7;
+    // weight slots, top-down: odd layers end at the top, an even layer sits just below its odd successor's
+    // slot (sizes are non-decreasing with depth, so it also clears its odd predecessor).
+    auto wsz = [&](int l) { return l >= 1 && l < OWW_N_CONV ? (P.L[l].w_bytes + 127) & ~127 : 0; };
+    for (int l = 1; l < OWW_N_CONV; ++l)
+        P.L[l].w_smem = (l & 1) ? kTop - wsz(l) : kTop - wsz(l + 1) - wsz(l);
+    for (int l = 1; l < OWW_N_CONV; ++l) {
+        // while layer l runs, its own slot and the prefetch of layer l+1 are live, next to the activations in use
+        int w_low = P.L[l].w_smem;
+        if (l + 1 < OWW_N_CONV && P.L[l + 1].w_smem < w_low) w_low = P.L[l + 1].w_smem;
+        int act_high = kActBase + use_x[l] * 16;
+        if (use_y[l]) act_high = kActBase + (P.x_units + use_y[l]) * 16;
+        // the phase before (l-1) writes this layer's input while slot l is being prefetched
+        int prev_high = kActBase + use_x[l - 1] * 16;
+        if (use_y[l - 1]) prev_high = kActBase + (P.x_units + use_y[l - 1]) * 16;
+        if (act_high > w_low || prev_high > P.L[l].w_smem)
+            return oww_fail(ctx, OWW_EUNSUPPORTED, "fused-CNN smem plan does not fit at layer %d (G=%d)", l, G);
+        if (l >= 2 && wsz(l) < wsz(l - 1)) return oww_fail(ctx, OWW_EUNSUPPORTED, "weight sizes must not shrink with depth");
+    }
+    P.w_total_bytes = (int)w_off;
+    P.smem_bytes = kTop;
+    *out = P;
+    return OWW_OK;
+}
+
+int oww_inc_setup(oww_ctx* ctx, const float* h_blob) {
+    // packed blob for the fused kernel: per layer fp16 [3][CGP][NP][8] | scale[NP] | bias[NP], 128-byte aligned
+    IncPlan P;
+    int rc = oww_inc_build_plan(ctx, kIncMaxG, kIncMaxG, &P);
+    if (rc) return rc;
+    std::vector<uint8_t> blob(P.w_total_bytes, 0);
+    size_t off = 0;
+    for (int li = 0; li < OWW_N_CONV; ++li) {
+        const ConvLayer& C = ctx->conv[li];
+        const size_t nw = (size_t)C.kh * C.kw * C.cin * C.cout;
+        const float* w = h_blob + off; const float* sc = w + nw; const float* bi = sc + C.cout;
+        off += nw + 2 * (size_t)C.cout;
+        if (li == 0) continue;
+        const IncLayer& L = P.L[li];
+        __half* hw = reinterpret_cast<__half*>(blob.data() + L.w_off);
+        for (int j = 0; j < 3; ++j)
+            for (int g = 0; g < L.cgp; ++g)
+                for (int n = 0; n < L.np; ++n)
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = g * 8 + e;
+                        const float v = (c < C.cin && n < C.cout) ? w[((size_t)j * C.cin + c) * C.cout + n] : 0.f;
+                        hw[(((size_t)j * L.cgp + g) * L.np + n) * 8 + e] = __float2half_rn(v);
+                    }
+        float* sb = reinterpret_cast<float*>(blob.data() + L.w_off + (size_t)3 * L.cgp * L.np * 16);
+        for (int n = 0; n < L.np; ++n) { sb[n] = n < C.cout ? sc[n] : 0.f; sb[L.np + n] = n < C.cout ? bi[n] : 0.f; }
+    }
+    if (!ctx->d_inc_w) OWW_CUDA(ctx, cudaMalloc(&ctx->d_inc_w, blob.size()));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_inc_w, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    return OWW_OK;
+}
+
+int oww_inc_alloc_streams(oww_ctx* ctx) {
+    int rc = oww_inc_build_plan(ctx, kIncMaxG, ctx->n_streams, &ctx->inc_plan);
+    if (rc) return rc;
+    const size_t bytes = (size_t)ctx->inc_plan.n_groups * ctx->inc_plan.tail_units * 16;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(ctx->d_inc_tails[i]); ctx->d_inc_tails[i] = nullptr;
+        OWW_CUDA(ctx, cudaMalloc(&ctx->d_inc_tails[i], bytes));
+        OWW_CUDA(ctx, cudaMemset(ctx->d_inc_tails[i], 0, bytes));
+    }
+    ctx->inc_cur = 0;
+    ctx->inc_primed = false;
+    OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
+    return OWW_OK;
+}
+
+// One incremental CNN pass for every stream: mel rows ending `back` rows before the newest.
+int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
+    IncArgs a;
+    a.plan = ctx->inc_plan;
+    a.mel = ctx->d_mel_ring; a.mel_count = ctx->d_mel_count; a.mel_stride = (int64_t)ctx->mel_rows * 32;
+    a.mel_mask = ctx->mel_rows - 1; a.back = back;
+    a.w0 = ctx->conv[0].d_w; a.s0 = ctx->conv[0].d_scale; a.b0 = ctx->conv[0].d_bias;
+    a.wblob = reinterpret_cast<const uint8_t*>(ctx->d_inc_w);
+    a.tails_in = reinterpret_cast<const uint4*>(ctx->d_inc_tails[ctx->inc_cur]);
+    a.tails_out = reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur ^ 1]);
+    a.emb = d_emb; a.B = ctx->n_streams;
+    const int grid = a.plan.n_groups < ctx->sm_count ? a.plan.n_groups : ctx->sm_count;
+    tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    OWW_LAUNCH_CHECK(ctx);
+    ctx->inc_cur ^= 1;
+    return OWW_OK;
+}
+
+// Tail capture hook for the full-window tensor-core pyramid (cnn_tc.cu): called after the layer
+// whose (possibly pooled) output feeds a (3,1) convolution.
+int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
+                    int stream0, cudaStream_t s) {
+    const IncLayer& L = ctx->inc_plan.L[layer];
+    if (L.nx_tail_off < 0) return OWW_OK;
+    const int Wp = W + 1;
+    const int64_t total = (int64_t)n_win * L.cg_out * 2 * Wp;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    tc_capture_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(planes), plane_pitch, T, Wp, L.cg_out, win0, n_win,
+                                          stream0, ctx->inc_plan.G, L.nx_tail_off, ctx->inc_plan.tail_units,
+                                          reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur]));
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}

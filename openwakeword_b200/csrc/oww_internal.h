@@ -31,6 +31,24 @@ struct Head {
     std::vector<size_t> w_off, b_off, g_off, h_off;   // float offsets per layer
 };
 
+// ---- fused incremental CNN (cnn_tc_inc.cu): per-layer geometry for a group of G streams --------
+struct IncLayer {            // "units" are 16-byte channel-group units (8 fp16 channels of one position)
+    int kh3, final;
+    int W, Wp;               // input width, Wp = W + 1 (one zero pad column)
+    int rows_in, T_out, M;   // input rows (2 tails + new for (3,1)), output rows, positions to compute
+    int cg_in, cgp, np, cg_out;
+    int in_buf, out_buf;     // 0 = X, 1 = Y
+    int in_pitch;            // units per plane of the input buffer
+    int tap[3];              // unit offset of each conv tap relative to the output position
+    int pool_t, pool_f, tmp_pitch;          // max-pool after the conv; pitch of the unpooled temp (in out_buf)
+    int nx_buf, nx_pitch, nx_W, nx_Wp, nx_rows_new, nx_t_off, nx_tail_off;   // what this phase leaves for layer l+1
+    int w_off, w_bytes, w_smem;             // packed weights: blob offset, size, smem byte offset
+};
+struct IncPlan {
+    int G, n_groups, tail_units, x_units, y_units, w_total_bytes, smem_bytes, pad_;
+    IncLayer L[OWW_N_CONV];
+};
+
 struct oww_ctx {
     oww_config cfg;
     int device = 0;
@@ -82,11 +100,12 @@ struct oww_ctx {
     void* d_tc_act[2] = {nullptr, nullptr};   // fp16 channel-group planes, ping-pong
     size_t tc_act_units = 0;
 
-    // incremental-mode state
-    float* d_tails = nullptr;        // per-stream cached rows (layout in cnn_incremental.cu)
-    float* d_inc_act[2] = {nullptr, nullptr};
-    size_t inc_act_floats = 0;
-    int* d_inc_valid = nullptr;      // [B] 1 = tails hold a consistent pyramid
+    // fused incremental path (cnn_tc_inc.cu)
+    void* d_inc_w = nullptr;         // packed per-layer {fp16 weights, scale, bias}
+    void* d_inc_tails[2] = {nullptr, nullptr};   // [n_groups][tail_units] 16-byte units, double-buffered per step
+    int inc_cur = 0;                 // tails buffer the next step reads
+    bool inc_primed = false;         // tails describe the newest window of every stream
+    IncPlan inc_plan;
 
     // host staging for oww_step_host
     cudaStream_t own_stream = nullptr;
@@ -150,13 +169,24 @@ struct WindowSrc {
 int oww_cnn_clip_fp32(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s);
 int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s);
 // mode dispatch (fp32 window / tcgen05 window) with sub-batching over ctx->window_batch
-int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s);
+int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s, bool capture_tails = false);
 
 // ---- cnn_tc.cu ----
 int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob);
 size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows);
 int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
 // fp32 pyramid with an optional early stop that leaves NHWC fp32 [n][T][W][C] of `stop_layer` in d_dbg
+// capture descriptor: which local windows of a full-window pass are the newest window of which streams
+struct TailCapture { int win0, n_win, stream0; };
+int oww_cnn_tc_pyramid_cap(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, const TailCapture* cap, cudaStream_t s);
+
+// ---- cnn_tc_inc.cu ----
+int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out);
+int oww_inc_setup(oww_ctx* ctx, const float* h_blob);
+int oww_inc_alloc_streams(oww_ctx* ctx);
+int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s);
+int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
+                    int stream0, cudaStream_t s);
 int oww_cnn_fp32_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
 
 // ---- heads.cu ----

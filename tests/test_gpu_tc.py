@@ -82,3 +82,35 @@ def test_tc_scores_vs_fp32_and_oracle(torch_cuda, built_library):
     d = np.abs(res[0] - res[TC])
     print("max |score_tc - score_fp32| =", d.max(), " mean", d.mean())
     assert d.max() < 1e-3
+
+
+def test_tc_incremental_vs_window_modes(torch_cuda, built_library):
+    """cnn_mode 3 (fused incremental kernel, tails in HBM) against cnn_mode 2 (full window, same fp16
+    quantisation points) and cnn_mode 0 (fp32): ragged group (B % 4 != 0), a 2-chunk step, a mid-stream
+    reset of two streams (forces a re-prime) and the first-chunk-of-5-rows case."""
+    from openwakeword_b200.engine import StreamEngine
+    rng = np.random.default_rng(21)
+    B = 37
+    hs = [head("alexa_v0.1"), head("timer_v0.1")]
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    plan = [1, 1, 1, 2, 1, 1, 1, 1, 1]
+    pcm = np.clip(rng.normal(0, 2500, (B, sum(plan) * 1280)), -32768, 32767).astype(np.int16)
+    pcm[::4] = rng.integers(-1000, 1000, (len(pcm[::4]), pcm.shape[1]))
+    pcm[1::4, : pcm.shape[1] // 2] = 0
+    out, feats, mels = {}, {}, {}
+    for mode in (0, 2, 3):
+        eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=mode, max_chunks=2)
+        pos, rows = 0, []
+        for si, n in enumerate(plan):
+            if si == 6:
+                eng.reset(fi, stream_ids=[3, 36])
+            rows.append(eng.step_host(np.ascontiguousarray(pcm[:, pos:pos + n * 1280]), n).copy())
+            pos += n * 1280
+        out[mode] = np.stack(rows, 1)
+        feats[mode] = np.stack([eng.ctx.get_features(b, 12) for b in (0, 3, 35, 36)])
+    d32 = np.abs(out[3] - out[2])
+    print("max |score_inc - score_window_tc| =", d32.max(), "  max |feat diff| =", np.abs(feats[3] - feats[2]).max())
+    print("max |score_inc - score_fp32| =", np.abs(out[3] - out[0]).max())
+    assert np.abs(feats[3] - feats[2]).max() < 2e-3
+    assert d32.max() < 2e-4
+    assert np.abs(out[3] - out[0]).max() < 1e-3
