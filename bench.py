@@ -36,6 +36,9 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_WINDOW = 2 * 41955840
 STREAMS_PER_GPU = 1024
 CHUNK = 1280
+# dram__bytes_read.sum + dram__bytes_write.sum of the CNN stage for one 1024-stream step, from the ncu --set full
+# captures summarised in profiles/README.md (bytes per step; None = not captured for that mode)
+TRAFFIC = {2: 1.177e9, 3: 2.44e7}
 METRIC = "80ms audio-frames/sec (concurrent streams)"
 UNIT = "frames/s"
 
@@ -294,6 +297,19 @@ def run_own_arm(args):
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     achieved_tf = B * FLOPS_PER_WINDOW / (cnn_ms * 1e-3) / 1e12
+    exec_flops = {0: FLOPS_PER_WINDOW, 2: FLOPS_PER_WINDOW, 3: 2 * 5612544}[args.cnn_mode]
+    executed_tf = B * exec_flops / (cnn_ms * 1e-3) / 1e12
+    mode_note = {
+        0: "fp32 CUDA-core path, full 76x32 window per frame: executed FLOPs == algorithmic FLOPs",
+        2: "tcgen05 fp16-operand/fp32-accumulate, full window per frame: executed == algorithmic (N/K padding excluded)",
+        3: "tcgen05 fused incremental kernel: the reference-algorithmic 83.9 MFLOP/frame is delivered by executing only the "
+           "8 new mel rows per frame (11.2 MFLOP, SURVEY.md F10/8d) - 'achieved' is reference-algorithmic, "
+           "'executed_tflops' is what the tensor pipe actually issued",
+    }[args.cnn_mode]
+    kernel_name = {0: "embedding CNN stage: 20 conv_kernel + 5 pool_kernel launches (cnn_fp32.cu)",
+                   2: "embedding CNN stage: tc_conv0 + 19 tc_conv_kernel + 5 tc_pool launches (cnn_tc.cu)",
+                   3: "embedding CNN stage: tc_inc_kernel, one fused launch (cnn_tc_inc.cu) + ring append"}[args.cnn_mode]
+    dtype = "f32" if args.cnn_mode == 0 else "f16 operands / f32 accumulate (mel, BN, heads in f32)"
     value = n_total * K / (ms_dev * 1e-3)
     e2e_v = n_total * K / (ms_e2e * 1e-3)
 
@@ -313,7 +329,7 @@ def run_own_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": dtype, "data": "synthetic",
         "config": {"workload": "configs[1]: 1024 concurrent synthetic 16 kHz streams per GPU, 80 ms frames, 1 wake-word head",
                    "streams_per_gpu": B, "heads": 1, "cnn_mode": args.cnn_mode,
                    "l2": f"inputs larger than L2: {POOL} distinct PCM batches ({POOL * B * CHUNK * 2 / 1e6:.0f} MB) cycled",
@@ -323,11 +339,12 @@ def run_own_arm(args):
         "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": B * CHUNK * 2 * world, "d2h_bytes_per_step": B * eng.n_cols * 4 * world},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "embedding CNN stage (20 conv + 5 max-pool + ring append launches)",
+        "roofline": {"bound": "tensor", "kernel": kernel_name,
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "peak_source": peak_src, "traffic": None,
-                     "flops_per_unit": FLOPS_PER_WINDOW, "units_per_launch": B, "stage_ms": stage,
-                     "note": "fp32 CUDA-core path: executed FLOPs == algorithmic FLOPs (full 76x32 window per frame)"},
+                     "executed_tflops": executed_tf, "executed_frac": executed_tf / peak_tf,
+                     "peak_source": peak_src, "traffic": TRAFFIC.get(args.cnn_mode),
+                     "flops_per_unit": FLOPS_PER_WINDOW, "executed_flops_per_unit": exec_flops,
+                     "units_per_launch": B, "stage_ms": stage, "note": mode_note},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -343,7 +360,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--cnn-mode", type=int, default=0)
+    ap.add_argument("--cnn-mode", type=int, default=3, help="0 fp32 window, 2 tcgen05 window, 3 tcgen05 fused incremental")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
