@@ -118,9 +118,15 @@ int oww_reset(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_f
  * per head the element-wise max over the n_chunks window positions (model.py:287-298).          */
 int oww_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks,
              float* d_scores, void* stream);
-/* Same, host buffers: H2D of the PCM and D2H of the scores through pinned staging on the
- * handle's own stream; returns after the scores have landed in h_scores.                        */
+/* Same, host buffers: H2D of the PCM and D2H of the scores through pinned staging inside the handle;
+ * returns after the scores have landed in h_scores (= submit + collect).                          */
 int oww_step_host(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, float* h_scores);
+/* Pipelined form for serving loops: submit copies the PCM to pinned memory, enqueues H2D (copy stream),
+ * the step (compute stream, in submission order) and the D2H of the scores, and returns a ticket (0/1)
+ * without waiting; at most two tickets may be in flight, so the H2D of step k+1 overlaps the kernels
+ * of step k.  collect blocks until that step's scores are in h_scores.                          */
+int oww_step_host_submit(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, int* ticket);
+int oww_step_host_collect(oww_ctx* ctx, int ticket, float* h_scores);
 /* last n rows of one stream's feature ring, ending `back` rows before the newest -> h_out[n][96];
  * rows older than the ring holds come back as zeros.  Synchronises.                             */
 int oww_get_features(oww_ctx* ctx, int stream_id, int n, int back, float* h_out);

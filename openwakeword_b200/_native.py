@@ -48,6 +48,8 @@ _SIGNATURES = {
     "oww_reset": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
     "oww_step": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "oww_step_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    "oww_step_host_submit": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(C.c_int)]),
+    "oww_step_host_collect": (C.c_int, [_P, C.c_int, _P]),
     "oww_get_features": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "oww_get_mel": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "oww_embed_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
@@ -187,6 +189,16 @@ class Context:
         assert pcm.dtype == np.int16 and pcm.flags.c_contiguous
         assert scores_out.dtype == np.float32 and scores_out.flags.c_contiguous
         self._check(self.lib.oww_step_host(self.h, _ptr(pcm), pcm.shape[1], n_chunks, _ptr(scores_out)))
+
+    def step_host_submit(self, pcm, n_chunks):
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous
+        t = C.c_int(-1)
+        self._check(self.lib.oww_step_host_submit(self.h, _ptr(pcm), pcm.shape[1], n_chunks, C.byref(t)))
+        return t.value
+
+    def step_host_collect(self, ticket, scores_out):
+        assert scores_out.dtype == np.float32 and scores_out.flags.c_contiguous
+        self._check(self.lib.oww_step_host_collect(self.h, ticket, _ptr(scores_out)))
 
     def get_features(self, stream_id, n, back=0):
         out = np.empty((n, 96), np.float32)

@@ -184,6 +184,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
         delete ctx; return OWW_EUNSUPPORTED;
     }
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     fill_layer_table(ctx);
     *out = ctx;
     return OWW_OK;
@@ -195,14 +196,18 @@ void oww_destroy(oww_ctx* ctx) {
     if (ctx->clip_ctx) { oww_ctx* c = ctx->clip_ctx; ctx->clip_ctx = nullptr; free_streams(c);
         cudaStreamDestroy(c->own_stream);
         cudaFree(c->d_tc_act[0]); cudaFree(c->d_tc_act[1]);
-        cudaFree(c->d_pcm_stage); delete c; }
+        cudaFree(c->slot[0].d_pcm); delete c; }
     free_streams(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
     cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
     cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w);
     for (auto& h : ctx->heads) cudaFree(h.d_blob);
-    cudaFreeHost(ctx->h_pcm_pinned); cudaFreeHost(ctx->h_scores_pinned);
-    cudaFree(ctx->d_pcm_stage); cudaFree(ctx->d_scores_stage);
+    for (auto& S : ctx->slot) {
+        cudaFreeHost(S.h_pcm); cudaFreeHost(S.h_scores); cudaFree(S.d_pcm); cudaFree(S.d_scores);
+        if (S.done) cudaEventDestroy(S.done);
+        if (S.h2d_done) cudaEventDestroy(S.h2d_done);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto e : ctx->ev) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -358,43 +363,74 @@ int oww_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunk
     return step_core(ctx, d_pcm, pcm_stride, n_chunks, d_scores, ctx->n_out_total, (cudaStream_t)stream);
 }
 
-int oww_step_host(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, float* h_scores) {
-    if (!ctx || !h_pcm || !h_scores) return oww_fail(ctx, OWW_EINVAL, "null argument");
+int oww_step_host_submit(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, int* ticket) {
+    if (!ctx || !h_pcm || !ticket) return oww_fail(ctx, OWW_EINVAL, "null argument");
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
     const int B = ctx->n_streams;
     if (B <= 0) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
+    if (n_chunks < 1 || n_chunks > ctx->cfg.max_chunks)
+        return oww_fail(ctx, OWW_EINVAL, "n_chunks=%d outside [1,%d]", n_chunks, ctx->cfg.max_chunks);
+    const int si = ctx->next_slot;
+    oww_ctx::HostSlot& S = ctx->slot[si];
+    if (S.busy) return oww_fail(ctx, OWW_EINVAL, "both host slots are in flight: collect a ticket first");
     const size_t row = (size_t)n_chunks * OWW_SAMPLES_PER_CHUNK;
     const size_t pcm_bytes = (size_t)B * row * sizeof(int16_t);
     const size_t sc_bytes = (size_t)B * std::max(ctx->n_out_total, 1) * sizeof(float);
-    if (ctx->h_pcm_bytes < pcm_bytes) {
-        cudaFreeHost(ctx->h_pcm_pinned); cudaFree(ctx->d_pcm_stage); ctx->h_pcm_pinned = nullptr; ctx->d_pcm_stage = nullptr;
-        OWW_CUDA(ctx, cudaMallocHost(&ctx->h_pcm_pinned, pcm_bytes));
-        OWW_CUDA(ctx, cudaMalloc(&ctx->d_pcm_stage, pcm_bytes));
-        ctx->h_pcm_bytes = ctx->d_pcm_bytes = pcm_bytes;
+    if (!S.done) { OWW_CUDA(ctx, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming)); OWW_CUDA(ctx, cudaEventCreateWithFlags(&S.h2d_done, cudaEventDisableTiming)); }
+    if (S.pcm_bytes < pcm_bytes) {
+        cudaFreeHost(S.h_pcm); cudaFree(S.d_pcm); S.h_pcm = nullptr; S.d_pcm = nullptr; S.pcm_bytes = 0;
+        OWW_CUDA(ctx, cudaMallocHost(&S.h_pcm, pcm_bytes));
+        OWW_CUDA(ctx, cudaMalloc(&S.d_pcm, pcm_bytes));
+        S.pcm_bytes = pcm_bytes;
     }
-    if (ctx->h_scores_bytes < sc_bytes) {
-        cudaFreeHost(ctx->h_scores_pinned); cudaFree(ctx->d_scores_stage); ctx->h_scores_pinned = nullptr; ctx->d_scores_stage = nullptr;
-        OWW_CUDA(ctx, cudaMallocHost(&ctx->h_scores_pinned, sc_bytes));
-        OWW_CUDA(ctx, cudaMalloc(&ctx->d_scores_stage, sc_bytes));
-        ctx->h_scores_bytes = ctx->d_scores_bytes = sc_bytes;
+    if (S.sc_bytes < sc_bytes) {
+        cudaFreeHost(S.h_scores); cudaFree(S.d_scores); S.h_scores = nullptr; S.d_scores = nullptr; S.sc_bytes = 0;
+        OWW_CUDA(ctx, cudaMallocHost(&S.h_scores, sc_bytes));
+        OWW_CUDA(ctx, cudaMalloc(&S.d_scores, sc_bytes));
+        S.sc_bytes = sc_bytes;
     }
     // pack rows into the pinned buffer (pcm_stride may exceed the row length)
     if (pcm_stride == (int64_t)row) {
-        std::memcpy(ctx->h_pcm_pinned, h_pcm, pcm_bytes);
+        std::memcpy(S.h_pcm, h_pcm, pcm_bytes);
     } else {
         for (int b = 0; b < B; ++b)
-            std::memcpy(ctx->h_pcm_pinned + (size_t)b * row, h_pcm + (size_t)b * pcm_stride, row * sizeof(int16_t));
+            std::memcpy(S.h_pcm + (size_t)b * row, h_pcm + (size_t)b * pcm_stride, row * sizeof(int16_t));
     }
+    OWW_CUDA(ctx, cudaMemcpyAsync(S.d_pcm, S.h_pcm, pcm_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    OWW_CUDA(ctx, cudaEventRecord(S.h2d_done, ctx->copy_stream));
     cudaStream_t s = ctx->own_stream;
-    OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_pcm_stage, ctx->h_pcm_pinned, pcm_bytes, cudaMemcpyHostToDevice, s));
-    int rc = step_core(ctx, ctx->d_pcm_stage, (int64_t)row, n_chunks, ctx->d_scores_stage, ctx->n_out_total, s);
+    OWW_CUDA(ctx, cudaStreamWaitEvent(s, S.h2d_done, 0));
+    int rc = step_core(ctx, S.d_pcm, (int64_t)row, n_chunks, S.d_scores, ctx->n_out_total, s);
     if (rc) return rc;
     if (ctx->n_out_total > 0)
-        OWW_CUDA(ctx, cudaMemcpyAsync(ctx->h_scores_pinned, ctx->d_scores_stage, (size_t)B * ctx->n_out_total * sizeof(float),
+        OWW_CUDA(ctx, cudaMemcpyAsync(S.h_scores, S.d_scores, (size_t)B * ctx->n_out_total * sizeof(float),
                                       cudaMemcpyDeviceToHost, s));
-    OWW_CUDA(ctx, cudaStreamSynchronize(s));
-    if (ctx->n_out_total > 0) std::memcpy(h_scores, ctx->h_scores_pinned, (size_t)B * ctx->n_out_total * sizeof(float));
+    OWW_CUDA(ctx, cudaEventRecord(S.done, s));
+    S.busy = true;
+    ctx->next_slot = si ^ 1;
+    *ticket = si;
     return OWW_OK;
+}
+
+int oww_step_host_collect(oww_ctx* ctx, int ticket, float* h_scores) {
+    if (!ctx || !h_scores) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (ticket < 0 || ticket > 1 || !ctx->slot[ticket].busy) return oww_fail(ctx, OWW_EINVAL, "ticket %d is not in flight", ticket);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    oww_ctx::HostSlot& S = ctx->slot[ticket];
+    OWW_CUDA(ctx, cudaEventSynchronize(S.done));
+    if (ctx->n_out_total > 0) std::memcpy(h_scores, S.h_scores, (size_t)ctx->n_streams * ctx->n_out_total * sizeof(float));
+    S.busy = false;
+    return OWW_OK;
+}
+
+int oww_step_host(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride, int n_chunks, float* h_scores) {
+    if (!ctx || !h_pcm || !h_scores) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    for (int i = 0; i < 2; ++i)
+        if (ctx->slot[i].busy) return oww_fail(ctx, OWW_EINVAL, "a submitted step is still in flight: collect it first");
+    int ticket = -1;
+    int rc = oww_step_host_submit(ctx, h_pcm, pcm_stride, n_chunks, &ticket);
+    if (rc) return rc;
+    return oww_step_host_collect(ctx, ticket, h_scores);
 }
 
 int oww_get_features(oww_ctx* ctx, int stream_id, int n, int back, float* h_out) {
@@ -493,16 +529,16 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
         if (c->n_streams != m) { if ((rc = oww_set_streams(c, m))) { ctx->err = c->err; break; } }
         if ((rc = oww_reset(c, nullptr, m, h_feature_init, h_feature_init ? n_rows : OWW_INIT_FEATURE_ROWS))) { ctx->err = c->err; break; }
         const size_t stage_bytes = (size_t)m * OWW_SAMPLES_PER_CHUNK * sizeof(int16_t);
-        if (c->d_pcm_bytes < stage_bytes) {
-            cudaFree(c->d_pcm_stage); c->d_pcm_stage = nullptr;
-            OWW_CUDA(ctx, cudaMalloc(&c->d_pcm_stage, stage_bytes));
-            c->d_pcm_bytes = stage_bytes;
+        if (c->slot[0].pcm_bytes < stage_bytes) {
+            cudaFree(c->slot[0].d_pcm); c->slot[0].d_pcm = nullptr;
+            OWW_CUDA(ctx, cudaMalloc(&c->slot[0].d_pcm, stage_bytes));
+            c->slot[0].pcm_bytes = stage_bytes;
         }
         for (int st = 0; st < steps; ++st) {
             unsigned grid = (unsigned)std::min<int64_t>(((int64_t)m * OWW_SAMPLES_PER_CHUNK + 255) / 256, (int64_t)ctx->sm_count * 32);
-            gather_chunk_kernel<<<grid, 256, 0, s>>>(d_pcm + (size_t)c0 * n_samples, m, n_samples, pad_samples, st, c->d_pcm_stage);
+            gather_chunk_kernel<<<grid, 256, 0, s>>>(d_pcm + (size_t)c0 * n_samples, m, n_samples, pad_samples, st, c->slot[0].d_pcm);
             c->launches++;
-            rc = step_core(c, c->d_pcm_stage, OWW_SAMPLES_PER_CHUNK, 1,
+            rc = step_core(c, c->slot[0].d_pcm, OWW_SAMPLES_PER_CHUNK, 1,
                            d_scores + ((size_t)c0 * steps + st) * ctx->n_out_total, steps * ctx->n_out_total, s);
             if (rc) { ctx->err = c->err; break; }
         }

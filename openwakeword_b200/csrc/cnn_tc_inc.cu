@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     // [0, 2048): barriers, TMEM slot, layer-0 weights.  Activations grow from 2048 up; the per-layer weight
     // slots sit at the top of the arena (offsets in the plan, checked against the activation extents).
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kIncAcc);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kIncAcc);
     float* s_l0 = reinterpret_cast<float*>(smem + 256);              // 9*24 + 24 + 24 floats
     uint4* bufX = reinterpret_cast<uint4*>(smem + 2048);
     uint4* bufY = bufX + P.x_units;
@@ -66,10 +66,12 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     auto wempty = [&](int i) { return bar0 + 8u * (2 + i); };
     auto tfull = [&](int s) { return bar0 + 8u * (4 + s); };
     auto tempty = [&](int s) { return bar0 + 8u * (4 + kIncAcc + s); };
+    const uint32_t tails_bar = bar0 + 8u * (4 + 2 * kIncAcc);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), 1); }
         for (int s = 0; s < kIncAcc; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), kIncEpiWarps * 32); }
+        mbar_init(tails_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 9 * 24; i += kIncThreads) s_l0[i] = a.w0[i];
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         uint32_t wpar[2] = {0, 0};
         int acc = 0; uint32_t acc_par = 0;
         bool have_prev = false; int prev_i = 0;
+        uint32_t tails_par = 0;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             for (int l = 1; l < OWW_N_CONV; ++l) {
                 const IncLayer& L = P.L[l];
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 if (lane == 0) {
                     // layer l-1's epilogue (which reads scale/bias from its weight slot) is done: free that slot
                     if (have_prev) mbar_arrive(wempty(prev_i));
+                    if (L.kh3) { mbar_wait(tails_bar, tails_par); tails_par ^= 1; }   // rows 0..1 of the input have landed
                     const int i = l & 1;
                     mbar_wait(wfull(i), wpar[i]);
                     wpar[i] ^= 1;
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_par = 0;
         uint32_t epar[2] = {0, 0};
+        uint32_t epi_tails_par = 0;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
@@ -158,18 +163,13 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 // ---- (a) tails of the buffer this phase fills (rows 0..1) and front guards.  In a pool phase that
                 //      buffer is still the conv's INPUT, so this is deferred until the tiles are drained. ----
                 auto fill_tails_and_guards = [&]() {
-                    if (L.nx_tail_off >= 0) {
-                        const int per = 2 * G * L.nx_Wp;
-                        for (int i = et; i < L.cg_out * per; i += kIncEpiWarps * 32) {
-                            const int pl = i / per, u = i - pl * per;
-                            const int g = (u / L.nx_Wp) % G;
-                            const bool live = grp * G + g < a.B;
-                            uint4 v = make_uint4(0, 0, 0, 0);
-                            if (live) v = __ldg(tin + L.nx_tail_off + i);
-                            nx[pl * L.nx_pitch + 1 + u] = v;
-                            if (L.nx_rows_new == 1 && u >= G * L.nx_Wp && live)      // single new row: old tail row 1 becomes row 0
-                                tout[L.nx_tail_off + pl * per + (u - G * L.nx_Wp)] = v;
-                        }
+                    if (L.nx_tail_off >= 0 && et == 0) {
+                        // rows 0..1 of every plane <- the tails the previous step left in HBM: one bulk copy per plane,
+                        // asynchronous; the MMA warp waits on tails_bar before it issues layer l+1
+                        const uint32_t per_bytes = (uint32_t)(2 * G * L.nx_Wp) * 16u;
+                        mbar_expect_tx(tails_bar, per_bytes * L.cg_out);
+                        for (int pl = 0; pl < L.cg_out; ++pl)
+                            bulk_g2s(smem_u32(nx + pl * L.nx_pitch + 1), tin + L.nx_tail_off + pl * (2 * G * L.nx_Wp), per_bytes, tails_bar);
                     }
                     if (!L.final && et < L.cg_out) nx[et * L.nx_pitch] = make_uint4(0, 0, 0, 0);
                 };
@@ -294,6 +294,16 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         // ---- max-pool: tmp (unpooled conv output) -> nx ----
                         named_bar_sync(2, kIncEpiWarps * 32);          // every tile drained: the conv input buffer is free
                         fill_tails_and_guards();
+                        if (L.nx_tail_off >= 0 && L.nx_rows_new == 1) {
+                            // single new row: next step's tails are (old tail row 1, new row); copy the old row once it landed
+                            mbar_wait(tails_bar, epi_tails_par);
+                            const int perrow = G * L.nx_Wp;
+                            for (int i = et; i < L.cg_out * perrow; i += kIncEpiWarps * 32) {
+                                const int pl = i / perrow, u = i - pl * perrow;
+                                if (grp * G + (u / L.nx_Wp) < a.B)
+                                    tout[L.nx_tail_off + pl * 2 * perrow + u] = nx[pl * L.nx_pitch + 1 + perrow + u];
+                            }
+                        }
                         const uint4* src = L.out_buf ? bufY : bufX;
                         const int T2 = L.T_out / L.pool_t;
                         const int per = T2 * G * L.nx_Wp;
@@ -324,6 +334,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         }
                     }
                 }
+                if (L.nx_tail_off >= 0) epi_tails_par ^= 1;
                 // ---- phase done: make generic-proxy smem writes visible to the tensor core ----
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 if (l < OWW_N_CONV - 1) {

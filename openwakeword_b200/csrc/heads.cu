@@ -14,6 +14,8 @@ namespace {
 constexpr int KC = 32;          // K chunk of the first (wide) layer
 constexpr int NTHREADS = 256;
 constexpr int HMAX = 256;       // widest hidden / output layer supported
+constexpr int kStages = 3;      // cp.async ring depth of the first layer
+constexpr int XS_LD = KC + 4;   // x tile row pitch (floats): 16-byte aligned rows, conflict-light
 
 struct HeadDev {
     const float* blob;
@@ -26,49 +28,82 @@ struct HeadsArgs {
     HeadDev head[16];
     FeatSrc src;
     int n; float* out; int out_stride; int combine_max;
+    int dmax;                       // widest layer over the heads of this launch, rounded up to 4
 };
 
 __device__ __forceinline__ int next_pow2_32(int d) { int p = 32; while (p < d) p <<= 1; return p; }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;                      // src-size 0 -> 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// First (wide) layer: out[tb][d] = sum_k x[tb][k] W[k][d], K = n_in*96, x gathered from the feature ring.
+// K is consumed in chunks of KC=32 through a kStages-deep cp.async ring (x tile + W tile per stage) so the
+// global/L2 latency of chunk c+2 hides under the FMAs of chunk c.
 // acc[i] holds output (row = rgrp + R*i, col = d) for this thread; DP = padded layer width.
 template <int TB, int DP>
-__device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& src, int s0, int n, float (*xs)[KC + 1],
-                                             float* ws, float* acc) {
+__device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& src, int s0, int n, float* xs_all,
+                                             float* ws_all, int ws_stage, float* acc) {
     constexpr int R = NTHREADS / DP, NR = TB / R;
     const int tid = threadIdx.x, d = tid % DP, rgrp = tid / DP;
     const int D = H.dims[1], K = H.dims[0];
     const float* W = H.blob + H.w_off[0];
+    const int n_chunks = K / KC;
 #pragma unroll
     for (int i = 0; i < NR; ++i) acc[i] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += KC) {
-        const int frow = k0 / 96, fcol = k0 % 96;
-        for (int q = tid; q < TB * KC; q += NTHREADS) {
-            const int tb = q / KC, kk = q % KC;
-            const int s = s0 + tb;
-            float v = 0.f;
-            if (s < n) {
-                if (src.count) {
-                    const int r = src.count[s] - src.back - H.n_in + frow;
-                    v = r >= 0 ? __ldg(src.base + (int64_t)s * src.stride + (int64_t)(r & src.rows_mask) * 96 + fcol + kk)
-                               : 0.f;
-                } else {
-                    v = __ldg(src.base + (int64_t)s * src.stride + (int64_t)frow * 96 + fcol + kk);
+    auto issue = [&](int c) {
+        if (c < n_chunks) {
+            const int k0 = c * KC;
+            const int frow = k0 / 96, fcol = k0 % 96;
+            float* xs = xs_all + (c % kStages) * (TB * XS_LD);
+            float* ws = ws_all + (c % kStages) * ws_stage;
+            for (int q = tid; q < TB * (KC / 4); q += NTHREADS) {
+                const int tb = q / (KC / 4), k4 = (q % (KC / 4)) * 4;
+                const int s = s0 + tb;
+                const float* g = src.base;
+                bool ok = s < n;
+                if (ok) {
+                    if (src.count) {
+                        const int r = src.count[s] - src.back - H.n_in + frow;
+                        ok = r >= 0;
+                        g = src.base + (int64_t)s * src.stride + (int64_t)(r & src.rows_mask) * 96 + fcol + k4;
+                    } else {
+                        g = src.base + (int64_t)s * src.stride + (int64_t)frow * 96 + fcol + k4;
+                    }
                 }
+                cp_async16(xs + tb * XS_LD + k4, g, ok);
             }
-            xs[tb][kk] = v;
+            if ((D & 3) == 0) {
+                for (int q = tid; q < KC * D / 4; q += NTHREADS) cp_async16(ws + q * 4, W + (int64_t)k0 * D + q * 4, true);
+            } else {                                   // odd widths: plain loads (visible after the next __syncthreads)
+                for (int q = tid; q < KC * D; q += NTHREADS) ws[q] = __ldg(W + (int64_t)k0 * D + q);
+            }
         }
-        for (int q = tid; q < KC * D; q += NTHREADS) ws[q] = __ldg(W + (int64_t)k0 * D + q);
-        __syncthreads();
+        cp_async_commit();
+    };
+    for (int c = 0; c < kStages - 1; ++c) issue(c);
+    for (int c = 0; c < n_chunks; ++c) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();                                   // chunk c landed for everyone; stage (c-1)%S is free
+        issue(c + kStages - 1);
+        const float* xs = xs_all + (c % kStages) * (TB * XS_LD);
+        const float* ws = ws_all + (c % kStages) * ws_stage;
         if (d < D) {
 #pragma unroll 8
             for (int kk = 0; kk < KC; ++kk) {
                 const float w = ws[kk * D + d];
 #pragma unroll
-                for (int i = 0; i < NR; ++i) acc[i] = fmaf(xs[rgrp + R * i][kk], w, acc[i]);
+                for (int i = 0; i < NR; ++i) acc[i] = fmaf(xs[(rgrp + R * i) * XS_LD + kk], w, acc[i]);
             }
         }
-        __syncthreads();
     }
+    cp_async_wait<0>();
+    __syncthreads();
 }
 
 template <int TB, int DP>
@@ -101,10 +136,11 @@ __device__ __forceinline__ void store_acc(const float* acc, const float* bias, i
 template <int TB>
 __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
     extern __shared__ __align__(16) float smem_dyn[];
-    float (*xs)[KC + 1] = reinterpret_cast<float (*)[KC + 1]>(smem_dyn);
-    float* ws = smem_dyn + TB * (KC + 1);
-    float (*hA)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + KC * HMAX);
-    float (*hB)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + KC * HMAX + TB * (HMAX + 1));
+    float* xs = smem_dyn;                                          // [kStages][TB][XS_LD]
+    float* ws = xs + kStages * TB * XS_LD;                         // [kStages][KC][dmax]
+    const int ws_stage = KC * a.dmax;
+    float (*hA)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + kStages * ws_stage);
+    float (*hB)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + kStages * ws_stage + TB * (HMAX + 1));
     const HeadDev& H = a.head[blockIdx.y];
     const int s0 = blockIdx.x * TB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,10 +153,10 @@ __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
         const int DP = next_pow2_32(D);
         if (l == 0) {
             switch (DP) {
-                case 32: dense_gather<TB, 32>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 32>(acc, H.blob + H.b_off[0], D, cur); break;
-                case 64: dense_gather<TB, 64>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 64>(acc, H.blob + H.b_off[0], D, cur); break;
-                case 128: dense_gather<TB, 128>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 128>(acc, H.blob + H.b_off[0], D, cur); break;
-                default: dense_gather<TB, 256>(H, a.src, s0, a.n, xs, ws, acc); store_acc<TB, 256>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 32: dense_gather<TB, 32>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 32>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 64: dense_gather<TB, 64>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 64>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 128: dense_gather<TB, 128>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 128>(acc, H.blob + H.b_off[0], D, cur); break;
+                default: dense_gather<TB, 256>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 256>(acc, H.blob + H.b_off[0], D, cur); break;
             }
         } else {
             const float* W = H.blob + H.w_off[l];
@@ -205,11 +241,16 @@ int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float
     a.src = src; a.n = n; a.out = d_out; a.out_stride = out_stride; a.combine_max = combine_max;
     // small batches: 8 samples per CTA so that the grid still covers the SMs
     const bool small = (n + 31) / 32 * nh < 2 * ctx->sm_count;
-    auto smem_of = [](int tb) { return sizeof(float) * (size_t)(tb * (KC + 1) + KC * HMAX + 2 * tb * (HMAX + 1)); };
+    int dmax = 4;
+    for (int i = 0; i < nh; ++i)
+        for (int l = 1; l <= a.head[i].n_layers; ++l) dmax = a.head[i].dims[l] > dmax ? a.head[i].dims[l] : dmax;
+    dmax = (dmax + 3) & ~3;
+    a.dmax = dmax;
+    auto smem_of = [&](int tb) { return sizeof(float) * (size_t)(kStages * tb * XS_LD + kStages * KC * dmax + 2 * tb * (HMAX + 1)); };
     static bool attr_set = false;
     if (!attr_set) {
-        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(32)));
-        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(8)));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     if (small) {

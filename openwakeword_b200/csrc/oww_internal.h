@@ -107,12 +107,17 @@ struct oww_ctx {
     bool inc_primed = false;         // tails describe the newest window of every stream
     IncPlan inc_plan;
 
-    // host staging for oww_step_host
+    // host staging for oww_step_host / oww_step_host_submit: two slots so the H2D copy of step k+1 (copy_stream)
+    // overlaps the kernels of step k (own_stream)
     cudaStream_t own_stream = nullptr;
-    int16_t* h_pcm_pinned = nullptr; size_t h_pcm_bytes = 0;
-    int16_t* d_pcm_stage = nullptr;  size_t d_pcm_bytes = 0;
-    float* h_scores_pinned = nullptr; size_t h_scores_bytes = 0;
-    float* d_scores_stage = nullptr;  size_t d_scores_bytes = 0;
+    cudaStream_t copy_stream = nullptr;
+    struct HostSlot {
+        int16_t* h_pcm = nullptr; int16_t* d_pcm = nullptr; size_t pcm_bytes = 0;
+        float* h_scores = nullptr; float* d_scores = nullptr; size_t sc_bytes = 0;
+        cudaEvent_t h2d_done = nullptr, done = nullptr;
+        bool busy = false;
+    } slot[2];
+    int next_slot = 0;
 
     // stage timing
     bool timing = false;

@@ -45,3 +45,13 @@ class StreamEngine:
             out = np.empty((self.n_streams, self.n_cols), np.float32)
         self.ctx.step_host(pcm, n_chunks, out)
         return out
+
+    def submit(self, pcm, n_chunks=1):
+        """Pipelined host path: enqueue H2D + step + D2H and return a ticket; at most two in flight."""
+        return self.ctx.step_host_submit(pcm, n_chunks)
+
+    def collect(self, ticket, out=None):
+        if out is None:
+            out = np.empty((self.n_streams, self.n_cols), np.float32)
+        self.ctx.step_host_collect(ticket, out)
+        return out

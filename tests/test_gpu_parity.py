@@ -230,3 +230,28 @@ def test_full_size_properties(torch_cuda, built_library):
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy(), runs[0][:, 0])
     assert eng.ctx.launch_count > 0
+
+
+def test_pipelined_submit_collect_equals_sequential(torch_cuda, built_library):
+    """oww_step_host_submit/collect with two tickets in flight gives the same scores as oww_step_host."""
+    from openwakeword_b200.engine import StreamEngine
+    from openwakeword_b200 import _native
+    rng = np.random.default_rng(4)
+    B, K = 200, 7
+    hs = [head("alexa_v0.1"), head("timer_v0.1")]
+    pcm = [np.ascontiguousarray(np.clip(rng.normal(0, 3000, (B, 1280)), -32768, 32767).astype(np.int16)) for _ in range(K)]
+    for mode in (0, 3):
+        seq = StreamEngine(hs, B, embedding=emb_weights(), cnn_mode=mode)
+        ref = [seq.step_host(p, 1).copy() for p in pcm]
+        pipe = StreamEngine(hs, B, embedding=emb_weights(), cnn_mode=mode)
+        got = []
+        t = pipe.submit(pcm[0])
+        for k in range(1, K + 1):
+            nxt = pipe.submit(pcm[k]) if k < K else None
+            got.append(pipe.collect(t).copy())
+            t = nxt
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+        t0 = pipe.submit(pcm[0]); t1 = pipe.submit(pcm[1])
+        with pytest.raises(_native.NativeError):
+            pipe.submit(pcm[2])                      # both slots in flight
+        pipe.collect(t0); pipe.collect(t1)
