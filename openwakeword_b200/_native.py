@@ -56,6 +56,7 @@ _SIGNATURES = {
     "oww_predict_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "oww_debug_layer": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "oww_debug_inc_plan": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
+    "oww_debug_inc_clocks": (C.c_int, [_P, _P]),
     "oww_launch_count": (C.c_uint64, [_P]),
     "oww_enable_stage_timing": (C.c_int, [_P, C.c_int]),
     "oww_stage_ms": (C.c_int, [_P, _P]),
@@ -221,6 +222,11 @@ class Context:
 
     def debug_layer(self, d_windows, n, layer, d_out, stream=None):
         self._check(self.lib.oww_debug_layer(self.h, _ptr(d_windows), n, layer, _ptr(d_out), stream))
+
+    def debug_inc_clocks(self):
+        out = np.zeros(101, np.int64)
+        self._check(self.lib.oww_debug_inc_clocks(self.h, _ptr(out)))
+        return out
 
     # ---- introspection ----
     def enable_stage_timing(self, n_slots=1):

@@ -26,11 +26,16 @@
 
 namespace {
 
-constexpr int kIncEpiWarps = 8;
-constexpr int kIncThreads = (kIncEpiWarps + 2) * 32;      // 320
+constexpr int kIncEpiWarps = 16;                         // four per TMEM lane quarter, each a quarter of the columns
+constexpr int kIncThreads = (kIncEpiWarps + 2) * 32;      // 576
 constexpr int kIncAcc = 4;                                // TMEM accumulator stages (4 x 128 columns)
 constexpr int kIncMaxG = 4;
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -46,6 +51,7 @@ struct IncArgs {
     const uint4* tails_in; uint4* tails_out;                  // [n_groups][tail_units]
     float* emb;                                               // [B][96]
     int B;
+    long long* dbg_clock;                                     // optional: 21 clock64 stamps of CTA 0's first group
 };
 
 __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_constant__ IncArgs a) {
@@ -60,7 +66,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     uint4* bufX = reinterpret_cast<uint4*>(smem + 2048);
     uint4* bufY = bufX + P.x_units;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+    const int lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto wfull = [&](int i) { return bar0 + 8u * i; };
     auto wempty = [&](int i) { return bar0 + 8u * (2 + i); };
@@ -84,7 +91,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == kIncEpiWarps) {
         // ===================== weight producer =====================
@@ -111,45 +118,63 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 const IncLayer& L = P.L[l];
                 named_bar_sync(1, (kIncEpiWarps + 1) * 32);       // layer l-1 output complete and fenced
                 tc_fence_after();
-                if (lane == 0) {
-                    // layer l-1's epilogue (which reads scale/bias from its weight slot) is done: free that slot
-                    if (have_prev) mbar_arrive(wempty(prev_i));
-                    if (L.kh3) { mbar_wait(tails_bar, tails_par); tails_par ^= 1; }   // rows 0..1 of the input have landed
-                    const int i = l & 1;
-                    mbar_wait(wfull(i), wpar[i]);
-                    wpar[i] ^= 1;
-                    const uint32_t w_addr = smem_u32(smem + L.w_smem);
-                    const uint32_t a_base = smem_u32(L.in_buf ? bufY : bufX);
-                    const uint32_t idesc = (1u << 4) | ((uint32_t)(L.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                    const int n_tiles = (L.M + 127) / 128;
-                    for (int tile = 0; tile < n_tiles; ++tile) {
-                        mbar_wait(tempty(acc), acc_par ^ 1);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-                        uint32_t accumulate = 0;
-                        for (int j = 0; j < 3; ++j) {
-                            for (int q = 0; q < L.cgp / 2; ++q) {
-                                // K = 16 = two channel-group planes; an odd plane count pairs the last plane with
-                                // itself (LBO 0) against zero weights, so no pad plane has to exist in smem
-                                const uint32_t lbo_a = (2 * q + 1 < L.cg_in) ? (uint32_t)L.in_pitch * 16u : 0u;
-                                const uint64_t ad = make_desc(a_base + (uint32_t)(2 * q * L.in_pitch + 1 + tile * 128 + L.tap[j]) * 16u, lbo_a, 128u);
-                                const uint64_t bd = make_desc(w_addr + (uint32_t)((j * L.cgp + 2 * q) * L.np) * 16u, (uint32_t)L.np * 16u, 128u);
-                                tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
-                                accumulate = 1;
-                            }
+                // layer l-1's epilogue (which reads scale/bias from its weight slot) is done: free that slot
+                if (lane == 0 && have_prev) mbar_arrive(wempty(prev_i));
+                if (L.kh3) { mbar_wait(tails_bar, tails_par); tails_par ^= 1; }   // rows 0..1 of the input have landed
+                const int i = l & 1;
+                const bool dbg = a.dbg_clock && blockIdx.x == 0 && grp == 0 && lane == 0;
+                long long c0 = 0;
+                if (dbg) c0 = clock64();
+                mbar_wait(wfull(i), wpar[i]);
+                wpar[i] ^= 1;
+                if (dbg) { const long long c1 = clock64(); a.dbg_clock[21 + l] = c1 - c0; c0 = c1; }
+                const uint32_t w_addr = smem_u32(smem + L.w_smem);
+                const uint32_t a_base = smem_u32(L.in_buf ? bufY : bufX);
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(L.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const int n_tiles = (L.M + 127) / 128;
+                // K = 16 = two channel-group planes per MMA; an odd plane count pairs the last plane with itself
+                // (LBO 0) against zero weights, so no pad plane has to exist in smem.  Only the 14-bit start
+                // address field changes between MMAs.  The issue block sits under elect.sync so that every
+                // operand is warp-uniform for the compiler (UTCHMMA straight from uniform registers - an
+                // `if (lane == 0)` region costs ~160 cycles per MMA in R2UR/waterfall code, see scripts/mma_probe.cu).
+                const int nq = L.cgp / 2;
+                const uint32_t a_hi_pair = (uint32_t)make_desc(0, (uint32_t)L.in_pitch * 16u, 128u);   // low word: LBO field
+                const uint32_t a_hi_self = (uint32_t)make_desc(0, 0u, 128u);
+                const uint32_t desc_hi = (uint32_t)(make_desc(0, 0u, 128u) >> 32);                    // SBO + version
+                const uint32_t b_lo0 = (uint32_t)make_desc(0, (uint32_t)L.np * 16u, 128u);
+                const uint32_t a_unit0 = (a_base >> 4) + 1u;
+                const uint32_t b_unit0 = w_addr >> 4;
+                for (int tile = 0; tile < n_tiles; ++tile) {
+                    mbar_wait(tempty(acc), acc_par ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+                    uint32_t accumulate = 0;
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const uint32_t a_tap = a_unit0 + (uint32_t)(tile * 128 + L.tap[j]);
+                        const uint32_t b_tap = b_unit0 + (uint32_t)(j * L.cgp * L.np);
+                        for (int q = 0; q < nq; ++q) {
+                            const uint32_t alo = ((2 * q + 1 < L.cg_in) ? a_hi_pair : a_hi_self) |
+                                                 ((a_tap + (uint32_t)(2 * q * L.in_pitch)) & 0x3FFFu);
+                            const uint32_t blo = b_lo0 | ((b_tap + (uint32_t)(2 * q * L.np)) & 0x3FFFu);
+                            if (elect_one())
+                                tc_mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | alo, ((uint64_t)desc_hi << 32) | blo, idesc, accumulate);
+                            accumulate = 1;
                         }
-                        tc_commit(tfull(acc));
-                        if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
                     }
-                    have_prev = true; prev_i = i;
+                    if (elect_one()) tc_commit(tfull(acc));
+                    __syncwarp();
+                    if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
                 }
+                if (dbg) a.dbg_clock[41 + l] = clock64() - c0;      // MMA issue time of the layer
+                have_prev = true; prev_i = i;
                 __syncwarp();
             }
         }
     } else {
         // ===================== epilogue / CUDA-core warps (256 threads) =====================
         const int et = threadIdx.x;                               // 0..255
-        const int quarter = warp & 3, half = warp >> 2;
+        const int quarter = warp & 3, part = warp >> 2;
         const int row = quarter * 32 + lane;
         int acc = 0; uint32_t acc_par = 0;
         uint32_t epar[2] = {0, 0};
@@ -159,6 +184,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
             for (int l = 0; l < OWW_N_CONV; ++l) {
                 const IncLayer& L = P.L[l];
+                if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[l] = clock64();
                 uint4* nx = L.nx_buf ? bufY : bufX;
                 // ---- (a) tails of the buffer this phase fills (rows 0..1) and front guards.  In a pool phase that
                 //      buffer is still the conv's INPUT, so this is deferred until the tiles are drained. ----
@@ -226,20 +252,24 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     epar[l & 1] ^= 1;
                     const float* sb = reinterpret_cast<const float*>(smem + L.w_smem + 3 * L.cgp * L.np * 16);
                     const int np8 = L.np / 8;
-                    const int ph = (np8 + 1) / 2;
-                    const int pl0 = half * ph, pl1 = min(np8, pl0 + ph);
+                    const int ph = (np8 + 3) / 4;
+                    const int pl0 = min(np8, part * ph), pl1 = min(np8, pl0 + ph);
                     uint4* dst = L.pool_t ? (L.out_buf ? bufY : bufX) : nx;
                     const int dpitch = L.pool_t ? L.tmp_pitch : L.nx_pitch;
                     const int t_off_units = L.pool_t ? 0 : L.nx_t_off * G * L.Wp;
                     const int n_tiles = (L.M + 127) / 128;
                     const int tail_start = (L.T_out - 2) * G * L.Wp;
+                    const bool edbg = a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0;
+                    long long e0 = 0;
+                    if (edbg) e0 = clock64();
                     for (int tile = 0; tile < n_tiles; ++tile) {
                         mbar_wait(tfull(acc), acc_par);
+                        if (edbg && tile == 0) a.dbg_clock[61 + l] = clock64() - e0;     // phase start -> first accumulator ready
                         tc_fence_after();
-                        uint32_t v[6][8];
+                        uint32_t v[3][8];
                         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u;
 #pragma unroll
-                        for (int k = 0; k < 6; ++k)
+                        for (int k = 0; k < 3; ++k)
                             if (pl0 + k < pl1) tmem_ld8(taddr + (pl0 + k) * 8, v[k]);
                         tmem_wait_ld();
                         tc_fence_before();
@@ -254,7 +284,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             if (f != 0 || !live) continue;
                             float* o = a.emb + (int64_t)(grp * G + g) * 96;
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) {
+                            for (int k = 0; k < 3; ++k) {
                                 if (pl0 + k >= pl1) continue;
                                 const int c = (pl0 + k) * 8;
                                 float4 r0, r1;
@@ -273,7 +303,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         }
                         const bool pad = f == L.W;
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) {
+                        for (int k = 0; k < 3; ++k) {
                             const int pl = pl0 + k;
                             if (pl >= pl1 || pl >= L.cg_out) continue;
                             const int c = pl * 8;
@@ -290,6 +320,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                                 tout[L.nx_tail_off + pl * (2 * G * L.Wp) + (m - tail_start)] = pk;
                         }
                     }
+                    if (edbg) a.dbg_clock[81 + l] = clock64() - e0;                       // phase start -> last tile stored
                     if (L.pool_t) {
                         // ---- max-pool: tmp (unpooled conv output) -> nx ----
                         named_bar_sync(2, kIncEpiWarps * 32);          // every tile drained: the conv input buffer is free
@@ -342,6 +373,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     named_bar_sync(1, (kIncEpiWarps + 1) * 32);
                 }
             }
+            if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[OWW_N_CONV] = clock64();
         }
     }
     tc_fence_before();
@@ -504,6 +536,7 @@ int oww_inc_alloc_streams(oww_ctx* ctx) {
 // One incremental CNN pass for every stream: mel rows ending `back` rows before the newest.
 int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
     IncArgs a;
+    a.dbg_clock = reinterpret_cast<long long*>(ctx->d_inc_dbg);
     a.plan = ctx->inc_plan;
     a.mel = ctx->d_mel_ring; a.mel_count = ctx->d_mel_count; a.mel_stride = (int64_t)ctx->mel_rows * 32;
     a.mel_mask = ctx->mel_rows - 1; a.back = back;

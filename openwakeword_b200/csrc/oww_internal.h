@@ -106,6 +106,7 @@ struct oww_ctx {
     int inc_cur = 0;                 // tails buffer the next step reads
     bool inc_primed = false;         // tails describe the newest window of every stream
     IncPlan inc_plan;
+    void* d_inc_dbg = nullptr;       // optional per-phase clock stamps (oww_debug_inc_clocks)
 
     // host staging for oww_step_host / oww_step_host_submit: two slots so the H2D copy of step k+1 (copy_stream)
     // overlaps the kernels of step k (own_stream)
