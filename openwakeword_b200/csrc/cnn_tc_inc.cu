@@ -29,7 +29,7 @@ namespace {
 constexpr int kIncEpiWarps = 16;                         // four per TMEM lane quarter, each a quarter of the columns
 constexpr int kIncThreads = (kIncEpiWarps + 2) * 32;      // 576
 constexpr int kIncAcc = 4;                                // TMEM accumulator stages (4 x 128 columns)
-constexpr int kIncMaxG = 4;
+constexpr int kIncMaxG = 7;
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -63,8 +63,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kIncAcc);
     float* s_l0 = reinterpret_cast<float*>(smem + 256);              // 9*24 + 24 + 24 floats
-    uint4* bufX = reinterpret_cast<uint4*>(smem + 2048);
-    uint4* bufY = bufX + P.x_units;
+    uint4* act0 = reinterpret_cast<uint4*>(smem + 2048);            // activation arena; tensors at plan offsets
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 wpar[i] ^= 1;
                 if (dbg) { const long long c1 = clock64(); a.dbg_clock[21 + l] = c1 - c0; c0 = c1; }
                 const uint32_t w_addr = smem_u32(smem + L.w_smem);
-                const uint32_t a_base = smem_u32(L.in_buf ? bufY : bufX);
+                const uint32_t a_base = smem_u32(act0 + L.in_base);
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(L.np >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
                 const int n_tiles = (L.M + 127) / 128;
                 // K = 16 = two channel-group planes per MMA; an odd plane count pairs the last plane with itself
@@ -185,7 +184,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             for (int l = 0; l < OWW_N_CONV; ++l) {
                 const IncLayer& L = P.L[l];
                 if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[l] = clock64();
-                uint4* nx = L.nx_buf ? bufY : bufX;
+                uint4* nx = act0 + L.nx_base;
                 // ---- (a) tails of the buffer this phase fills (rows 0..1) and front guards.  In a pool phase that
                 //      buffer is still the conv's INPUT, so this is deferred until the tiles are drained. ----
                 auto fill_tails_and_guards = [&]() {
@@ -200,7 +199,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     if (!L.final && et < L.cg_out) nx[et * L.nx_pitch] = make_uint4(0, 0, 0, 0);
                 };
                 if (!L.pool_t) fill_tails_and_guards();
-                else if (et < L.cg_out) (L.out_buf ? bufY : bufX)[et * L.tmp_pitch] = make_uint4(0, 0, 0, 0);
+                else if (et < L.cg_out) (act0 + L.tmp_base)[et * L.tmp_pitch] = make_uint4(0, 0, 0, 0);
 
                 if (l == 0) {
                     // ---- layer 0 on CUDA cores: 8 new rows from the last 10 mel rows of each stream ----
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     const int np8 = L.np / 8;
                     const int ph = (np8 + 3) / 4;
                     const int pl0 = min(np8, part * ph), pl1 = min(np8, pl0 + ph);
-                    uint4* dst = L.pool_t ? (L.out_buf ? bufY : bufX) : nx;
+                    uint4* dst = L.pool_t ? (act0 + L.tmp_base) : nx;
                     const int dpitch = L.pool_t ? L.tmp_pitch : L.nx_pitch;
                     const int t_off_units = L.pool_t ? 0 : L.nx_t_off * G * L.Wp;
                     const int n_tiles = (L.M + 127) / 128;
@@ -335,7 +334,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                                     tout[L.nx_tail_off + pl * 2 * perrow + u] = nx[pl * L.nx_pitch + 1 + perrow + u];
                             }
                         }
-                        const uint4* src = L.out_buf ? bufY : bufX;
+                        const uint4* src = act0 + L.tmp_base;
                         const int T2 = L.T_out / L.pool_t;
                         const int per = T2 * G * L.nx_Wp;
                         for (int i = et; i < L.cg_out * per; i += kIncEpiWarps * 32) {
@@ -463,21 +462,46 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
     }
     P.tail_units = tail_units;
     P.x_units = (x_units + 7) & ~7; P.y_units = (y_units + 7) & ~7;
+    // ---- placement: class-0 tensors sit at offset 0; a class-1 tensor sits just above the largest class-0 tensor
+    //      that is alive at any time during its own lifetime (produced in phase p, consumed in phase p+1) ----
+    int size_nx[OWW_N_CONV], size_tmp[OWW_N_CONV], xlive[OWW_N_CONV + 1];
+    for (int l = 0; l < OWW_N_CONV; ++l) {
+        const IncLayer& L = P.L[l];
+        size_nx[l] = L.final ? 0 : L.nx_pitch * L.cg_out;
+        size_tmp[l] = L.pool_t ? L.tmp_pitch * L.cg_out : 0;
+    }
+    for (int l = 0; l <= OWW_N_CONV; ++l) xlive[l] = 0;
+    for (int l = 0; l < OWW_N_CONV; ++l) {
+        const IncLayer& L = P.L[l];
+        auto upd = [&](int cls, int sz) { if (cls == 0 && sz > xlive[l]) xlive[l] = sz; };
+        if (l > 0) upd(L.in_buf, size_nx[l - 1]);
+        if (L.pool_t) upd(L.out_buf, size_tmp[l]);
+        upd(L.nx_buf, size_nx[l]);
+    }
+    auto r8 = [](int v) { return (v + 7) & ~7; };
+    int act_high[OWW_N_CONV] = {0};
+    for (int l = 0; l < OWW_N_CONV; ++l) {
+        IncLayer& L = P.L[l];
+        L.in_base = l > 0 ? P.L[l - 1].nx_base : 0;
+        L.tmp_base = (L.pool_t && L.out_buf == 1) ? r8(xlive[l]) : 0;
+        L.nx_base = L.nx_buf == 1 ? r8(xlive[l] > xlive[l + 1] ? xlive[l] : xlive[l + 1]) : 0;
+        int hi = 0;
+        if (l > 0 && L.in_base + size_nx[l - 1] > hi) hi = L.in_base + size_nx[l - 1];
+        if (L.pool_t && L.tmp_base + size_tmp[l] > hi) hi = L.tmp_base + size_tmp[l];
+        if (L.nx_base + size_nx[l] > hi) hi = L.nx_base + size_nx[l];
+        act_high[l] = kActBase + hi * 16;
+    }
     // weight slots, top-down: odd layers end at the top, an even layer sits just below its odd successor's
     // slot (sizes are non-decreasing with depth, so it also clears its odd predecessor).
     auto wsz = [&](int l) { return l >= 1 && l < OWW_N_CONV ? (P.L[l].w_bytes + 127) & ~127 : 0; };
     for (int l = 1; l < OWW_N_CONV; ++l)
         P.L[l].w_smem = (l & 1) ? kTop - wsz(l) : kTop - wsz(l + 1) - wsz(l);
     for (int l = 1; l < OWW_N_CONV; ++l) {
-        // while layer l runs, its own slot and the prefetch of layer l+1 are live, next to the activations in use
+        // while layer l runs, its own slot and the prefetch of layer l+1 are live next to the activations in use;
+        // slot l itself was filled during phase l-1
         int w_low = P.L[l].w_smem;
         if (l + 1 < OWW_N_CONV && P.L[l + 1].w_smem < w_low) w_low = P.L[l + 1].w_smem;
-        int act_high = kActBase + use_x[l] * 16;
-        if (use_y[l]) act_high = kActBase + (P.x_units + use_y[l]) * 16;
-        // the phase before (l-1) writes this layer's input while slot l is being prefetched
-        int prev_high = kActBase + use_x[l - 1] * 16;
-        if (use_y[l - 1]) prev_high = kActBase + (P.x_units + use_y[l - 1]) * 16;
-        if (act_high > w_low || prev_high > P.L[l].w_smem)
+        if (act_high[l] > w_low || act_high[l - 1] > P.L[l].w_smem)
             return oww_fail(ctx, OWW_EUNSUPPORTED, "fused-CNN smem plan does not fit at layer %d (G=%d)", l, G);
         if (l >= 2 && wsz(l) < wsz(l - 1)) return oww_fail(ctx, OWW_EUNSUPPORTED, "weight sizes must not shrink with depth");
     }
@@ -490,7 +514,7 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
 int oww_inc_setup(oww_ctx* ctx, const float* h_blob) {
     // packed blob for the fused kernel: per layer fp16 [3][CGP][NP][8] | scale[NP] | bias[NP], 128-byte aligned
     IncPlan P;
-    int rc = oww_inc_build_plan(ctx, kIncMaxG, kIncMaxG, &P);
+    int rc = oww_inc_build_plan(ctx, 1, 1, &P);
     if (rc) return rc;
     std::vector<uint8_t> blob(P.w_total_bytes, 0);
     size_t off = 0;
@@ -519,7 +543,19 @@ int oww_inc_setup(oww_ctx* ctx, const float* h_blob) {
 }
 
 int oww_inc_alloc_streams(oww_ctx* ctx) {
-    int rc = oww_inc_build_plan(ctx, kIncMaxG, ctx->n_streams, &ctx->inc_plan);
+    // Group size: a group's latency is mostly per-layer fixed cost (about 50 us + 6.5 us per stream on B200), so take
+    // the feasible G that minimises rounds(G) * T(G) for this stream count.
+    int best_g = 0; double best_cost = 0;
+    for (int g = 1; g <= kIncMaxG; ++g) {
+        IncPlan P;
+        if (oww_inc_build_plan(ctx, g, ctx->n_streams, &P) != OWW_OK) continue;
+        const int rounds = (P.n_groups + ctx->sm_count - 1) / ctx->sm_count;
+        const double cost = rounds * (50.0 + 6.5 * g);
+        if (!best_g || cost < best_cost) { best_g = g; best_cost = cost; }
+    }
+    if (!best_g) return oww_fail(ctx, OWW_EUNSUPPORTED, "no feasible group size for the fused CNN kernel");
+    ctx->err.clear();
+    int rc = oww_inc_build_plan(ctx, best_g, ctx->n_streams, &ctx->inc_plan);
     if (rc) return rc;
     const size_t bytes = (size_t)ctx->inc_plan.n_groups * ctx->inc_plan.tail_units * 16;
     for (int i = 0; i < 2; ++i) {

@@ -37,7 +37,8 @@ struct IncLayer {            // "units" are 16-byte channel-group units (8 fp16 
     int W, Wp;               // input width, Wp = W + 1 (one zero pad column)
     int rows_in, T_out, M;   // input rows (2 tails + new for (3,1)), output rows, positions to compute
     int cg_in, cgp, np, cg_out;
-    int in_buf, out_buf;     // 0 = X, 1 = Y
+    int in_buf, out_buf;     // buffer class: 0 = low (base 0), 1 = high (base above the live low tensors)
+    int in_base, tmp_base, nx_base;   // unit offsets of the input, unpooled temp and produced tensor in the activation arena
     int in_pitch;            // units per plane of the input buffer
     int tap[3];              // unit offset of each conv tap relative to the output position
     int pool_t, pool_f, tmp_pitch;          // max-pool after the conv; pitch of the unpooled temp (in out_buf)

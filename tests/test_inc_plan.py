@@ -15,7 +15,7 @@ from openwakeword_b200 import _native
 from oracle import embedding, mel
 from helpers import emb_weights
 
-NAMES = ("kh3 final W Wp rows_in T_out M cg_in cgp np cg_out in_buf out_buf in_pitch tap0 tap1 tap2 pool_t pool_f "
+NAMES = ("kh3 final W Wp rows_in T_out M cg_in cgp np cg_out in_buf out_buf in_base tmp_base nx_base in_pitch tap0 tap1 tap2 pool_t pool_f "
          "tmp_pitch nx_buf nx_pitch nx_W nx_Wp nx_rows_new nx_t_off nx_tail_off w_off w_bytes w_smem").split()
 LEAK, FLOOR = float(embedding.LEAK), float(embedding.FLOOR)
 
@@ -38,7 +38,7 @@ class Emu:
     def __init__(self, hdr, layers, weights):
         self.h, self.L, self.w = hdr, layers, weights
         self.G = int(hdr["G"])
-        self.buf = [np.full((int(hdr["x_units"]), 8), np.nan), np.full((int(hdr["y_units"]), 8), np.nan)]
+        self.arena = np.full(((227 * 1024 - 2048) // 16, 8), np.nan)      # the activation arena; tensors at plan offsets
         self.tails = np.zeros((int(hdr["tail_units"]), 8))
         self.sb = [embedding.fold_bn(*[np.asarray(p, np.float64) for p in weights["bn"][i]]) for i in range(19)]
 
@@ -64,7 +64,7 @@ class Emu:
         tin, tout = self.tails, self.tails.copy()
         emb = np.zeros((G, 96))
         for l, L in enumerate(self.L):
-            nx = self.buf[L["nx_buf"]]
+            nx = self.arena[L["nx_base"]:]
 
             def fill():
                 if L["nx_tail_off"] >= 0:
@@ -82,7 +82,7 @@ class Emu:
                 fill()
             else:
                 for pl in range(L["cg_out"]):
-                    self.buf[L["out_buf"]][pl * L["tmp_pitch"]] = 0.0
+                    self.arena[L["tmp_base"] + pl * L["tmp_pitch"]] = 0.0
             if l == 0:
                 w0 = self.w["conv"][0].astype(np.float64)[:, :, 0, :]           # [3,3,24]
                 s, b = self.sb[0]
@@ -102,7 +102,7 @@ class Emu:
                     for pl in range(3):
                         nx[pl * L["nx_pitch"] + 1 + p] = y[pl * 8:pl * 8 + 8]
                 continue
-            src = self.buf[L["in_buf"]]
+            src = self.arena[L["in_base"]:]
             Wt = self.w["conv"][l].astype(np.float64).reshape(3, L["cg_in"] * 8, -1)   # [tap, cin, cout]
             M = L["M"]
             taps = (L["tap0"], L["tap1"], L["tap2"])
@@ -118,7 +118,7 @@ class Emu:
                 continue
             s, b = self.sb[l]
             y = act(accum * s + b)
-            dst = self.buf[L["out_buf"]] if L["pool_t"] else nx
+            dst = self.arena[L["tmp_base"]:] if L["pool_t"] else nx
             dpitch = L["tmp_pitch"] if L["pool_t"] else L["nx_pitch"]
             t_off_units = 0 if L["pool_t"] else L["nx_t_off"] * G * L["Wp"]
             tail_start = (L["T_out"] - 2) * G * L["Wp"]
@@ -131,7 +131,7 @@ class Emu:
                         tout[L["nx_tail_off"] + pl * 2 * G * L["Wp"] + (m - tail_start)] = v
             if L["pool_t"]:
                 fill()
-                tmp = self.buf[L["out_buf"]]
+                tmp = self.arena[L["tmp_base"]:]
                 T2 = L["T_out"] // L["pool_t"]
                 per = T2 * G * L["nx_Wp"]
                 for i in range(L["cg_out"] * per):
@@ -152,10 +152,25 @@ class Emu:
         return emb
 
 
-@pytest.mark.parametrize("G", [4, 3])
+@pytest.mark.parametrize("G", [7, 4, 1])
 def test_fused_plan_reproduces_full_window_embeddings(built_library, G):
     hdr, layers = get_plan(G, G, built_library)
     assert hdr["smem_bytes"] <= 227 * 1024
+    # live tensors of a phase never overlap each other or the weight slots in use (weights start at w_smem - 2048 bytes)
+    for l, L in enumerate(layers):
+        spans = []
+        if l > 0:
+            spans.append((L["in_base"], L["in_base"] + layers[l - 1]["nx_pitch"] * layers[l - 1]["cg_out"]))
+        if L["pool_t"]:
+            spans.append((L["tmp_base"], L["tmp_base"] + L["tmp_pitch"] * L["cg_out"]))
+        if not L["final"] and not L["pool_t"]:
+            spans.append((L["nx_base"], L["nx_base"] + L["nx_pitch"] * L["cg_out"]))
+        spans.sort()
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 <= b0, (l, spans)
+        if l >= 1:
+            wl = min(L["w_smem"], layers[l + 1]["w_smem"] if l + 1 < 20 else 1 << 30)
+            assert 2048 + 16 * max(e for _, e in spans) <= wl, (l, spans, wl)
     # weight slots never overlap the activations alive in the same or the previous phase (checked by the builder)
     w = emb_weights()
     rng = np.random.default_rng(3)
