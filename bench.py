@@ -233,8 +233,11 @@ def run_own_arm(args):
     sh = owd.ShardedStreams(n_total, factory, rank=rank, world=world)
     eng = sh.engine
     host_pcm = synth_pcm(B, POOL, 1234 + rank)                   # [B, POOL*1280]
-    host_steps = [np.ascontiguousarray(host_pcm[:, i * CHUNK:(i + 1) * CHUNK]) for i in range(POOL)]
-    dev_steps = [torch.from_numpy(h).to(dev) for h in host_steps]
+    # host inputs live in page-locked memory (what a capture/ingest thread would hand over); numpy views of them go
+    # through the public host API, which DMAs straight from pinned sources
+    pinned = [torch.from_numpy(np.ascontiguousarray(host_pcm[:, i * CHUNK:(i + 1) * CHUNK])).pin_memory() for i in range(POOL)]
+    host_steps = [p.numpy() for p in pinned]
+    dev_steps = [p.to(dev) for p in pinned]
     scores = torch.empty((B, eng.n_cols), dtype=torch.float32, device=dev)
 
     def barrier():

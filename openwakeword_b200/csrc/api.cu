@@ -389,14 +389,22 @@ int oww_step_host_submit(oww_ctx* ctx, const int16_t* h_pcm, int64_t pcm_stride,
         OWW_CUDA(ctx, cudaMalloc(&S.d_scores, sc_bytes));
         S.sc_bytes = sc_bytes;
     }
-    // pack rows into the pinned buffer (pcm_stride may exceed the row length)
-    if (pcm_stride == (int64_t)row) {
+    // Source already page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory) and dense: DMA straight from
+    // the caller's buffer (it must stay untouched until the ticket is collected).  Otherwise stage through pinned memory.
+    const int16_t* src = S.h_pcm;
+    cudaPointerAttributes attr;
+    const bool pinned = pcm_stride == (int64_t)row && cudaPointerGetAttributes(&attr, h_pcm) == cudaSuccess &&
+                        attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();                                     // unregistered host memory reports an error on older drivers
+    if (pinned) {
+        src = h_pcm;
+    } else if (pcm_stride == (int64_t)row) {
         std::memcpy(S.h_pcm, h_pcm, pcm_bytes);
     } else {
         for (int b = 0; b < B; ++b)
             std::memcpy(S.h_pcm + (size_t)b * row, h_pcm + (size_t)b * pcm_stride, row * sizeof(int16_t));
     }
-    OWW_CUDA(ctx, cudaMemcpyAsync(S.d_pcm, S.h_pcm, pcm_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    OWW_CUDA(ctx, cudaMemcpyAsync(S.d_pcm, src, pcm_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
     OWW_CUDA(ctx, cudaEventRecord(S.h2d_done, ctx->copy_stream));
     cudaStream_t s = ctx->own_stream;
     OWW_CUDA(ctx, cudaStreamWaitEvent(s, S.h2d_done, 0));

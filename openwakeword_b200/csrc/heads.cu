@@ -11,10 +11,10 @@
 
 namespace {
 
-constexpr int KC = 32;          // K chunk of the first (wide) layer
+constexpr int KC = 96;          // K chunk of the first (wide) layer = one 96-wide feature row
 constexpr int NTHREADS = 256;
 constexpr int HMAX = 256;       // widest hidden / output layer supported
-constexpr int kStages = 3;      // cp.async ring depth of the first layer
+constexpr int kMaxStages = 4;   // cp.async ring depth of the first layer: 2..4, chosen per launch to fit shared memory
 constexpr int XS_LD = KC + 4;   // x tile row pitch (floats): 16-byte aligned rows, conflict-light
 
 struct HeadDev {
@@ -28,7 +28,8 @@ struct HeadsArgs {
     HeadDev head[16];
     FeatSrc src;
     int n; float* out; int out_stride; int combine_max;
-    int dmax;                       // widest layer over the heads of this launch, rounded up to 4
+    int dmax;                       // widest layer over the heads of this launch (power of two >= 32)
+    int stages;                     // cp.async ring depth
 };
 
 __device__ __forceinline__ int next_pow2_32(int d) { int p = 32; while (p < d) p <<= 1; return p; }
@@ -39,23 +40,33 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {       // wait until at most n groups are pending
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
 
-// First (wide) layer: out[tb][d] = sum_k x[tb][k] W[k][d], K = n_in*96, x gathered from the feature ring.
+// First (wide) layer: out[tb][d] = b[d] + sum_k x[tb][k] W[k][d], K = n_in*96, x gathered from the feature ring.
 // K is consumed in chunks of KC=32 through a kStages-deep cp.async ring (x tile + W tile per stage) so the
-// global/L2 latency of chunk c+2 hides under the FMAs of chunk c.
-// acc[i] holds output (row = rgrp + R*i, col = d) for this thread; DP = padded layer width.
+// global/L2 latency of chunk c+2 hides under the FMAs of chunk c.  Register tiling: the 256 threads are
+// 4 K-slices x 64; a thread owns RPT = TB/4 rows x CPT = DP/16 columns and walks 8 of the chunk's 32 k values,
+// so one broadcast x load + one vector W load feed RPT*CPT FMAs; the 4 slices are summed through hout at the end.
 template <int TB, int DP>
 __device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& src, int s0, int n, float* xs_all,
-                                             float* ws_all, int ws_stage, float* acc) {
-    constexpr int R = NTHREADS / DP, NR = TB / R;
-    const int tid = threadIdx.x, d = tid % DP, rgrp = tid / DP;
+                                             float* ws_all, int ws_stage, int kStages, float (*hout)[HMAX + 1]) {
+    constexpr int CPT = DP / 16, RPT = TB / 4;
+    const int tid = threadIdx.x, slice = tid >> 6, t = tid & 63, rq = t >> 4, cq = t & 15;
     const int D = H.dims[1], K = H.dims[0];
     const float* W = H.blob + H.w_off[0];
     const int n_chunks = K / KC;
+    float acc[RPT][CPT];
 #pragma unroll
-    for (int i = 0; i < NR; ++i) acc[i] = 0.f;
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
     auto issue = [&](int c) {
         if (c < n_chunks) {
             const int k0 = c * KC;
@@ -78,32 +89,64 @@ __device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& sr
                 }
                 cp_async16(xs + tb * XS_LD + k4, g, ok);
             }
+            // W tile rows are padded to DP columns in smem (zero beyond D) so the vector reads below stay in bounds
             if ((D & 3) == 0) {
-                for (int q = tid; q < KC * D / 4; q += NTHREADS) cp_async16(ws + q * 4, W + (int64_t)k0 * D + q * 4, true);
-            } else {                                   // odd widths: plain loads (visible after the next __syncthreads)
-                for (int q = tid; q < KC * D; q += NTHREADS) ws[q] = __ldg(W + (int64_t)k0 * D + q);
+                for (int q = tid; q < KC * (D / 4); q += NTHREADS) {
+                    const int kk = q / (D / 4), c4 = (q % (D / 4)) * 4;
+                    cp_async16(ws + kk * DP + c4, W + (int64_t)(k0 + kk) * D + c4, true);
+                }
+            } else {
+                for (int q = tid; q < KC * D; q += NTHREADS) ws[(q / D) * DP + (q % D)] = __ldg(W + (int64_t)k0 * D + q);
             }
         }
         cp_async_commit();
     };
+    if (D < DP) {   // zero the padded columns of every stage once
+        for (int q = tid; q < kStages * KC * (DP - D); q += NTHREADS) {
+            const int st = q / (KC * (DP - D)), r = q % (KC * (DP - D));
+            ws_all[st * ws_stage + (r / (DP - D)) * DP + D + (r % (DP - D))] = 0.f;
+        }
+    }
     for (int c = 0; c < kStages - 1; ++c) issue(c);
     for (int c = 0; c < n_chunks; ++c) {
-        cp_async_wait<kStages - 2>();
+        cp_async_wait_dyn(kStages - 2);
         __syncthreads();                                   // chunk c landed for everyone; stage (c-1)%S is free
         issue(c + kStages - 1);
         const float* xs = xs_all + (c % kStages) * (TB * XS_LD);
         const float* ws = ws_all + (c % kStages) * ws_stage;
-        if (d < D) {
-#pragma unroll 8
-            for (int kk = 0; kk < KC; ++kk) {
-                const float w = ws[kk * D + d];
 #pragma unroll
-                for (int i = 0; i < NR; ++i) acc[i] = fmaf(xs[(rgrp + R * i) * XS_LD + kk], w, acc[i]);
+        for (int k8 = 0; k8 < KC / 4; ++k8) {
+            const int kk = slice * (KC / 4) + k8;
+            float wv[CPT];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) wv[j] = ws[kk * DP + cq * CPT + j];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const float x = xs[(rq * RPT + i) * XS_LD + kk];
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(x, wv[j], acc[i][j]);
             }
         }
     }
-    cp_async_wait<0>();
+    cp_async_wait_dyn(0);
     __syncthreads();
+    // sum the 4 K-slices in a fixed order (deterministic) through hout, slice 0 seeds with the bias
+    const float* bias = H.blob + H.b_off[0];
+    for (int sl = 0; sl < 4; ++sl) {
+        if (slice == sl) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int d = cq * CPT + j;
+                    if (d < D) {
+                        float* o = &hout[rq * RPT + i][d];
+                        *o = (sl == 0 ? __ldg(bias + d) : *o) + acc[i][j];
+                    }
+                }
+        }
+        __syncthreads();
+    }
 }
 
 template <int TB, int DP>
@@ -136,8 +179,9 @@ __device__ __forceinline__ void store_acc(const float* acc, const float* bias, i
 template <int TB>
 __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
     extern __shared__ __align__(16) float smem_dyn[];
-    float* xs = smem_dyn;                                          // [kStages][TB][XS_LD]
-    float* ws = xs + kStages * TB * XS_LD;                         // [kStages][KC][dmax]
+    const int kStages = a.stages;
+    float* xs = smem_dyn;                                          // [stages][TB][XS_LD]
+    float* ws = xs + kStages * TB * XS_LD;                         // [stages][KC][dmax]
     const int ws_stage = KC * a.dmax;
     float (*hA)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + kStages * ws_stage);
     float (*hB)[HMAX + 1] = reinterpret_cast<float (*)[HMAX + 1]>(ws + kStages * ws_stage + TB * (HMAX + 1));
@@ -153,10 +197,13 @@ __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
         const int DP = next_pow2_32(D);
         if (l == 0) {
             switch (DP) {
-                case 32: dense_gather<TB, 32>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 32>(acc, H.blob + H.b_off[0], D, cur); break;
-                case 64: dense_gather<TB, 64>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 64>(acc, H.blob + H.b_off[0], D, cur); break;
-                case 128: dense_gather<TB, 128>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 128>(acc, H.blob + H.b_off[0], D, cur); break;
-                default: dense_gather<TB, 256>(H, a.src, s0, a.n, xs, ws, ws_stage, acc); store_acc<TB, 256>(acc, H.blob + H.b_off[0], D, cur); break;
+                case 32: dense_gather<TB, 32>(H, a.src, s0, a.n, xs, ws, ws_stage, kStages, cur); break;
+                case 64: dense_gather<TB, 64>(H, a.src, s0, a.n, xs, ws, ws_stage, kStages, cur); break;
+                case 128: dense_gather<TB, 128>(H, a.src, s0, a.n, xs, ws, ws_stage, kStages, cur); break;
+                default:
+                    if constexpr (TB <= 8) dense_gather<TB, 256>(H, a.src, s0, a.n, xs, ws, ws_stage, kStages, cur);
+                    else __trap();                    // the host never launches 32-row tiles for layers wider than 128
+                    break;
             }
         } else {
             const float* W = H.blob + H.w_off[l];
@@ -239,26 +286,34 @@ int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float
         d.col0 = (head_id < 0 ? h.col0 : 0) + out_col0;
     }
     a.src = src; a.n = n; a.out = d_out; a.out_stride = out_stride; a.combine_max = combine_max;
-    // small batches: 8 samples per CTA so that the grid still covers the SMs
-    const bool small = (n + 31) / 32 * nh < 2 * ctx->sm_count;
     int dmax = 4;
     for (int i = 0; i < nh; ++i)
         for (int l = 1; l <= a.head[i].n_layers; ++l) dmax = a.head[i].dims[l] > dmax ? a.head[i].dims[l] : dmax;
-    dmax = (dmax + 3) & ~3;
+    { int p2 = 32; while (p2 < dmax) p2 <<= 1; dmax = p2; }   // the first layer pads its W tile to the power-of-two width
     a.dmax = dmax;
-    auto smem_of = [&](int tb) { return sizeof(float) * (size_t)(kStages * tb * XS_LD + kStages * KC * dmax + 2 * tb * (HMAX + 1)); };
+    // small batches: 8 samples per CTA so that the grid still covers the SMs; wide layers: register budget
+    auto smem_of = [&](int tb, int st) { return sizeof(float) * (size_t)(st * tb * XS_LD + st * KC * dmax + 2 * tb * (HMAX + 1)); };
+    const size_t kLimit = 224 * 1024;
+    // 8 samples per CTA for small batches (grid covers the SMs) and whenever the 32-row tile does not fit
+    bool small = (n + 31) / 32 * nh < 2 * ctx->sm_count || dmax > 128 || smem_of(32, 2) > kLimit;
+    const int tb = small ? 8 : 32;
+    int stages = kMaxStages;
+    while (stages > 2 && smem_of(tb, stages) > kLimit) --stages;
+    if (smem_of(tb, stages) > kLimit)
+        return oww_fail(ctx, OWW_EUNSUPPORTED, "head layer width %d needs too much shared memory", dmax);
+    a.stages = stages;
     static bool attr_set = false;
     if (!attr_set) {
-        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
     if (small) {
         dim3 grid((n + 7) / 8, nh);
-        heads_kernel<8><<<grid, NTHREADS, smem_of(8), s>>>(a);
+        heads_kernel<8><<<grid, NTHREADS, smem_of(8, stages), s>>>(a);
     } else {
         dim3 grid((n + 31) / 32, nh);
-        heads_kernel<32><<<grid, NTHREADS, smem_of(32), s>>>(a);
+        heads_kernel<32><<<grid, NTHREADS, smem_of(32, stages), s>>>(a);
     }
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
