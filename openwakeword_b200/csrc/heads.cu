@@ -89,24 +89,28 @@ __device__ __forceinline__ void dense_gather(const HeadDev& H, const FeatSrc& sr
                 }
                 cp_async16(xs + tb * XS_LD + k4, g, ok);
             }
-            // W tile rows are padded to DP columns in smem (zero beyond D) so the vector reads below stay in bounds
+            // W tile: [KC][DP] in smem; DP is a power of two so the item -> (row, column) split is shifts; columns
+            // beyond the real width D are zero-filled by cp.async (src-size 0)
+            constexpr int CQ = DP / 4;
             if ((D & 3) == 0) {
-                for (int q = tid; q < KC * (D / 4); q += NTHREADS) {
-                    const int kk = q / (D / 4), c4 = (q % (D / 4)) * 4;
-                    cp_async16(ws + kk * DP + c4, W + (int64_t)(k0 + kk) * D + c4, true);
+#pragma unroll
+                for (int it = 0; it < (KC * CQ + NTHREADS - 1) / NTHREADS; ++it) {
+                    const int q = tid + it * NTHREADS;
+                    if (q < KC * CQ) {
+                        const int kk = q / CQ, c4 = (q % CQ) * 4;
+                        const bool ok = c4 < D;
+                        cp_async16(ws + kk * DP + c4, W + (int64_t)(k0 + kk) * D + (ok ? c4 : 0), ok);
+                    }
                 }
-            } else {
-                for (int q = tid; q < KC * D; q += NTHREADS) ws[(q / D) * DP + (q % D)] = __ldg(W + (int64_t)k0 * D + q);
+            } else {                                   // odd widths: plain loads (visible after the next __syncthreads)
+                for (int q = tid; q < KC * DP; q += NTHREADS) {
+                    const int kk = q / DP, cc = q % DP;
+                    ws[q] = cc < D ? __ldg(W + (int64_t)(k0 + kk) * D + cc) : 0.f;
+                }
             }
         }
         cp_async_commit();
     };
-    if (D < DP) {   // zero the padded columns of every stage once
-        for (int q = tid; q < kStages * KC * (DP - D); q += NTHREADS) {
-            const int st = q / (KC * (DP - D)), r = q % (KC * (DP - D));
-            ws_all[st * ws_stage + (r / (DP - D)) * DP + D + (r % (DP - D))] = 0.f;
-        }
-    }
     for (int c = 0; c < kStages - 1; ++c) issue(c);
     for (int c = 0; c < n_chunks; ++c) {
         cp_async_wait_dyn(kStages - 2);

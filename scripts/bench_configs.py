@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""BASELINE.json configs other than the bench.py headline (configs[1]), on one GPU:
+  C1  single WAV-sized clip (10 000 samples, the size of tests/data/alexa_test.wav), 1 head, Model.predict_clip
+  C3  8192 concurrent streams, all 6 pretrained head SHAPES (5 binary 1536-64-64-1 + timer 3264-128-128-7)
+  C5  bulk predict_clips over 2 s clips, per-GPU share of the 1M-clip job = 125 000 clips, 6 heads
+Weights synthetic (exact reference shapes).  Prints one JSON object per config."""
+import json, sys, time, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from openwakeword_b200 import Model, weights as W
+from openwakeword_b200.engine import StreamEngine
+
+def heads6():
+    hs = [W.synthetic_head(seed=10 + i) for i in range(5)]
+    hs.append(W.synthetic_head(n_in=34, hidden=128, n_out=7, layernorm=False, final="relu_softmax", seed=20))
+    return hs
+
+def c1():
+    rng = np.random.default_rng(0)
+    m = Model(wakeword_models=[{"name": "alexa", "head": W.synthetic_head(seed=1)}], embedding_model_path="synthetic:0",
+              feature_init=np.zeros((41, 96), np.float32), cnn_mode=3)
+    clip = rng.integers(-3000, 3000, 10000).astype(np.int16)
+    m.predict_clip(clip)
+    m.reset()
+    t0 = time.perf_counter(); n = 0
+    for _ in range(20):
+        m.reset(); r = m.predict_clip(clip); n += len(r)
+    dt = time.perf_counter() - t0
+    return {"config": "C1 single 10000-sample clip, 1 head, Model.predict_clip (32 steps, per-step dict API, 1 stream)",
+            "steps_per_clip": len(r), "frames_per_s": n / dt, "ms_per_predict_call": 1e3 * dt / n}
+
+def c3(B=8192, K=100):
+    eng = StreamEngine(heads6(), B, cnn_mode=3)
+    rng = np.random.default_rng(1)
+    pcm = [torch.from_numpy(rng.integers(-1000, 1000, (B, 1280)).astype(np.int16)).cuda() for _ in range(16)]   # 336 MB > L2
+    out = torch.empty((B, eng.n_cols), dtype=torch.float32, device="cuda")
+    for k in range(5): eng.step(pcm[k % 16], 1, out)
+    eng.ctx.enable_stage_timing(K)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for k in range(K): eng.step(pcm[k % 16], 1, out)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    st = eng.ctx.stage_ms()
+    return {"config": f"C3 {B} streams x 6 heads (11 labels), 1 GPU, device-resident PCM", "frames_per_s": B / (ms * 1e-3),
+            "ms_per_step": ms, "stage_ms": st}
+
+def c5(N=125000, S=32000, slab=25000):
+    m = Model(wakeword_models=[{"name": f"h{i}", "head": h} for i, h in enumerate(heads6())], embedding_model_path="synthetic:0",
+              feature_init=np.zeros((41, 96), np.float32), cnn_mode=3)
+    rng = np.random.default_rng(2)
+    base = rng.integers(-2000, 2000, (slab, S)).astype(np.int16)
+    t0 = time.perf_counter(); frames = 0; done = 0
+    while done < N:
+        n = min(slab, N - done)
+        sc, labels = m.predict_clips_array(base[:n], padding=1)
+        frames += sc.shape[0] * sc.shape[1]; done += n
+    dt = time.perf_counter() - t0
+    return {"config": f"C5 share: bulk predict_clips over {N} x 2 s clips (host arrays in, host scores out), 6 heads, 1 GPU",
+            "clips_per_s": N / dt, "frames_per_s": frames / dt, "seconds": dt, "steps_per_clip": sc.shape[1], "labels": len(labels)}
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c3", "c5"]
+    for w in which:
+        print(json.dumps({"c1": c1, "c3": c3, "c5": c5}[w]()), flush=True)
