@@ -213,6 +213,7 @@ def run_own_arm(args):
     from openwakeword_b200.engine import StreamEngine
     import __graft_entry__ as g
     g.build()
+    from oracle.probe import parity_label      # labelling only (which oracle the 1e-3 gate was checked against)
 
     rank, world, local = owd.init_process_group("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if world != args.gpus:
@@ -342,6 +343,7 @@ def run_own_arm(args):
                    "streams_per_gpu": B, "heads": 1, "cnn_mode": args.cnn_mode,
                    "l2": f"inputs larger than L2: {POOL} distinct PCM batches ({POOL * B * CHUNK * 2 / 1e6:.0f} MB) cycled",
                    "weights": "synthetic seed 0 (reference shapes); released .onnx weights absent",
+                   "parity": parity_label(),
                    "parallelism": f"dp{world} (streams sharded, weights replicated, 1 score all-gather/step)"},
         "clocks": clocks,
         "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / K,

@@ -22,11 +22,13 @@ from . import registry as _registry
 
 
 def _load_head_file(path):
+    """-> (head dict, class mapping or None).  ``.npz`` = weights.save_head container; ``.onnx`` = a reference head
+    file (torch.onnx.export of train.py's DNN family), read without the onnx package (onnx_io.py)."""
     if path.endswith(".npz"):
         return _weights.load_head(path)
     if path.endswith(".onnx"):
-        raise ValueError(f"ONNX head ingestion is not available in this build ({path}); convert with "
-                         "openwakeword_b200.weights.save_head")
+        from .onnx_io import head_from_onnx
+        return head_from_onnx(path), None
     raise ValueError(f"unsupported model file '{path}'")
 
 

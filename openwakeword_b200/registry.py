@@ -19,4 +19,12 @@ model_class_mappings = {
 
 
 def get_pretrained_model_paths(inference_framework="b200"):
-    return [MODELS[k]["model_path"] for k in MODELS]
+    """Paths of the six pretrained heads: the .npz container if present, else a same-named .onnx (the reference's
+    release asset dropped into resources/models/), else the .npz path (construction then reports the missing file)."""
+    out = []
+    for k in MODELS:
+        p = MODELS[k]["model_path"]
+        if not os.path.exists(p) and os.path.exists(p[:-4] + ".onnx"):
+            p = p[:-4] + ".onnx"
+        out.append(p)
+    return out

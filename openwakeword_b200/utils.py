@@ -38,8 +38,8 @@ def _torch():
 
 
 def load_embedding_weights(path):
-    """'' -> resources/models/embedding_model.npz ; 'synthetic[:seed]' -> seeded synthetic weights;
-    '*.npz' -> weights.load_embedding.  (.onnx ingestion: SURVEY.md Appendix E, next round.)"""
+    """'' -> resources/models/embedding_model.{npz,onnx} ; 'synthetic[:seed]' -> seeded synthetic weights;
+    '*.npz' -> weights.load_embedding ; '*.onnx' -> onnx_io.embedding_from_onnx."""
     if isinstance(path, dict):
         return path
     if path.startswith("synthetic"):
@@ -47,12 +47,17 @@ def load_embedding_weights(path):
         return _weights.synthetic_embedding(seed)
     if path == "":
         path = os.path.join(_MODELS_DIR, "embedding_model.npz")
+        if not os.path.exists(path) and os.path.exists(path[:-4] + ".onnx"):
+            path = path[:-4] + ".onnx"
     if ".tflite" in path:
         raise ValueError("The b200 inference framework is selected, but tflite models were provided!")
     if not os.path.exists(path):
         raise ValueError(
             f"Embedding model file '{path}' not found. The reference's released weights are download-only; "
             "convert them with openwakeword_b200.weights.save_embedding or pass embedding_model_path='synthetic:0'.")
+    if path.endswith(".onnx"):
+        from .onnx_io import embedding_from_onnx
+        return embedding_from_onnx(path)
     return _weights.load_embedding(path)
 
 
@@ -75,10 +80,12 @@ class AudioFeatures:
             raise ValueError("only 16 kHz audio is supported")
         self.ctx = _native.Context(device=device_index, max_chunks=max_chunks, cnn_mode=cnn_mode,
                                    window_batch=window_batch)
-        if melspec_model_path not in ("", "builtin"):
+        if melspec_model_path.endswith(".npz"):
             z = np.load(melspec_model_path)
             self.ctx.load_mel(z["window"], z["mel_fb"])
-        else:
+        else:       # '' / 'builtin' / a melspectrogram.onnx path: the graph's constants are closed-form
+            if ".tflite" in melspec_model_path:
+                raise ValueError("The b200 inference framework is selected, but tflite models were provided!")
             self.ctx.load_mel()
         self.embedding_weights = load_embedding_weights(embedding_model_path)
         self.ctx.load_embedding(_weights.pack_embedding_blob(self.embedding_weights))

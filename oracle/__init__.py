@@ -19,4 +19,4 @@ PARITY STATUS
     (file:line cited per function) and is cross-checked against independent
     implementations (torch.stft + torchaudio filterbank; torch conv2d).
 """
-from . import mel, embedding, heads, streaming  # noqa: F401
+from . import mel, embedding, heads, streaming, probe  # noqa: F401

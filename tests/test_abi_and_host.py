@@ -155,3 +155,21 @@ def test_multi_stream_batch_equals_singles(fake_ctx):
             for k in r1:
                 assert abs(r1[k] - rb[k][b]) < 1e-6
     assert "1_hour_timer" in rb and rb["alexa_v0.1"].shape == (3,)
+
+
+def test_model_loads_reference_style_onnx_files(fake_ctx, tmp_path):
+    """wakeword_models given as .onnx paths (key = basename, model.py:91-92) + embedding_model.onnx, no onnx package."""
+    from openwakeword_b200 import onnx_io
+    c = load_case("alexa_c1280")
+    hp = str(tmp_path / "alexa_v0.1.onnx")
+    ep = str(tmp_path / "embedding_model.onnx")
+    onnx_io.write_head_onnx(hp, head("alexa_v0.1"))
+    onnx_io.write_embedding_onnx(ep, emb_weights())
+    m = owb.Model(wakeword_models=[hp], embedding_model_path=ep, melspec_model_path=str(tmp_path / "melspectrogram.onnx"),
+                  feature_init=c["feature_init"])
+    assert list(m.models) == ["alexa_v0.1"] and m.model_inputs["alexa_v0.1"] == 16 and m.model_outputs["alexa_v0.1"] == 1
+    res = m.predict_clip(c["pcm"])
+    got = np.array([[r[l] for l in c["labels"]] for r in res], dtype=np.float32)
+    np.testing.assert_allclose(got, c["scores"], atol=1e-5)
+    with pytest.raises(ValueError):
+        owb.Model(wakeword_models=[str(tmp_path / "x.tflite")], embedding_model_path=ep)

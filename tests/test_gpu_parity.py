@@ -255,3 +255,22 @@ def test_pipelined_submit_collect_equals_sequential(torch_cuda, built_library):
         with pytest.raises(_native.NativeError):
             pipe.submit(pcm[2])                      # both slots in flight
         pipe.collect(t0); pipe.collect(t1)
+
+
+def test_model_from_onnx_files(torch_cuda, built_library, tmp_path):
+    import openwakeword_b200 as owb
+    from openwakeword_b200 import onnx_io
+    c = load_case("mycroft_all4_c1280")
+    paths = []
+    for n in c["names"]:
+        p = str(tmp_path / f"{n}.onnx")
+        onnx_io.write_head_onnx(p, head(n), fused_layernorm=n.startswith("big"))
+        paths.append(p)
+    ep = str(tmp_path / "embedding_model.onnx")
+    onnx_io.write_embedding_onnx(ep, emb_weights())
+    m = owb.Model(wakeword_models=paths, embedding_model_path=ep, feature_init=c["feature_init"], cnn_mode=3)
+    m.class_mapping["timer_v0.1"] = class_mapping(["timer_v0.1"])["timer_v0.1"]      # as tests/golden/make_golden.py does
+    res = m.predict_clip(c["pcm"])
+    assert list(res[0].keys()) == c["labels"]
+    got = np.array([[r[l] for l in c["labels"]] for r in res], dtype=np.float32)
+    assert np.abs(got - c["scores"]).max() < SCORE_TOL
