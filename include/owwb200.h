@@ -65,7 +65,8 @@ typedef struct oww_config {
     int32_t max_chunks;    /* largest n_chunks a single oww_step may carry (>=1)                */
     int32_t cnn_mode;      /* OWW_CNN_*                                                         */
     int32_t window_batch;  /* windows per CNN sub-batch in the window modes (0 = default)       */
-    int32_t reserved[4];
+    int32_t reserved[4];   /* reserved[0] bit 0: 1 = keep mode 3's steady-state step as separate launches
+                              (mel, CNN, append, heads) instead of the single fused step kernel      */
 } oww_config;
 
 typedef struct oww_head_desc {

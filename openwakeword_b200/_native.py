@@ -16,6 +16,7 @@ MAX_HEAD_LAYERS = 8
 CNN_FP32_WINDOW = 0
 CNN_FP32_INCREMENTAL = 1
 CNN_TC_WINDOW = 2
+CNN_TC_INCREMENTAL = 3
 
 
 class Config(C.Structure):
@@ -103,9 +104,10 @@ def _ptr(a):
 class Context:
     """One handle = one GPU's weights + stream state (include/owwb200.h conventions)."""
 
-    def __init__(self, device=0, max_chunks=4, cnn_mode=CNN_FP32_WINDOW, window_batch=0):
+    def __init__(self, device=0, max_chunks=4, cnn_mode=CNN_FP32_WINDOW, window_batch=0, fuse_step=True):
         self.lib = load_library()
         cfg = Config(device=device, max_chunks=max_chunks, cnn_mode=cnn_mode, window_batch=window_batch)
+        cfg.reserved[0] = 0 if fuse_step else 1
         h = _P()
         rc = self.lib.oww_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -124,6 +124,14 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
     int rc;
     cudaEvent_t* ev = ctx->timing ? &ctx->ev[4 * (ctx->ev_steps % ctx->ev_slots)] : nullptr;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[0], s));
+    if (n_chunks == 1 && oww_fused_step_supported(ctx)) {
+        // steady state: the whole step (frontend, CNN, ring append, heads) is ONE launch; the stage events then
+        // bracket that launch as the "cnn" stage and report zero-length mel / heads stages
+        if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
+        if ((rc = oww_fused_step(ctx, d_pcm, pcm_stride, d_scores, out_stride, s))) return rc;
+        if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[2], s)); OWW_CUDA(ctx, cudaEventRecord(ev[3], s)); ctx->ev_steps++; }
+        return OWW_OK;
+    }
     MelLaunch m{d_pcm, pcm_stride, n_chunks * OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
                 (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, B, 1, n_chunks};
     if ((rc = oww_mel_launch(ctx, m, s))) return rc;
@@ -171,6 +179,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     ctx->cfg = *cfg;
     if (ctx->cfg.max_chunks < 1) ctx->cfg.max_chunks = 1;
     ctx->device = cfg->device;
+    ctx->fuse_step = (cfg->reserved[0] & 1) == 0;
     ctx->window_batch = cfg->window_batch > 0 ? cfg->window_batch : (cfg->cnn_mode == OWW_CNN_FP32_WINDOW ? 512 : 1024);
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) {
         oww_fail(nullptr, OWW_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
@@ -200,7 +209,7 @@ void oww_destroy(oww_ctx* ctx) {
     free_streams(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
     cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
-    cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w);
+    cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w); cudaFree(ctx->d_head_devs);
     for (auto& h : ctx->heads) cudaFree(h.d_blob);
     for (auto& S : ctx->slot) {
         cudaFreeHost(S.h_pcm); cudaFreeHost(S.h_scores); cudaFree(S.d_pcm); cudaFree(S.d_scores);
@@ -269,7 +278,7 @@ int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, s
     ctx->max_n_in = std::max(ctx->max_n_in, desc->n_in);
     ctx->heads.push_back(h);
     if (head_id) *head_id = (int)ctx->heads.size() - 1;
-    return OWW_OK;
+    return oww_heads_sync_devs(ctx);
 }
 
 int oww_n_heads(const oww_ctx* ctx) { return ctx ? (int)ctx->heads.size() : 0; }
@@ -530,7 +539,7 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     c->emb_loaded = ctx->emb_loaded;
     for (int li = 0; li < OWW_N_CONV; ++li) { c->conv[li] = ctx->conv[li]; c->tc_w_off[li] = ctx->tc_w_off[li]; c->tc_sb_off[li] = ctx->tc_sb_off[li]; }
     c->d_tc_w = ctx->d_tc_w; c->d_tc_sb = ctx->d_tc_sb; c->d_inc_w = ctx->d_inc_w;
-    c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in;
+    c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in; c->d_head_devs = ctx->d_head_devs;
     int rc = OWW_OK;
     for (int c0 = 0; c0 < n_clips && rc == OWW_OK; c0 += slab_max) {
         const int m = std::min(slab_max, n_clips - c0);
@@ -553,6 +562,7 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     }
     ctx->launches += c->launches; c->launches = 0;
     c->heads.clear();   // do not let the child free shared blobs
+    c->d_head_devs = nullptr;
     return rc;
 }
 

@@ -22,6 +22,7 @@
 // Max-pools are an smem->smem pass of the same warps.  Warp 8 = weight producer, warp 9 = MMA issuer.
 #include "oww_internal.h"
 #include "tc_common.cuh"
+#include "mel_device.cuh"
 #include <cstring>
 
 namespace {
@@ -52,6 +53,15 @@ struct IncArgs {
     float* emb;                                               // [B][96]
     int B;
     long long* dbg_clock;                                     // optional: 21 clock64 stamps of CTA 0's first group
+    // ---- fused step (fused != 0): the same launch also runs the log-mel frontend before layer 0, appends the embedding
+    //      to the feature ring and evaluates every head, i.e. PCM in -> scores out ----
+    int fused;
+    const int16_t* pcm; int64_t pcm_stride;                   // this step's 1280 samples per stream
+    int16_t* tail; int* seen; float* mel_rw; int* mel_count_rw;
+    const float* mel_window; const float2* mel_twiddle; const int* mel_start; const int* mel_len; const float* mel_w; int mel_kmax;
+    float* feat_ring; int64_t feat_stride; int feat_mask; int* feat_count;
+    const HeadDev* heads; int n_heads; int max_n_in;
+    float* scores; int score_stride;
 };
 
 __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_constant__ IncArgs a) {
@@ -181,6 +191,65 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
+            int* s_cnt = reinterpret_cast<int*>(smem + 1536);      // [0..7] mel row count, [8..15] feature count, before this step
+            float* s_mel = reinterpret_cast<float*>(smem + P.scratch_off + 6144 + 65536 + kIncEpiWarps * 264 * 4);   // [G][8][32]
+            if (a.fused) {
+                // ===== frontend: log-mel of this step's 8 frames per stream (K1 inside the step kernel) =====
+                uint8_t* sc = smem + P.scratch_off;
+                float2* s_tw = reinterpret_cast<float2*>(sc);
+                float* s_win = reinterpret_cast<float*>(sc + 4096);
+                float2* s_buf = reinterpret_cast<float2*>(sc + 6144);
+                float* s_pow = reinterpret_cast<float*>(sc + 6144 + 65536);
+                float* s_floor = s_mel + G * 256;
+                for (int i = et; i < 512; i += kIncEpiWarps * 32) { s_tw[i] = a.mel_twiddle[i]; s_win[i] = a.mel_window[i]; }
+                if (et < G) {
+                    const int b = grp * G + et;
+                    s_cnt[et] = b < a.B ? a.mel_count_rw[b] : 0;
+                    s_cnt[8 + et] = b < a.B ? a.feat_count[b] : 0;
+                }
+                named_bar_sync(2, kIncEpiWarps * 32);
+                const int my_start = a.mel_start[lane], my_len = a.mel_len[lane];
+                const float* my_w = a.mel_w + lane * OWW_MEL_MAXSUPPORT;
+                for (int fi = warp; fi < G * 8; fi += kIncEpiWarps) {
+                    const int g = fi >> 3, f = fi & 7, b = grp * G + g;
+                    float db = 0.f;
+                    if (b < a.B)
+                        db = mel_frame_db(a.tail + (int64_t)b * OWW_TAIL, OWW_TAIL, a.pcm + (int64_t)b * a.pcm_stride, f,
+                                          s_buf + warp * 512, s_buf + warp * 512 + 256, s_pow + warp * 264, s_tw, s_win, a.mel_kmax,
+                                          my_start, my_len, my_w, lane);
+                    s_mel[fi * 32 + lane] = db;
+                    __syncwarp();
+                }
+                named_bar_sync(2, kIncEpiWarps * 32);
+                if (warp < G) {                                    // per-call (= per stream, this step) maximum -> -80 dB floor
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) m = fmaxf(m, s_mel[warp * 256 + j * 32 + lane]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (lane == 0) s_floor[warp] = m - 80.0f;
+                }
+                named_bar_sync(2, kIncEpiWarps * 32);
+                for (int i = et; i < G * 256; i += kIncEpiWarps * 32) {
+                    const int g = i >> 8, b = grp * G + g;
+                    float v = fmaxf(s_mel[i], s_floor[g]);
+                    v = v / 10.0f + 2.0f;
+                    s_mel[i] = v;
+                    if (b < a.B)
+                        a.mel_rw[(int64_t)b * a.mel_stride + (int64_t)((s_cnt[g] + ((i >> 5) & 7)) & a.mel_mask) * 32 + (i & 31)] = v;
+                }
+                for (int i = et; i < G * OWW_TAIL; i += kIncEpiWarps * 32) {
+                    const int g = i / OWW_TAIL, k = i - g * OWW_TAIL, b = grp * G + g;
+                    if (b < a.B) a.tail[(int64_t)b * OWW_TAIL + k] = __ldg(a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + k);
+                }
+                if (et < G && grp * G + et < a.B) {
+                    const int b = grp * G + et;
+                    a.mel_count_rw[b] = s_cnt[et] + 8;
+                    const int sn = a.seen[b] + 1;
+                    a.seen[b] = sn > (1 << 30) ? (1 << 30) : sn;
+                }
+                named_bar_sync(2, kIncEpiWarps * 32);
+            }
             for (int l = 0; l < OWW_N_CONV; ++l) {
                 const IncLayer& L = P.L[l];
                 if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[l] = clock64();
@@ -214,15 +283,17 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             continue;
                         }
                         const float* base = a.mel + (int64_t)b * a.mel_stride;
-                        const int row0 = a.mel_count[b] - a.back - 10 + t;
+                        // rows 0..9 of the input = two rows from before this step + the eight new ones
+                        const int row0 = (a.fused ? s_cnt[g] - 2 : a.mel_count[b] - a.back - 10) + t;
                         float x[9];
 #pragma unroll
                         for (int dt = 0; dt < 3; ++dt) {
-                            const float* rp = base + (int64_t)((row0 + dt) & a.mel_mask) * 32;
+                            const float* rp = (a.fused && t + dt >= 2) ? s_mel + (g * 8 + t + dt - 2) * 32
+                                                                       : base + (int64_t)((row0 + dt) & a.mel_mask) * 32;
 #pragma unroll
                             for (int df = 0; df < 3; ++df) {
                                 const int ff = f + df - 1;
-                                x[dt * 3 + df] = (ff >= 0 && ff < 32) ? __ldg(rp + ff) : 0.f;
+                                x[dt * 3 + df] = (ff >= 0 && ff < 32) ? rp[ff] : 0.f;
                             }
                         }
 #pragma unroll
@@ -281,7 +352,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         const bool live = grp * G + g < a.B;
                         if (L.final) {
                             if (f != 0 || !live) continue;
-                            float* o = a.emb + (int64_t)(grp * G + g) * 96;
+                            float* o = a.fused ? a.feat_ring + (int64_t)(grp * G + g) * a.feat_stride + (int64_t)(s_cnt[8 + g] & a.feat_mask) * 96
+                                               : a.emb + (int64_t)(grp * G + g) * 96;
 #pragma unroll
                             for (int k = 0; k < 3; ++k) {
                                 if (pl0 + k >= pl1) continue;
@@ -373,6 +445,122 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 }
             }
             if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[OWW_N_CONV] = clock64();
+            if (a.fused) {
+                // ===== K3 inside the step kernel: every head on this group's streams, straight from the feature ring =====
+                named_bar_sync(2, kIncEpiWarps * 32);              // the new embedding rows (written by this CTA) are visible
+                const int NI = a.max_n_in;
+                float* feats = reinterpret_cast<float*>(smem + 2048);            // [G][NI][96]
+                float* red = feats + G * NI * 96;                                // [4][G][128]
+                float* hA = red + 4 * G * 128;                                   // [G][256]
+                float* hB = hA + G * 256;
+                for (int i = et; i < G * NI * 24; i += kIncEpiWarps * 32) {
+                    const int g = i / (NI * 24), r = (i / 24) % NI, c4 = (i % 24) * 4, b = grp * G + g;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < a.B) {
+                        const int row = s_cnt[8 + g] + 1 - NI + r;
+                        if (row >= 0) v = __ldcg(reinterpret_cast<const float4*>(a.feat_ring + (int64_t)b * a.feat_stride + (int64_t)(row & a.feat_mask) * 96 + c4));
+                    }
+                    *reinterpret_cast<float4*>(feats + (g * NI + r) * 96 + c4) = v;
+                }
+                named_bar_sync(2, kIncEpiWarps * 32);
+                for (int hh = 0; hh < a.n_heads; ++hh) {
+                    const HeadDev& H = a.heads[hh];
+                    const int D1 = H.dims[1], off = NI - H.n_in;
+                    {   // first layer: 4 K-slices x 128 columns, same summation order as heads_kernel
+                        const int slice = et >> 7, d = et & 127;
+                        float acc[kIncMaxG];
+#pragma unroll
+                        for (int g = 0; g < kIncMaxG; ++g) acc[g] = 0.f;
+                        if (d < D1) {
+                            const float* W = H.blob + H.w_off[0];
+                            for (int c = 0; c < H.n_in; ++c) {
+                                const float* wr = W + (int64_t)(c * 96 + slice * 24) * D1 + d;
+                                const float* xr = feats + (off + c) * 96 + slice * 24;
+#pragma unroll 8
+                                for (int k8 = 0; k8 < 24; ++k8) {
+                                    const float w = __ldg(wr + (int64_t)k8 * D1);
+#pragma unroll
+                                    for (int g = 0; g < kIncMaxG; ++g)
+                                        if (g < G) acc[g] = fmaf(xr[g * NI * 96 + k8], w, acc[g]);
+                                }
+                            }
+#pragma unroll
+                            for (int g = 0; g < kIncMaxG; ++g)
+                                if (g < G) red[(slice * G + g) * 128 + d] = acc[g];
+                        }
+                    }
+                    named_bar_sync(2, kIncEpiWarps * 32);
+                    for (int i = et; i < G * D1; i += kIncEpiWarps * 32) {
+                        const int g = i / D1, d = i - g * D1;
+                        float v = __ldg(H.blob + H.b_off[0] + d) + red[(0 * G + g) * 128 + d];
+                        v += red[(1 * G + g) * 128 + d];
+                        v += red[(2 * G + g) * 128 + d];
+                        v += red[(3 * G + g) * 128 + d];
+                        hA[g * 256 + d] = v;
+                    }
+                    named_bar_sync(2, kIncEpiWarps * 32);
+                    float* cur = hA; float* nxt = hB;
+                    for (int l = 0; l < H.n_layers; ++l) {
+                        const int D = H.dims[l + 1], K = H.dims[l];
+                        if (l > 0) {
+                            const float* W = H.blob + H.w_off[l];
+                            for (int i = et; i < G * D; i += kIncEpiWarps * 32) {
+                                const int g = i / D, d = i - g * D;
+                                float acc = 0.f;
+                                for (int k = 0; k < K; ++k) acc = fmaf(cur[g * 256 + k], __ldg(W + (int64_t)k * D + d), acc);
+                                nxt[g * 256 + d] = acc + __ldg(H.blob + H.b_off[l] + d);
+                            }
+                            named_bar_sync(2, kIncEpiWarps * 32);
+                            float* t = cur; cur = nxt; nxt = t;
+                        }
+                        if (l < H.n_layers - 1) {
+                            if (warp < G) {
+                                float* row = cur + warp * 256;
+                                if (H.layernorm) {
+                                    float sum = 0.f;
+                                    for (int d = lane; d < D; d += 32) sum += row[d];
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                                    const float mu = sum / (float)D;
+                                    float sq = 0.f;
+                                    for (int d = lane; d < D; d += 32) { const float c = row[d] - mu; sq = fmaf(c, c, sq); }
+#pragma unroll
+                                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                                    const float rstd = 1.0f / sqrtf(sq / (float)D + 1e-5f);
+                                    const float* gm = H.blob + H.g_off[l];
+                                    const float* hb = H.blob + H.h_off[l];
+                                    for (int d = lane; d < D; d += 32)
+                                        row[d] = fmaxf((row[d] - mu) * rstd * __ldg(gm + d) + __ldg(hb + d), 0.f);
+                                } else {
+                                    for (int d = lane; d < D; d += 32) row[d] = fmaxf(row[d], 0.f);
+                                }
+                            }
+                            named_bar_sync(2, kIncEpiWarps * 32);
+                        }
+                    }
+                    if (et < G && grp * G + et < a.B) {
+                        const int n_out = H.dims[H.n_layers];
+                        float* row = cur + et * 256;
+                        if (H.final_act == 1) {
+                            for (int d = 0; d < n_out; ++d) row[d] = 1.0f / (1.0f + expf(-row[d]));
+                        } else if (H.final_act == 2 || H.final_act == 3) {
+                            float m = -INFINITY;
+                            for (int d = 0; d < n_out; ++d) {
+                                if (H.final_act == 3) row[d] = fmaxf(row[d], 0.f);
+                                m = fmaxf(m, row[d]);
+                            }
+                            float sum = 0.f;
+                            for (int d = 0; d < n_out; ++d) { row[d] = expf(row[d] - m); sum += row[d]; }
+                            for (int d = 0; d < n_out; ++d) row[d] = row[d] / sum;
+                        }
+                        float* o = a.scores + (int64_t)(grp * G + et) * a.score_stride + H.col0;
+                        for (int d = 0; d < n_out; ++d) o[d] = row[d];
+                    }
+                    named_bar_sync(2, kIncEpiWarps * 32);
+                }
+                if (et < G && grp * G + et < a.B) a.feat_count[grp * G + et] = s_cnt[8 + et] + 1;
+                named_bar_sync(2, kIncEpiWarps * 32);
+            }
         }
     }
     tc_fence_before();
@@ -505,6 +693,13 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
             return oww_fail(ctx, OWW_EUNSUPPORTED, "fused-CNN smem plan does not fit at layer %d (G=%d)", l, G);
         if (l >= 2 && wsz(l) < wsz(l - 1)) return oww_fail(ctx, OWW_EUNSUPPORTED, "weight sizes must not shrink with depth");
     }
+    // frontend scratch used before phase 0 (fused step): twiddles 4 KB | window 2 KB | 16 x two 256-point buffers 64 KB |
+    // 16 x 264 power bins | G x 8 x 32 mel rows | G floors - placed right above layer 0's output, below the weight slots
+    {
+        const int off = kActBase + r8(size_nx[0]) * 16;
+        const int need_b = 6144 + 65536 + kIncEpiWarps * 264 * 4 + G * 256 * 4 + 64;
+        P.scratch_off = (off + need_b <= P.L[1].w_smem && off + need_b <= P.L[2].w_smem) ? off : 0;
+    }
     P.w_total_bytes = (int)w_off;
     P.smem_bytes = kTop;
     *out = P;
@@ -569,18 +764,79 @@ int oww_inc_alloc_streams(oww_ctx* ctx) {
     return OWW_OK;
 }
 
-// One incremental CNN pass for every stream: mel rows ending `back` rows before the newest.
-int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
-    IncArgs a;
-    a.dbg_clock = reinterpret_cast<long long*>(ctx->d_inc_dbg);
+int oww_heads_sync_devs(oww_ctx* ctx) {
+    std::vector<HeadDev> v(ctx->heads.size());
+    for (size_t i = 0; i < ctx->heads.size(); ++i) {
+        const Head& h = ctx->heads[i];
+        HeadDev& d = v[i];
+        std::memset(&d, 0, sizeof(d));
+        d.blob = h.d_blob;
+        d.n_in = h.desc.n_in; d.n_layers = h.desc.n_layers; d.layernorm = h.desc.layernorm; d.final_act = h.desc.final_act;
+        for (int l = 0; l <= h.desc.n_layers; ++l) d.dims[l] = h.desc.dims[l];
+        for (int l = 0; l < h.desc.n_layers; ++l) {
+            d.w_off[l] = (int)h.w_off[l]; d.b_off[l] = (int)h.b_off[l];
+            d.g_off[l] = (int)h.g_off[l]; d.h_off[l] = (int)h.h_off[l];
+        }
+        d.col0 = h.col0;
+    }
+    cudaFree(ctx->d_head_devs); ctx->d_head_devs = nullptr;
+    if (v.empty()) return OWW_OK;
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_head_devs, v.size() * sizeof(HeadDev)));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_head_devs, v.data(), v.size() * sizeof(HeadDev), cudaMemcpyHostToDevice));
+    return OWW_OK;
+}
+
+// Can the whole step run as one launch?  (steady state, one chunk, heads within the in-kernel limits)
+bool oww_fused_step_supported(const oww_ctx* ctx) {
+    if (!ctx->fuse_step || ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || !ctx->inc_primed) return false;
+    if (ctx->inc_plan.scratch_off == 0 || ctx->heads.size() > 16) return false;
+    for (const Head& h : ctx->heads) {
+        if (h.desc.dims[1] > 128) return false;
+        for (int l = 1; l <= h.desc.n_layers; ++l) if (h.desc.dims[l] > 256) return false;
+    }
+    const size_t floats = (size_t)ctx->inc_plan.G * ((size_t)ctx->max_n_in * 96 + 4 * 128 + 2 * 256);
+    return 2048 + floats * 4 <= (size_t)ctx->inc_plan.L[OWW_N_CONV - 1].w_smem;
+}
+
+static void fill_inc_args(oww_ctx* ctx, IncArgs& a) {
+    std::memset(&a, 0, sizeof(a));
     a.plan = ctx->inc_plan;
     a.mel = ctx->d_mel_ring; a.mel_count = ctx->d_mel_count; a.mel_stride = (int64_t)ctx->mel_rows * 32;
-    a.mel_mask = ctx->mel_rows - 1; a.back = back;
+    a.mel_mask = ctx->mel_rows - 1;
     a.w0 = ctx->conv[0].d_w; a.s0 = ctx->conv[0].d_scale; a.b0 = ctx->conv[0].d_bias;
     a.wblob = reinterpret_cast<const uint8_t*>(ctx->d_inc_w);
     a.tails_in = reinterpret_cast<const uint4*>(ctx->d_inc_tails[ctx->inc_cur]);
     a.tails_out = reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur ^ 1]);
-    a.emb = d_emb; a.B = ctx->n_streams;
+    a.B = ctx->n_streams;
+    a.dbg_clock = reinterpret_cast<long long*>(ctx->d_inc_dbg);
+}
+
+// PCM -> scores for every stream in ONE launch: frontend, 20-layer CNN, ring append and all heads.
+int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, cudaStream_t s) {
+    IncArgs a;
+    fill_inc_args(ctx, a);
+    a.fused = 1;
+    a.pcm = d_pcm; a.pcm_stride = pcm_stride;
+    a.tail = ctx->d_tail; a.seen = ctx->d_seen; a.mel_rw = ctx->d_mel_ring; a.mel_count_rw = ctx->d_mel_count;
+    a.mel_window = ctx->d_window; a.mel_twiddle = ctx->d_twiddle; a.mel_start = ctx->d_mel_start; a.mel_len = ctx->d_mel_len;
+    a.mel_w = ctx->d_mel_w; a.mel_kmax = ctx->mel_kmax;
+    a.feat_ring = ctx->d_feat_ring; a.feat_stride = (int64_t)ctx->feat_rows * 96; a.feat_mask = ctx->feat_rows - 1;
+    a.feat_count = ctx->d_feat_count;
+    a.heads = ctx->d_head_devs; a.n_heads = (int)ctx->heads.size(); a.max_n_in = ctx->max_n_in > 0 ? ctx->max_n_in : 1;
+    a.scores = d_scores; a.score_stride = out_stride;
+    const int grid = a.plan.n_groups < ctx->sm_count ? a.plan.n_groups : ctx->sm_count;
+    tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    OWW_LAUNCH_CHECK(ctx);
+    ctx->inc_cur ^= 1;
+    return OWW_OK;
+}
+
+// One incremental CNN pass for every stream: mel rows ending `back` rows before the newest.
+int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
+    IncArgs a;
+    fill_inc_args(ctx, a);
+    a.back = back;
+    a.emb = d_emb;
     const int grid = a.plan.n_groups < ctx->sm_count ? a.plan.n_groups : ctx->sm_count;
     tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
     OWW_LAUNCH_CHECK(ctx);

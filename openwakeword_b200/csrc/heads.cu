@@ -17,13 +17,6 @@ constexpr int HMAX = 256;       // widest hidden / output layer supported
 constexpr int kMaxStages = 4;   // cp.async ring depth of the first layer: 2..4, chosen per launch to fit shared memory
 constexpr int XS_LD = KC + 4;   // x tile row pitch (floats): 16-byte aligned rows, conflict-light
 
-struct HeadDev {
-    const float* blob;
-    int n_in, n_layers, layernorm, final_act;
-    int dims[OWW_MAX_HEAD_LAYERS + 1];
-    int w_off[OWW_MAX_HEAD_LAYERS], b_off[OWW_MAX_HEAD_LAYERS], g_off[OWW_MAX_HEAD_LAYERS], h_off[OWW_MAX_HEAD_LAYERS];
-    int col0;
-};
 struct HeadsArgs {
     HeadDev head[16];
     FeatSrc src;

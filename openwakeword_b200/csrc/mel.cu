@@ -12,6 +12,7 @@
 // maximum is a block reduction; the CTA also advances the stream's PCM tail and mel
 // ring, so the whole frontend is one launch with no host round trip.
 #include "oww_internal.h"
+#include "mel_device.cuh"
 #include <cmath>
 #include <cstring>
 
@@ -28,10 +29,6 @@ struct MelDev {
     const float* mel_w;        // [32][OWW_MEL_MAXSUPPORT]
     int kmax;
 };
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
 
 __global__ void __launch_bounds__(kThreads) mel_kernel(MelLaunch p, MelDev c) {
     __shared__ float2 s_buf[kWarps][2][256];
@@ -63,68 +60,8 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelLaunch p, MelDev c) {
     float vmax = -INFINITY;
 
     for (int f = f0 + warp; f < T; f += kWarps) {
-        float2* a = s_buf[warp][0];
-        float2* b = s_buf[warp][1];
-        // windowed frame, packed z[n] = x[2n] + i x[2n+1]
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = lane + 32 * j;
-            const int s0 = f * OWW_HOP + 2 * n;
-            float x0, x1;
-            if (s0 + 1 < prefix) { x0 = (float)tail[s0]; x1 = (float)tail[s0 + 1]; }
-            else if (s0 >= prefix) { x0 = (float)__ldg(body + (s0 - prefix)); x1 = (float)__ldg(body + (s0 + 1 - prefix)); }
-            else { x0 = (float)tail[s0]; x1 = (float)__ldg(body); }
-            a[n] = make_float2(x0 * s_win[2 * n], x1 * s_win[2 * n + 1]);
-        }
-        __syncwarp();
-        // 256-point complex FFT, radix-4 Stockham autosort, 4 passes
-#pragma unroll
-        for (int Ns = 1; Ns < 256; Ns *= 4) {
-            const int tstep = 128 / Ns;
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int j = lane + 32 * jj;
-                const int k = j & (Ns - 1);
-                float2 v0 = a[j];
-                float2 v1 = cmul(a[j + 64], s_tw[k * tstep]);
-                float2 v2 = cmul(a[j + 128], s_tw[2 * k * tstep]);
-                float2 v3 = cmul(a[j + 192], s_tw[3 * k * tstep]);
-                float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
-                float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
-                float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
-                float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
-                float2 a3 = make_float2(d.y, -d.x);          // -i * (v1 - v3)
-                const int dst = (j / Ns) * Ns * 4 + k;
-                b[dst] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                b[dst + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                b[dst + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                b[dst + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
-            }
-            __syncwarp();
-            float2* t = a; a = b; b = t;
-        }
-        // unpack the real spectrum, power of the bins the filterbank reads
-        for (int k = lane; k < c.kmax; k += 32) {
-            float pw;
-            if (k == 256) {
-                const float x = a[0].x - a[0].y;
-                pw = x * x;
-            } else {
-                const float2 zk = a[k & 255];
-                const float2 zc = a[(256 - k) & 255];
-                const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
-                const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);   // Zk - conj(Zc')
-                const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);  // -i/2 * dd
-                const float2 t2 = cmul(s_tw[k], xo);
-                const float re = xe.x + t2.x, im = xe.y + t2.y;
-                pw = re * re + im * im;
-            }
-            s_pow[warp][k] = pw;
-        }
-        __syncwarp();
-        float acc = 0.f;
-        for (int i = 0; i < my_len; ++i) acc = fmaf(s_pow[warp][my_start + i], my_w[i], acc);
-        const float db = 10.0f * logf(fmaxf(acc, 1e-10f)) / logf(10.0f);
+        const float db = mel_frame_db(tail, prefix, body, f, s_buf[warp][0], s_buf[warp][1], s_pow[warp], s_tw, s_win, c.kmax,
+                                      my_start, my_len, my_w, lane);
         vmax = fmaxf(vmax, db);
         const int r = f - f0;
         const int slot = p.out_rows_mask >= 0 ? ((row0 + r) & p.out_rows_mask) : r;

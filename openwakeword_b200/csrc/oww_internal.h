@@ -31,6 +31,15 @@ struct Head {
     std::vector<size_t> w_off, b_off, g_off, h_off;   // float offsets per layer
 };
 
+// device-side description of one head (heads.cu launches, and the fused step kernel reads an array of these)
+struct HeadDev {
+    const float* blob;
+    int n_in, n_layers, layernorm, final_act;
+    int dims[OWW_MAX_HEAD_LAYERS + 1];
+    int w_off[OWW_MAX_HEAD_LAYERS], b_off[OWW_MAX_HEAD_LAYERS], g_off[OWW_MAX_HEAD_LAYERS], h_off[OWW_MAX_HEAD_LAYERS];
+    int col0;
+};
+
 // ---- fused incremental CNN (cnn_tc_inc.cu): per-layer geometry for a group of G streams --------
 struct IncLayer {            // "units" are 16-byte channel-group units (8 fp16 channels of one position)
     int kh3, final;
@@ -46,7 +55,8 @@ struct IncLayer {            // "units" are 16-byte channel-group units (8 fp16 
     int w_off, w_bytes, w_smem;             // packed weights: blob offset, size, smem byte offset
 };
 struct IncPlan {
-    int G, n_groups, tail_units, x_units, y_units, w_total_bytes, smem_bytes, pad_;
+    int G, n_groups, tail_units, x_units, y_units, w_total_bytes, smem_bytes;
+    int scratch_off;         // byte offset of the frontend (mel) scratch used before phase 0; 0 = does not fit
     IncLayer L[OWW_N_CONV];
 };
 
@@ -107,7 +117,9 @@ struct oww_ctx {
     int inc_cur = 0;                 // tails buffer the next step reads
     bool inc_primed = false;         // tails describe the newest window of every stream
     IncPlan inc_plan;
-    void* d_inc_dbg = nullptr;       // optional per-phase clock stamps (oww_debug_inc_clocks)
+    void* d_inc_dbg = nullptr;
+    HeadDev* d_head_devs = nullptr;  // device copy of the head descriptors (fused step kernel)
+    bool fuse_step = true;           // mode 3: run mel + CNN + ring append + heads as ONE launch when the step allows it       // optional per-phase clock stamps (oww_debug_inc_clocks)
 
     // host staging for oww_step_host / oww_step_host_submit: two slots so the H2D copy of step k+1 (copy_stream)
     // overlaps the kernels of step k (own_stream)
@@ -192,6 +204,10 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out);
 int oww_inc_setup(oww_ctx* ctx, const float* h_blob);
 int oww_inc_alloc_streams(oww_ctx* ctx);
 int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s);
+// whole step in one launch (n_chunks == 1, primed): PCM -> mel -> CNN -> ring append -> heads -> scores
+bool oww_fused_step_supported(const oww_ctx* ctx);
+int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, cudaStream_t s);
+int oww_heads_sync_devs(oww_ctx* ctx);
 int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
                     int stream0, cudaStream_t s);
 int oww_cnn_fp32_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);

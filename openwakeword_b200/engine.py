@@ -14,10 +14,10 @@ from .utils import load_embedding_weights, _torch
 
 class StreamEngine:
     def __init__(self, heads, n_streams, embedding="synthetic:0", feature_init=None, device_index=0,
-                 max_chunks=1, cnn_mode=_native.CNN_FP32_WINDOW, window_batch=0):
+                 max_chunks=1, cnn_mode=_native.CNN_FP32_WINDOW, window_batch=0, fuse_step=True):
         """heads: list of head dicts (weights.synthetic_head / load_head)."""
         self.ctx = _native.Context(device=device_index, max_chunks=max_chunks, cnn_mode=cnn_mode,
-                                   window_batch=window_batch)
+                                   window_batch=window_batch, fuse_step=fuse_step)
         self.ctx.load_mel()
         self.ctx.load_embedding(_weights.pack_embedding_blob(load_embedding_weights(embedding)))
         for h in heads:

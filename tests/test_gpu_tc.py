@@ -98,8 +98,9 @@ def test_tc_incremental_vs_window_modes(torch_cuda, built_library):
     pcm[::4] = rng.integers(-1000, 1000, (len(pcm[::4]), pcm.shape[1]))
     pcm[1::4, : pcm.shape[1] // 2] = 0
     out, feats, mels = {}, {}, {}
-    for mode in (0, 2, 3):
-        eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=mode, max_chunks=2)
+    for mode in (0, 2, 3, 13):        # 13 = mode 3 with the steady-state step kept as separate launches
+        eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=mode % 10, max_chunks=2,
+                           fuse_step=mode != 13)
         pos, rows = 0, []
         for si, n in enumerate(plan):
             if si == 6:
@@ -111,6 +112,9 @@ def test_tc_incremental_vs_window_modes(torch_cuda, built_library):
     d32 = np.abs(out[3] - out[2])
     print("max |score_inc - score_window_tc| =", d32.max(), "  max |feat diff| =", np.abs(feats[3] - feats[2]).max())
     print("max |score_inc - score_fp32| =", np.abs(out[3] - out[0]).max())
+    print("fused step vs separate launches: max |score diff| =", np.abs(out[3] - out[13]).max(),
+          " max |feat diff| =", np.abs(feats[3] - feats[13]).max())
     assert np.abs(feats[3] - feats[2]).max() < 2e-3
+    assert np.abs(out[3] - out[13]).max() < 1e-6 and np.abs(feats[3] - feats[13]).max() < 1e-6
     assert d32.max() < 2e-4
     assert np.abs(out[3] - out[0]).max() < 1e-3
