@@ -154,11 +154,13 @@ int oww_debug_layer(oww_ctx* ctx, const float* d_windows, int n, int layer, floa
  * Pure host computation (usable without a GPU): tests/test_inc_plan.py replays it in NumPy.          */
 int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int max_ints);
 
-/* cnn_mode 3 only: re-runs the last fused incremental pass with clock64() stamps taken by CTA 0 at the start
- * of each of the 20 layer phases of its first group (+ one at the end) in h_out[0..20]; then per layer l:
- * h_out[21+l] cycles the MMA warp waited for the layer's weights, [41+l] its MMA issue time, [61+l] phase
- * start -> first accumulator ready (epilogue view), [81+l] phase start -> last tile stored.  101 values. */
-int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_out101);
+/* cnn_mode 3 only, instrumentation: oww_debug_inc_clocks arms a clock buffer; the next step then records clock64()
+ * stamps taken by CTA 0 on its first group; oww_debug_inc_clocks_read synchronises and returns 104 values:
+ * [0..19] start of each layer phase, [20] end of layer 19, per layer l [21+l] cycles the MMA warp waited for weights,
+ * [41+l] its MMA issue time, [61+l] phase start -> first accumulator ready, [81+l] phase start -> last tile stored,
+ * [101] group start (before the fused frontend), [102] end of the fused heads phase (0 when the step was not fused). */
+int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_unused);
+int oww_debug_inc_clocks_read(oww_ctx* ctx, int64_t* h_out104);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 uint64_t oww_launch_count(const oww_ctx* ctx);       /* kernels launched by this handle so far   */

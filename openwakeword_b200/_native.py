@@ -58,6 +58,7 @@ _SIGNATURES = {
     "oww_debug_layer": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "oww_debug_inc_plan": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
     "oww_debug_inc_clocks": (C.c_int, [_P, _P]),
+    "oww_debug_inc_clocks_read": (C.c_int, [_P, _P]),
     "oww_launch_count": (C.c_uint64, [_P]),
     "oww_enable_stage_timing": (C.c_int, [_P, C.c_int]),
     "oww_stage_ms": (C.c_int, [_P, _P]),
@@ -225,9 +226,13 @@ class Context:
     def debug_layer(self, d_windows, n, layer, d_out, stream=None):
         self._check(self.lib.oww_debug_layer(self.h, _ptr(d_windows), n, layer, _ptr(d_out), stream))
 
-    def debug_inc_clocks(self):
-        out = np.zeros(101, np.int64)
+    def debug_inc_clocks_arm(self):
+        out = np.zeros(104, np.int64)
         self._check(self.lib.oww_debug_inc_clocks(self.h, _ptr(out)))
+
+    def debug_inc_clocks_read(self):
+        out = np.zeros(104, np.int64)
+        self._check(self.lib.oww_debug_inc_clocks_read(self.h, _ptr(out)))
         return out
 
     # ---- introspection ----

@@ -597,16 +597,17 @@ int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_out21) {
         return oww_fail(ctx, OWW_EINVAL, "needs cnn_mode 3 after at least one step");
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
     OWW_CUDA(ctx, cudaDeviceSynchronize());
-    if (!ctx->d_inc_dbg) OWW_CUDA(ctx, cudaMalloc(&ctx->d_inc_dbg, 101 * sizeof(int64_t)));
-    OWW_CUDA(ctx, cudaMemset(ctx->d_inc_dbg, 0, 101 * sizeof(int64_t)));
-    // re-run the newest window's incremental pass into the scratch embeddings (tails ping-pong restored afterwards)
-    const int cur = ctx->inc_cur;
-    ctx->inc_cur = cur ^ 1;                       // read the tails the last step consumed
-    int rc = oww_cnn_inc_step(ctx, 0, ctx->d_emb_tmp, ctx->own_stream);
-    ctx->inc_cur = cur;
-    if (rc) return rc;
-    OWW_CUDA(ctx, cudaStreamSynchronize(ctx->own_stream));
-    OWW_CUDA(ctx, cudaMemcpy(h_out21, ctx->d_inc_dbg, 101 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (!ctx->d_inc_dbg) OWW_CUDA(ctx, cudaMalloc(&ctx->d_inc_dbg, 104 * sizeof(int64_t)));
+    OWW_CUDA(ctx, cudaMemset(ctx->d_inc_dbg, 0, 104 * sizeof(int64_t)));
+    // stamps are taken by the NEXT step the caller runs; this call only arms the buffer
+    return OWW_OK;
+}
+
+int oww_debug_inc_clocks_read(oww_ctx* ctx, int64_t* h_out21) {
+    if (!ctx || !h_out21 || !ctx->d_inc_dbg) return oww_fail(ctx, OWW_EINVAL, "clock buffer not armed");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaDeviceSynchronize());
+    OWW_CUDA(ctx, cudaMemcpy(h_out21, ctx->d_inc_dbg, 104 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     cudaFree(ctx->d_inc_dbg); ctx->d_inc_dbg = nullptr;
     return OWW_OK;
 }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 128); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
         mbar_init(wfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
             for (int c = 0; c < NP; c += 16) tmem_ld16(taddr + c, v + c);
             tmem_wait_ld();
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
             const int64_t m = (int64_t)tile * 128 + row;

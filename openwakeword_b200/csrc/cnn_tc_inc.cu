@@ -31,6 +31,7 @@ constexpr int kIncEpiWarps = 16;                         // four per TMEM lane q
 constexpr int kIncThreads = (kIncEpiWarps + 2) * 32;      // 576
 constexpr int kIncAcc = 4;                                // TMEM accumulator stages (4 x 128 columns)
 constexpr int kIncMaxG = 7;
+constexpr int kMelNF = 2;                                  // frames a warp of the fused frontend processes at once
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -62,6 +63,7 @@ struct IncArgs {
     float* feat_ring; int64_t feat_stride; int feat_mask; int* feat_count;
     const HeadDev* heads; int n_heads; int max_n_in;
     float* scores; int score_stride;
+    int hring_off, hslot_bytes, hns;                          // smem ring the producer streams the heads' first-layer weights through
 };
 
 __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_constant__ IncArgs a) {
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     // [0, 2048): barriers, TMEM slot, layer-0 weights.  Activations grow from 2048 up; the per-layer weight
     // slots sit at the top of the arena (offsets in the plan, checked against the activation extents).
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 + 2 * kIncAcc);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * kIncAcc);
     float* s_l0 = reinterpret_cast<float*>(smem + 256);              // 9*24 + 24 + 24 floats
     uint4* act0 = reinterpret_cast<uint4*>(smem + 2048);            // activation arena; tensors at plan offsets
 
@@ -83,11 +85,16 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
     auto tfull = [&](int s) { return bar0 + 8u * (4 + s); };
     auto tempty = [&](int s) { return bar0 + 8u * (4 + kIncAcc + s); };
     const uint32_t tails_bar = bar0 + 8u * (4 + 2 * kIncAcc);
+    const uint32_t hstart_bar = bar0 + 8u * (5 + 2 * kIncAcc);
+    auto hfull = [&](int i) { return bar0 + 8u * (6 + 2 * kIncAcc + i); };
+    auto hempty = [&](int i) { return bar0 + 8u * (10 + 2 * kIncAcc + i); };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(wfull(i), 1); mbar_init(wempty(i), 1); }
-        for (int s = 0; s < kIncAcc; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), kIncEpiWarps * 32); }
+        for (int s = 0; s < kIncAcc; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), kIncEpiWarps); }   // one arrival per epilogue warp
         mbar_init(tails_bar, 1);
+        mbar_init(hstart_bar, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(hfull(i), 1); mbar_init(hempty(i), kIncEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 9 * 24; i += kIncThreads) s_l0[i] = a.w0[i];
@@ -106,6 +113,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         // ===================== weight producer =====================
         if (lane == 0) {
             uint32_t par[2] = {0, 0};
+            uint32_t hs_par = 0, he_par = 0; int hchunk = 0;
             for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
                 for (int l = 1; l < OWW_N_CONV; ++l) {
                     const int i = l & 1;
@@ -113,6 +121,23 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     mbar_expect_tx(wfull(i), (uint32_t)P.L[l].w_bytes);
                     bulk_g2s(smem_u32(smem + P.L[l].w_smem), a.wblob + P.L[l].w_off, (uint32_t)P.L[l].w_bytes, wfull(i));
                     par[i] ^= 1;
+                }
+                if (a.fused && a.n_heads > 0) {
+                    // heads phase: stream every head's first-layer matrix, one 96-row feature-row chunk at a time
+                    mbar_wait(hstart_bar, hs_par); hs_par ^= 1;
+                    for (int hh = 0; hh < a.n_heads; ++hh) {
+                        const HeadDev& H = a.heads[hh];
+                        const uint32_t bytes = (uint32_t)(96 * H.dims[1]) * 4u;
+                        const float* W = H.blob + H.w_off[0];
+                        for (int c = 0; c < H.n_in; ++c) {
+                            const int slot = hchunk % a.hns;
+                            mbar_wait(hempty(slot), ((he_par >> slot) & 1u) ^ 1u);
+                            mbar_expect_tx(hfull(slot), bytes);
+                            bulk_g2s(smem_u32(smem + a.hring_off + slot * a.hslot_bytes), W + (int64_t)c * 96 * H.dims[1], bytes, hfull(slot));
+                            he_par ^= 1u << slot;
+                            ++hchunk;
+                        }
+                    }
                 }
             }
         }
@@ -188,18 +213,19 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         int acc = 0; uint32_t acc_par = 0;
         uint32_t epar[2] = {0, 0};
         uint32_t epi_tails_par = 0;
+        uint32_t hf_par = 0; int hchunk_e = 0;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
             int* s_cnt = reinterpret_cast<int*>(smem + 1536);      // [0..7] mel row count, [8..15] feature count, before this step
-            float* s_mel = reinterpret_cast<float*>(smem + P.scratch_off + 6144 + 65536 + kIncEpiWarps * 264 * 4);   // [G][8][32]
+            float* s_mel = reinterpret_cast<float*>(smem + P.scratch_off + 6144);   // [G][8][32] this step's mel rows
+            if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[101] = clock64();
             if (a.fused) {
                 // ===== frontend: log-mel of this step's 8 frames per stream (K1 inside the step kernel) =====
                 uint8_t* sc = smem + P.scratch_off;
                 float2* s_tw = reinterpret_cast<float2*>(sc);
                 float* s_win = reinterpret_cast<float*>(sc + 4096);
-                float2* s_buf = reinterpret_cast<float2*>(sc + 6144);
-                float* s_pow = reinterpret_cast<float*>(sc + 6144 + 65536);
+                uint8_t* s_work = smem + 2048 + warp * (kMelNF * kMelFrameScratch);   // FFT work buffers: arena base, dead after this phase
                 float* s_floor = s_mel + G * 256;
                 for (int i = et; i < 512; i += kIncEpiWarps * 32) { s_tw[i] = a.mel_twiddle[i]; s_win[i] = a.mel_window[i]; }
                 if (et < G) {
@@ -210,15 +236,21 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 named_bar_sync(2, kIncEpiWarps * 32);
                 const int my_start = a.mel_start[lane], my_len = a.mel_len[lane];
                 const float* my_w = a.mel_w + lane * OWW_MEL_MAXSUPPORT;
-                for (int fi = warp; fi < G * 8; fi += kIncEpiWarps) {
-                    const int g = fi >> 3, f = fi & 7, b = grp * G + g;
-                    float db = 0.f;
-                    if (b < a.B)
-                        db = mel_frame_db(a.tail + (int64_t)b * OWW_TAIL, OWW_TAIL, a.pcm + (int64_t)b * a.pcm_stride, f,
-                                          s_buf + warp * 512, s_buf + warp * 512 + 256, s_pow + warp * 264, s_tw, s_win, a.mel_kmax,
-                                          my_start, my_len, my_w, lane);
-                    s_mel[fi * 32 + lane] = db;
-                    __syncwarp();
+                // kMelNF frames per warp at a time (interleaved instruction streams); frames of dead slots in a ragged last
+                // group are computed on stream 0's audio and discarded
+                for (int fi = warp * kMelNF; fi < G * 8; fi += kIncEpiWarps * kMelNF) {
+                    const int16_t* tl[kMelNF]; const int16_t* bd[kMelNF]; int fr[kMelNF]; float db[kMelNF];
+#pragma unroll
+                    for (int i = 0; i < kMelNF; ++i) {
+                        const int fj = fi + i < G * 8 ? fi + i : fi;
+                        int b = grp * G + (fj >> 3);
+                        if (b >= a.B) b = grp * G;
+                        tl[i] = a.tail + (int64_t)b * OWW_TAIL; bd[i] = a.pcm + (int64_t)b * a.pcm_stride; fr[i] = fj & 7;
+                    }
+                    mel_frames_db<kMelNF>(tl, OWW_TAIL, bd, fr, s_work, s_tw, s_win, a.mel_kmax, my_start, my_len, my_w, lane, db);
+#pragma unroll
+                    for (int i = 0; i < kMelNF; ++i)
+                        if (fi + i < G * 8) s_mel[(fi + i) * 32 + lane] = db[i];
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 if (warp < G) {                                    // per-call (= per stream, this step) maximum -> -80 dB floor
@@ -343,7 +375,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             if (pl0 + k < pl1) tmem_ld8(taddr + (pl0 + k) * 8, v[k]);
                         tmem_wait_ld();
                         tc_fence_before();
-                        mbar_arrive(tempty(acc));
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty(acc));       // per-warp arrival: 16 smem atomics per tile instead of 512
                         if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
                         const int m = tile * 128 + row;
                         if (m >= L.M) continue;
@@ -448,6 +481,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             if (a.fused) {
                 // ===== K3 inside the step kernel: every head on this group's streams, straight from the feature ring =====
                 named_bar_sync(2, kIncEpiWarps * 32);              // the new embedding rows (written by this CTA) are visible
+                if (et == 0 && a.n_heads > 0) mbar_arrive(hstart_bar);           // producer may start streaming head weights
                 const int NI = a.max_n_in;
                 float* feats = reinterpret_cast<float*>(smem + 2048);            // [G][NI][96]
                 float* red = feats + G * NI * 96;                                // [4][G][128]
@@ -466,24 +500,32 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 for (int hh = 0; hh < a.n_heads; ++hh) {
                     const HeadDev& H = a.heads[hh];
                     const int D1 = H.dims[1], off = NI - H.n_in;
-                    {   // first layer: 4 K-slices x 128 columns, same summation order as heads_kernel
+                    {   // first layer: 4 K-slices x 128 columns, same summation order as heads_kernel; the weight rows
+                        // of feature row c arrive in ring slot (chunk % hns), streamed by the producer warp
                         const int slice = et >> 7, d = et & 127;
                         float acc[kIncMaxG];
 #pragma unroll
                         for (int g = 0; g < kIncMaxG; ++g) acc[g] = 0.f;
-                        if (d < D1) {
-                            const float* W = H.blob + H.w_off[0];
-                            for (int c = 0; c < H.n_in; ++c) {
-                                const float* wr = W + (int64_t)(c * 96 + slice * 24) * D1 + d;
+                        for (int c = 0; c < H.n_in; ++c) {
+                            const int slot = hchunk_e % a.hns;
+                            mbar_wait(hfull(slot), (hf_par >> slot) & 1u);
+                            hf_par ^= 1u << slot;
+                            ++hchunk_e;
+                            if (d < D1) {
+                                const float* wr = reinterpret_cast<const float*>(smem + a.hring_off + slot * a.hslot_bytes) + slice * 24 * D1 + d;
                                 const float* xr = feats + (off + c) * 96 + slice * 24;
 #pragma unroll 8
                                 for (int k8 = 0; k8 < 24; ++k8) {
-                                    const float w = __ldg(wr + (int64_t)k8 * D1);
+                                    const float w = wr[k8 * D1];
 #pragma unroll
                                     for (int g = 0; g < kIncMaxG; ++g)
                                         if (g < G) acc[g] = fmaf(xr[g * NI * 96 + k8], w, acc[g]);
                                 }
                             }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(hempty(slot));
+                        }
+                        if (d < D1) {
 #pragma unroll
                             for (int g = 0; g < kIncMaxG; ++g)
                                 if (g < G) red[(slice * G + g) * 128 + d] = acc[g];
@@ -507,6 +549,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             for (int i = et; i < G * D; i += kIncEpiWarps * 32) {
                                 const int g = i / D, d = i - g * D;
                                 float acc = 0.f;
+                                // the weight loads are independent of acc: unrolled 16 deep they overlap (each is an L2 round trip)
+#pragma unroll 16
                                 for (int k = 0; k < K; ++k) acc = fmaf(cur[g * 256 + k], __ldg(W + (int64_t)k * D + d), acc);
                                 nxt[g * 256 + d] = acc + __ldg(H.blob + H.b_off[l] + d);
                             }
@@ -560,6 +604,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 }
                 if (et < G && grp * G + et < a.B) a.feat_count[grp * G + et] = s_cnt[8 + et] + 1;
                 named_bar_sync(2, kIncEpiWarps * 32);
+                if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[102] = clock64();
             }
         }
     }
@@ -693,11 +738,13 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
             return oww_fail(ctx, OWW_EUNSUPPORTED, "fused-CNN smem plan does not fit at layer %d (G=%d)", l, G);
         if (l >= 2 && wsz(l) < wsz(l - 1)) return oww_fail(ctx, OWW_EUNSUPPORTED, "weight sizes must not shrink with depth");
     }
-    // frontend scratch used before phase 0 (fused step): twiddles 4 KB | window 2 KB | 16 x two 256-point buffers 64 KB |
-    // 16 x 264 power bins | G x 8 x 32 mel rows | G floors - placed right above layer 0's output, below the weight slots
+    // frontend of the fused step: FFT work buffers at the arena base (dead before layer 0 writes its output there);
+    // twiddles 4 KB | window 2 KB | G x 8 x 32 mel rows | G floors sit above both, below the weight slots of layers 1-2
     {
-        const int off = kActBase + r8(size_nx[0]) * 16;
-        const int need_b = 6144 + 65536 + kIncEpiWarps * 264 * 4 + G * 256 * 4 + 64;
+        int off = kActBase + r8(size_nx[0]) * 16;
+        const int work_end = kActBase + kIncEpiWarps * kMelNF * kMelFrameScratch;
+        if (work_end > off) off = (work_end + 127) & ~127;
+        const int need_b = 6144 + G * 256 * 4 + 64;
         P.scratch_off = (off + need_b <= P.L[1].w_smem && off + need_b <= P.L[2].w_smem) ? off : 0;
     }
     P.w_total_bytes = (int)w_off;
@@ -790,12 +837,21 @@ int oww_heads_sync_devs(oww_ctx* ctx) {
 bool oww_fused_step_supported(const oww_ctx* ctx) {
     if (!ctx->fuse_step || ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || !ctx->inc_primed) return false;
     if (ctx->inc_plan.scratch_off == 0 || ctx->heads.size() > 16) return false;
+    // In the fused kernel every group of G streams re-streams each head's first-layer matrix from L2; with many
+    // groups x many/large heads that traffic (and the 7-row tiles) loses to the stand-alone heads kernel's 32-row tiles.
+    {
+        size_t w1 = 0;
+        for (const Head& h : ctx->heads) w1 += (size_t)h.desc.dims[0] * h.desc.dims[1] * sizeof(float);
+        if ((size_t)ctx->inc_plan.n_groups * w1 > ((size_t)256 << 20)) return false;
+    }
     for (const Head& h : ctx->heads) {
         if (h.desc.dims[1] > 128) return false;
         for (int l = 1; l <= h.desc.n_layers; ++l) if (h.desc.dims[l] > 256) return false;
     }
     const size_t floats = (size_t)ctx->inc_plan.G * ((size_t)ctx->max_n_in * 96 + 4 * 128 + 2 * 256);
-    return 2048 + floats * 4 <= (size_t)ctx->inc_plan.L[OWW_N_CONV - 1].w_smem;
+    int d1max = 32;
+    for (const Head& h : ctx->heads) d1max = h.desc.dims[1] > d1max ? h.desc.dims[1] : d1max;
+    return 2048 + floats * 4 + 128 + (size_t)96 * d1max * 4 <= (size_t)ctx->inc_plan.L[2].w_smem;
 }
 
 static void fill_inc_args(oww_ctx* ctx, IncArgs& a) {
@@ -824,6 +880,18 @@ int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float
     a.feat_count = ctx->d_feat_count;
     a.heads = ctx->d_head_devs; a.n_heads = (int)ctx->heads.size(); a.max_n_in = ctx->max_n_in > 0 ? ctx->max_n_in : 1;
     a.scores = d_scores; a.score_stride = out_stride;
+    {   // ring for the heads' first-layer weights: after feats/red/h, below the first weight slot the next group prefetches
+        int d1max = 32;
+        for (const Head& h : ctx->heads) d1max = h.desc.dims[1] > d1max ? h.desc.dims[1] : d1max;
+        const int G = a.plan.G;
+        const int used = 2048 + (G * (a.max_n_in * 96 + 4 * 128 + 2 * 256)) * 4;
+        a.hring_off = (used + 127) & ~127;
+        a.hslot_bytes = 96 * d1max * 4;
+        const int avail = a.plan.L[2].w_smem - a.hring_off;
+        a.hns = avail / a.hslot_bytes;
+        if (a.hns > 4) a.hns = 4;
+        if (a.hns < 1 && !ctx->heads.empty()) return oww_fail(ctx, OWW_EUNSUPPORTED, "no room for the fused heads weight ring");
+    }
     const int grid = a.plan.n_groups < ctx->sm_count ? a.plan.n_groups : ctx->sm_count;
     tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
     OWW_LAUNCH_CHECK(ctx);

@@ -6,8 +6,10 @@
 
 namespace {
 
+// Explicit rounding intrinsics: the compiler may not re-associate or contract these differently in different inlined
+// contexts, so the stand-alone frontend kernel and the fused step kernel produce bit-identical mel rows.
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    return make_float2(__fmaf_rn(a.x, b.x, -__fmul_rn(a.y, b.y)), __fmaf_rn(a.x, b.y, __fmul_rn(a.y, b.x)));
 }
 
 // One warp computes frame f (512 samples at hop 160) of the virtual clip [tail (prefix samples) | body]:
@@ -26,7 +28,7 @@ __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, c
             if (s0 + 1 < prefix) { x0 = (float)tail[s0]; x1 = (float)tail[s0 + 1]; }
             else if (s0 >= prefix) { x0 = (float)__ldg(body + (s0 - prefix)); x1 = (float)__ldg(body + (s0 + 1 - prefix)); }
             else { x0 = (float)tail[s0]; x1 = (float)__ldg(body); }
-            a[n] = make_float2(x0 * s_win[2 * n], x1 * s_win[2 * n + 1]);
+            a[n] = make_float2(__fmul_rn(x0, s_win[2 * n]), __fmul_rn(x1, s_win[2 * n + 1]));
         }
         __syncwarp();
         // 256-point complex FFT, radix-4 Stockham autosort, 4 passes
@@ -60,7 +62,7 @@ __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, c
             float pw;
             if (k == 256) {
                 const float x = a[0].x - a[0].y;
-                pw = x * x;
+                pw = __fmul_rn(x, x);
             } else {
                 const float2 zk = a[k & 255];
                 const float2 zc = a[(256 - k) & 255];
@@ -68,8 +70,8 @@ __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, c
                 const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);   // Zk - conj(Zc')
                 const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);  // -i/2 * dd
                 const float2 t2 = cmul(s_tw[k], xo);
-                const float re = xe.x + t2.x, im = xe.y + t2.y;
-                pw = re * re + im * im;
+                const float re = __fadd_rn(xe.x, t2.x), im = __fadd_rn(xe.y, t2.y);
+                pw = __fmaf_rn(re, re, __fmul_rn(im, im));
             }
             pw_buf[k] = pw;
         }
@@ -78,6 +80,100 @@ __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, c
         for (int i = 0; i < my_len; ++i) acc = fmaf(pw_buf[my_start + i], my_w[i], acc);
         const float db = 10.0f * logf(fmaxf(acc, 1e-10f)) / logf(10.0f);
     return db;
+}
+
+// Same arithmetic as mel_frame_db for NF frames at once: the NF instruction streams are interleaved stage by stage, so
+// a lone warp (the fused step kernel runs only 16 of them per SM) has NF independent dependency chains in flight.
+// Frame i: clip pointers tail[i]/body[i], frame index f[i], work buffers bufs + i*kMelFrameScratch bytes laid out as
+// a[256] float2 | b[256] float2 | pw[320] float.  db[i] receives this lane's dB value.
+constexpr int kMelFrameScratch = 2048 + 2048 + 1280;
+template <int NF>
+__device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int prefix, const int16_t* const* body, const int* f,
+                                              uint8_t* bufs, const float2* s_tw, const float* s_win, int kmax, int my_start,
+                                              int my_len, const float* my_w, int lane, float* db) {
+    float2* a[NF]; float2* b[NF]; float* pw[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        a[i] = reinterpret_cast<float2*>(bufs + i * kMelFrameScratch);
+        b[i] = a[i] + 256;
+        pw[i] = reinterpret_cast<float*>(b[i] + 256);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = lane + 32 * j;
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            const int s0 = f[i] * OWW_HOP + 2 * n;
+            float x0, x1;
+            if (s0 + 1 < prefix) { x0 = (float)tail[i][s0]; x1 = (float)tail[i][s0 + 1]; }
+            else if (s0 >= prefix) { x0 = (float)__ldg(body[i] + (s0 - prefix)); x1 = (float)__ldg(body[i] + (s0 + 1 - prefix)); }
+            else { x0 = (float)tail[i][s0]; x1 = (float)__ldg(body[i]); }
+            a[i][n] = make_float2(__fmul_rn(x0, s_win[2 * n]), __fmul_rn(x1, s_win[2 * n + 1]));
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int Ns = 1; Ns < 256; Ns *= 4) {
+        const int tstep = 128 / Ns;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = lane + 32 * jj;
+            const int k = j & (Ns - 1);
+            const float2 t1 = s_tw[k * tstep], t2 = s_tw[2 * k * tstep], t3 = s_tw[3 * k * tstep];
+            const int dst = (j / Ns) * Ns * 4 + k;
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                float2 v0 = a[i][j];
+                float2 v1 = cmul(a[i][j + 64], t1);
+                float2 v2 = cmul(a[i][j + 128], t2);
+                float2 v3 = cmul(a[i][j + 192], t3);
+                float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
+                float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+                float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+                float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
+                float2 a3 = make_float2(d.y, -d.x);
+                b[i][dst] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                b[i][dst + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                b[i][dst + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                b[i][dst + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NF; ++i) { float2* t = a[i]; a[i] = b[i]; b[i] = t; }
+    }
+    for (int k = lane; k < kmax; k += 32) {
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            float p;
+            if (k == 256) {
+                const float x = a[i][0].x - a[i][0].y;
+                p = __fmul_rn(x, x);
+            } else {
+                const float2 zk = a[i][k & 255];
+                const float2 zc = a[i][(256 - k) & 255];
+                const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+                const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);
+                const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);
+                const float2 t2 = cmul(s_tw[k], xo);
+                const float re = __fadd_rn(xe.x, t2.x), im = __fadd_rn(xe.y, t2.y);
+                p = __fmaf_rn(re, re, __fmul_rn(im, im));
+            }
+            pw[i][k] = p;
+        }
+    }
+    __syncwarp();
+    float acc[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) acc[i] = 0.f;
+    for (int q = 0; q < my_len; ++q) {
+        const float w = my_w[q];
+#pragma unroll
+        for (int i = 0; i < NF; ++i) acc[i] = fmaf(pw[i][my_start + q], w, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NF; ++i) db[i] = 10.0f * logf(fmaxf(acc[i], 1e-10f)) / logf(10.0f);
+    __syncwarp();
 }
 
 }  // namespace
