@@ -39,7 +39,7 @@ STREAMS_PER_GPU = 1024
 CHUNK = 1280
 # dram__bytes_read.sum + dram__bytes_write.sum of the CNN stage for one 1024-stream step, from the ncu --set full
 # captures summarised in profiles/README.md (bytes per step; None = not captured for that mode)
-TRAFFIC = {2: 1.177e9, 3: 2.44e7}
+TRAFFIC = {2: 1.177e9, 3: 3.37e7}
 METRIC = "80ms audio-frames/sec (concurrent streams)"
 UNIT = "frames/s"
 
@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)],
+                                          "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -180,8 +180,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     arm = CpuArm()
-    frames_each = 4
-    for _ in range(max(args.warmup, 3)):
+    frames_each = max(1, min(4, 400 // max(args.steps, 1)))      # bounded sample: the whole run stays within minutes
+    for _ in range(min(max(args.warmup, 3), 5)):
         arm.step(frames_each)
     t = 0.0
     for _ in range(args.steps):
@@ -230,7 +230,7 @@ def run_own_arm(args):
 
     def factory(n_local, lo, hi):
         return StreamEngine(bench_heads(), n_local, embedding="synthetic:0", device_index=local, max_chunks=1,
-                            cnn_mode=args.cnn_mode)
+                            cnn_mode=args.cnn_mode, fuse_step=not args.no_fuse)
     sh = owd.ShardedStreams(n_total, factory, rank=rank, world=world)
     eng = sh.engine
     host_pcm = synth_pcm(B, POOL, 1234 + rank)                   # [B, POOL*1280]
@@ -315,9 +315,12 @@ def run_own_arm(args):
            "8 new mel rows per frame (11.2 MFLOP, SURVEY.md F10/8d) - 'achieved' is reference-algorithmic, "
            "'executed_tflops' is what the tensor pipe actually issued",
     }[args.cnn_mode]
+    fused = args.cnn_mode == 3 and not args.no_fuse
     kernel_name = {0: "embedding CNN stage: 20 conv_kernel + 5 pool_kernel launches (cnn_fp32.cu)",
                    2: "embedding CNN stage: tc_conv0 + 19 tc_conv_kernel + 5 tc_pool launches (cnn_tc.cu)",
-                   3: "embedding CNN stage: tc_inc_kernel, one fused launch (cnn_tc_inc.cu) + ring append"}[args.cnn_mode]
+                   3: "tc_inc_kernel (cnn_tc_inc.cu): the whole step in ONE launch - log-mel frontend, 20-layer tcgen05 CNN, ring "
+                      "append and heads; its duration therefore includes the frontend (~21 us) and heads (~33 us) phases"
+                      if fused else "embedding CNN stage: tc_inc_kernel (fused 20-layer launch) + ring append"}[args.cnn_mode]
     dtype = "f32" if args.cnn_mode == 0 else "f16 operands / f32 accumulate (mel, BN, heads in f32)"
     value = n_total * K / (ms_dev * 1e-3)
     e2e_v = n_total * K / (ms_e2e * 1e-3)
@@ -340,7 +343,7 @@ def run_own_arm(args):
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": dtype, "data": "synthetic",
         "config": {"workload": "configs[1]: 1024 concurrent synthetic 16 kHz streams per GPU, 80 ms frames, 1 wake-word head",
-                   "streams_per_gpu": B, "heads": 1, "cnn_mode": args.cnn_mode,
+                   "streams_per_gpu": B, "heads": 1, "cnn_mode": args.cnn_mode, "fused_step": bool(fused),
                    "l2": f"inputs larger than L2: {POOL} distinct PCM batches ({POOL * B * CHUNK * 2 / 1e6:.0f} MB) cycled",
                    "weights": "synthetic seed 0 (reference shapes); released .onnx weights absent",
                    "parity": parity_label(),
@@ -367,11 +370,12 @@ def run_own_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--cnn-mode", type=int, default=3, help="0 fp32 window, 2 tcgen05 window, 3 tcgen05 fused incremental")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="mode 3: keep mel / CNN / append / heads as separate launches (stage breakdown)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
