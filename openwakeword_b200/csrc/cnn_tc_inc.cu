@@ -354,8 +354,14 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     epar[l & 1] ^= 1;
                     const float* sb = reinterpret_cast<const float*>(smem + L.w_smem + 3 * L.cgp * L.np * 16);
                     const int np8 = L.np / 8;
-                    const int ph = (np8 + 3) / 4;
-                    const int pl0 = min(np8, part * ph), pl1 = min(np8, pl0 + ph);
+                    // Work split of the 16 warps (4 lane quarters x 4 "parts").  A part owns up to 3 channel-group planes of a
+                    // tile; layers with few planes therefore need only PT = 1 or 2 parts per tile, and the other parts take
+                    // the NEXT tiles: 4/PT tiles are drained concurrently (one TMEM stage each), so the per-tile latency
+                    // chain (wait -> tcgen05.ld -> math -> store) of one part overlaps the others'.
+                    const int PT = L.final ? 4 : (L.cg_out <= 3 ? 1 : (L.cg_out <= 6 ? 2 : 4));
+                    const int sets = 4 / PT, my_set = part / PT, my_sub = part % PT;
+                    const int ph = PT == 4 ? (np8 + 3) / 4 : 3;
+                    const int pl0 = min(np8, my_sub * ph), pl1 = min(np8, pl0 + ph);
                     uint4* dst = L.pool_t ? (act0 + L.tmp_base) : nx;
                     const int dpitch = L.pool_t ? L.tmp_pitch : L.nx_pitch;
                     const int t_off_units = L.pool_t ? 0 : L.nx_t_off * G * L.Wp;
@@ -364,20 +370,22 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     const bool edbg = a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0;
                     long long e0 = 0;
                     if (edbg) e0 = clock64();
-                    for (int tile = 0; tile < n_tiles; ++tile) {
-                        mbar_wait(tfull(acc), acc_par);
+                    const int acc0 = acc; const uint32_t par0 = acc_par;
+                    for (int tile = my_set; tile < n_tiles; tile += sets) {
+                        const int stage = (acc0 + tile) & (kIncAcc - 1);
+                        const uint32_t spar = par0 ^ (uint32_t)(((acc0 + tile) >> 2) & 1);
+                        mbar_wait(tfull(stage), spar);
                         if (edbg && tile == 0) a.dbg_clock[61 + l] = clock64() - e0;     // phase start -> first accumulator ready
                         tc_fence_after();
                         uint32_t v[3][8];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u;
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)stage * 128u;
 #pragma unroll
                         for (int k = 0; k < 3; ++k)
                             if (pl0 + k < pl1) tmem_ld8(taddr + (pl0 + k) * 8, v[k]);
                         tmem_wait_ld();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty(acc));       // per-warp arrival: 16 smem atomics per tile instead of 512
-                        if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
+                        if (lane == 0) mbar_arrive_cnt(tempty(stage), (uint32_t)sets);   // 4*PT warps drain a tile: sets arrivals each = 16
                         const int m = tile * 128 + row;
                         if (m >= L.M) continue;
                         const int f = m % L.Wp;
@@ -424,6 +432,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                                 tout[L.nx_tail_off + pl * (2 * G * L.Wp) + (m - tail_start)] = pk;
                         }
                     }
+                    acc_par = par0 ^ (uint32_t)(((acc0 + n_tiles) >> 2) & 1);
+                    acc = (acc0 + n_tiles) & (kIncAcc - 1);
                     if (edbg) a.dbg_clock[81 + l] = clock64() - e0;                       // phase start -> last tile stored
                     if (L.pool_t) {
                         // ---- max-pool: tmp (unpooled conv output) -> nx ----
