@@ -60,7 +60,39 @@ def c5(N=125000, S=32000, slab=25000):
     return {"config": f"C5 share: bulk predict_clips over {N} x 2 s clips (host arrays in, host scores out), 6 heads, 1 GPU",
             "clips_per_s": N / dt, "frames_per_s": frames / dt, "seconds": dt, "steps_per_clip": sc.shape[1], "labels": len(labels)}
 
+def c4(B=8192, K=200):
+    """C4: 65 536 streams sharded over 8 GPUs (8192 per GPU), 4 heads, VAD off; launch under torchrun --nproc-per-node 8."""
+    import torch.distributed as dist
+    from openwakeword_b200 import distributed as owd
+    rank, world, local = owd.init_process_group("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    torch.cuda.set_device(local)
+    hs = [W.synthetic_head(seed=10 + i) for i in range(4)]
+    eng = StreamEngine(hs, B, cnn_mode=3, device_index=local)
+    rng = np.random.default_rng(100 + rank)
+    pcm = [torch.from_numpy(rng.integers(-1000, 1000, (B, 1280)).astype(np.int16)).cuda() for _ in range(16)]
+    out = torch.empty((B, eng.n_cols), dtype=torch.float32, device="cuda")
+    def step(k):
+        eng.step(pcm[k % 16], 1, out)
+        return owd.gather_scores(out, B * world)
+    for k in range(5): step(k)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K): g = step(k)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    res = {"config": f"C4 {B * world} streams on {world} GPUs ({B}/GPU), 4 heads, one score all-gather per step",
+           "frames_per_s": B * world / (ms * 1e-3), "ms_per_step": ms, "gathered_shape": list(g.shape)}
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    return res if rank == 0 else None
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c3", "c5"]
     for w in which:
-        print(json.dumps({"c1": c1, "c3": c3, "c5": c5}[w]()), flush=True)
+        r = {"c1": c1, "c3": c3, "c5": c5, "c4": c4}[w]()
+        if r is not None:
+            print(json.dumps(r), flush=True)
