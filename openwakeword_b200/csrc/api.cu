@@ -257,21 +257,34 @@ int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, s
     if (ctx->heads.size() >= 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 heads per handle");
     Head h;
     h.desc = *desc;
-    size_t off = 0;
+    // Device layout: the caller's tensors in order, each starting on a 16-byte boundary (the fused step kernel streams
+    // weight rows with bulk copies, which need 16-byte aligned sources).  `src` walks the packed host blob.
+    size_t off = 0, src = 0;
+    std::vector<float> staged;
+    auto place = [&](size_t n) {
+        off = (off + 3) & ~(size_t)3;
+        const size_t at = off;
+        if (src + n <= n_floats) {
+            staged.resize(at + n + 4, 0.f);
+            std::memcpy(staged.data() + at, h_blob + src, n * sizeof(float));
+        }
+        src += n; off += n;
+        return at;
+    };
     for (int l = 0; l < desc->n_layers; ++l) {
         const int din = desc->dims[l], dout = desc->dims[l + 1];
         if (dout < 1 || dout > 256) return oww_fail(ctx, OWW_EUNSUPPORTED, "layer width %d outside 1..256", dout);
-        h.w_off.push_back(off); off += (size_t)din * dout;
-        h.b_off.push_back(off); off += dout;
+        h.w_off.push_back(place((size_t)din * dout));
+        h.b_off.push_back(place(dout));
         if (desc->layernorm && l < desc->n_layers - 1) {
-            h.g_off.push_back(off); off += dout;
-            h.h_off.push_back(off); off += dout;
+            h.g_off.push_back(place(dout));
+            h.h_off.push_back(place(dout));
         } else { h.g_off.push_back(0); h.h_off.push_back(0); }
     }
-    if (off != n_floats) return oww_fail(ctx, OWW_EINVAL, "head blob has %zu floats, descriptor needs %zu", n_floats, off);
+    if (src != n_floats) return oww_fail(ctx, OWW_EINVAL, "head blob has %zu floats, descriptor needs %zu", n_floats, src);
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
-    OWW_CUDA(ctx, cudaMalloc(&h.d_blob, off * sizeof(float)));
-    OWW_CUDA(ctx, cudaMemcpy(h.d_blob, h_blob, off * sizeof(float), cudaMemcpyHostToDevice));
+    OWW_CUDA(ctx, cudaMalloc(&h.d_blob, staged.size() * sizeof(float)));
+    OWW_CUDA(ctx, cudaMemcpy(h.d_blob, staged.data(), staged.size() * sizeof(float), cudaMemcpyHostToDevice));
     h.n_out = desc->dims[desc->n_layers];
     h.col0 = ctx->n_out_total;
     ctx->n_out_total += h.n_out;

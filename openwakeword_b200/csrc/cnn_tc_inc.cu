@@ -66,6 +66,13 @@ struct IncArgs {
     int hring_off, hslot_bytes, hns;                          // smem ring the producer streams the heads' first-layer weights through
 };
 
+// Rows of a later head layer (K x D floats) per ring chunk: a multiple of 4 rows (16-byte chunk starts) that fits a slot.
+__device__ __forceinline__ int head_rows(int slot_bytes, int K, int D) {
+    const int r = (slot_bytes / (D * 4)) & ~3;
+    return r < K ? r : K;
+}
+
+// 96 registers is the ceiling for 18 warps: registers are allocated for warps in fours (20 x 32 x 96 = 61 440 of 65 536)
 __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_constant__ IncArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const IncPlan& P = a.plan;
@@ -137,6 +144,21 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             he_par ^= 1u << slot;
                             ++hchunk;
                         }
+                        // the later (small) layers follow through the same ring, head_rows() weight rows at a time
+                        for (int l = 1; l < H.n_layers; ++l) {
+                            const int K = H.dims[l], D = H.dims[l + 1];
+                            const int rows = head_rows(a.hslot_bytes, K, D);
+                            const float* Wl = H.blob + H.w_off[l];
+                            for (int k0 = 0; k0 < K; k0 += rows) {
+                                const uint32_t cb = ((uint32_t)(min(rows, K - k0) * D) * 4u + 15u) & ~15u;
+                                const int slot = hchunk % a.hns;
+                                mbar_wait(hempty(slot), ((he_par >> slot) & 1u) ^ 1u);
+                                mbar_expect_tx(hfull(slot), cb);
+                                bulk_g2s(smem_u32(smem + a.hring_off + slot * a.hslot_bytes), Wl + (int64_t)k0 * D, cb, hfull(slot));
+                                he_par ^= 1u << slot;
+                                ++hchunk;
+                            }
+                        }
                     }
                 }
             }
@@ -182,21 +204,23 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     mbar_wait(tempty(acc), acc_par ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-                    uint32_t accumulate = 0;
+                    // one elect.sync per tile: the elected lane issues the tile's MMAs and the commit back to back
+                    if (elect_one()) {
+                        uint32_t accumulate = 0;
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const uint32_t a_tap = a_unit0 + (uint32_t)(tile * 128 + L.tap[j]);
-                        const uint32_t b_tap = b_unit0 + (uint32_t)(j * L.cgp * L.np);
-                        for (int q = 0; q < nq; ++q) {
-                            const uint32_t alo = ((2 * q + 1 < L.cg_in) ? a_hi_pair : a_hi_self) |
-                                                 ((a_tap + (uint32_t)(2 * q * L.in_pitch)) & 0x3FFFu);
-                            const uint32_t blo = b_lo0 | ((b_tap + (uint32_t)(2 * q * L.np)) & 0x3FFFu);
-                            if (elect_one())
+                        for (int j = 0; j < 3; ++j) {
+                            const uint32_t a_tap = a_unit0 + (uint32_t)(tile * 128 + L.tap[j]);
+                            const uint32_t b_tap = b_unit0 + (uint32_t)(j * L.cgp * L.np);
+                            for (int q = 0; q < nq; ++q) {
+                                const uint32_t alo = ((2 * q + 1 < L.cg_in) ? a_hi_pair : a_hi_self) |
+                                                     ((a_tap + (uint32_t)(2 * q * L.in_pitch)) & 0x3FFFu);
+                                const uint32_t blo = b_lo0 | ((b_tap + (uint32_t)(2 * q * L.np)) & 0x3FFFu);
                                 tc_mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | alo, ((uint64_t)desc_hi << 32) | blo, idesc, accumulate);
-                            accumulate = 1;
+                                accumulate = 1;
+                            }
                         }
+                        tc_commit(tfull(acc));
                     }
-                    if (elect_one()) tc_commit(tfull(acc));
                     __syncwarp();
                     if (++acc == kIncAcc) { acc = 0; acc_par ^= 1; }
                 }
@@ -304,48 +328,60 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
 
                 if (l == 0) {
                     // ---- layer 0 on CUDA cores: 8 new rows from the last 10 mel rows of each stream ----
-                    const int Wp = 33;
-                    for (int p = et; p < 8 * G * Wp; p += kIncEpiWarps * 32) {
-                        const int f = p % Wp, tg = p / Wp, g = tg % G, t = tg / G;
+                    // A thread computes two adjacent positions (f, f+1): every weight it reads from shared memory (a broadcast
+                    // load - the phase is bound by those) feeds two FMAs.  17 pairs per row: 16 real ones and the pad column.
+                    const int Wp = 33, NP2 = 17;
+                    for (int q = et; q < 8 * G * NP2; q += kIncEpiWarps * 32) {
+                        const int j = q % NP2, tg = q / NP2, g = tg % G, t = tg / G;
+                        const int f0 = 2 * j;
                         const int b = grp * G + g;
-                        uint4* o = nx + 1 + p;
-                        if (f == 32 || b >= a.B) {
-                            const uint4 z = make_uint4(0, 0, 0, 0);
+                        uint4* o = nx + 1 + tg * Wp + f0;
+                        const uint4 z = make_uint4(0, 0, 0, 0);
+                        if (j == 16) { o[0] = z; o[L.nx_pitch] = z; o[2 * L.nx_pitch] = z; continue; }      // pad column f = 32
+                        if (b >= a.B) {
                             o[0] = z; o[L.nx_pitch] = z; o[2 * L.nx_pitch] = z;
+                            o[1] = z; o[L.nx_pitch + 1] = z; o[2 * L.nx_pitch + 1] = z;
                             continue;
                         }
                         const float* base = a.mel + (int64_t)b * a.mel_stride;
                         // rows 0..9 of the input = two rows from before this step + the eight new ones
                         const int row0 = (a.fused ? s_cnt[g] - 2 : a.mel_count[b] - a.back - 10) + t;
-                        float x[9];
+                        float x[3][4];                               // mel rows t..t+2, columns f0-1..f0+2
 #pragma unroll
                         for (int dt = 0; dt < 3; ++dt) {
                             const float* rp = (a.fused && t + dt >= 2) ? s_mel + (g * 8 + t + dt - 2) * 32
                                                                        : base + (int64_t)((row0 + dt) & a.mel_mask) * 32;
 #pragma unroll
-                            for (int df = 0; df < 3; ++df) {
-                                const int ff = f + df - 1;
-                                x[dt * 3 + df] = (ff >= 0 && ff < 32) ? rp[ff] : 0.f;
+                            for (int i = 0; i < 4; ++i) {
+                                const int ff = f0 + i - 1;
+                                x[dt][i] = (ff >= 0 && ff < 32) ? rp[ff] : 0.f;
                             }
                         }
 #pragma unroll
                         for (int pl = 0; pl < 3; ++pl) {
-                            __half2 h[4];
+                            __half2 h0[4], h1[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                float v2[2];
+                                float v0[2], v1[2];
 #pragma unroll
                                 for (int e = 0; e < 2; ++e) {
                                     const int c = pl * 8 + u * 2 + e;
-                                    float s = 0.f;
+                                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                                    for (int k = 0; k < 9; ++k) s = fmaf(x[k], s_l0[k * 24 + c], s);
-                                    s = fmaxf(s, 0.f);
-                                    v2[e] = act(fmaf(s, s_l0[216 + c], s_l0[240 + c]));
+                                    for (int k = 0; k < 9; ++k) {
+                                        const float w = s_l0[k * 24 + c];
+                                        s0 = fmaf(x[k / 3][k % 3], w, s0);
+                                        s1 = fmaf(x[k / 3][k % 3 + 1], w, s1);
+                                    }
+                                    const float sc = s_l0[216 + c], bi = s_l0[240 + c];
+                                    v0[e] = act(fmaf(fmaxf(s0, 0.f), sc, bi));
+                                    v1[e] = act(fmaf(fmaxf(s1, 0.f), sc, bi));
                                 }
-                                h[u] = __floats2half2_rn(v2[0], v2[1]);
+                                h0[u] = __floats2half2_rn(v0[0], v0[1]);
+                                h1[u] = __floats2half2_rn(v1[0], v1[1]);
                             }
-                            o[pl * L.nx_pitch] = *reinterpret_cast<uint4*>(h);
+                            o[pl * L.nx_pitch] = *reinterpret_cast<uint4*>(h0);
+                            o[pl * L.nx_pitch + 1] = *reinterpret_cast<uint4*>(h1);
                         }
                     }
                 } else {
@@ -367,6 +403,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     const int t_off_units = L.pool_t ? 0 : L.nx_t_off * G * L.Wp;
                     const int n_tiles = (L.M + 127) / 128;
                     const int tail_start = (L.T_out - 2) * G * L.Wp;
+                    const uint32_t wp_magic = 0xFFFFFFFFu / (uint32_t)L.Wp + 1u, g_magic = G > 1 ? 0xFFFFFFFFu / (uint32_t)G + 1u : 0u;
                     const bool edbg = a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0;
                     long long e0 = 0;
                     if (edbg) e0 = clock64();
@@ -388,8 +425,10 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         if (lane == 0) mbar_arrive_cnt(tempty(stage), (uint32_t)sets);   // 4*PT warps drain a tile: sets arrivals each = 16
                         const int m = tile * 128 + row;
                         if (m >= L.M) continue;
-                        const int f = m % L.Wp;
-                        const int g = (m / L.Wp) % G;
+                        // m = (t*G + g)*Wp + f; exact division by multiply-high (m < 2^16, divisors < 2^6)
+                        const int tg = (int)__umulhi((uint32_t)m, wp_magic);
+                        const int f = m - tg * L.Wp;
+                        const int g = G > 1 ? tg - (int)__umulhi((uint32_t)tg, g_magic) * G : 0;
                         const bool live = grp * G + g < a.B;
                         if (L.final) {
                             if (f != 0 || !live) continue;
@@ -414,22 +453,25 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             continue;
                         }
                         const bool pad = f == L.W;
+                        uint4* d0 = dst + (1 + t_off_units + m);
+                        const bool keep_tail = !L.pool_t && L.nx_tail_off >= 0 && m >= tail_start && live;
+                        uint4* t0 = tout + (L.nx_tail_off + (m - tail_start));
+                        const int n_pl = min(pl1, L.cg_out) - pl0;
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
+                            if (k >= n_pl) break;
                             const int pl = pl0 + k;
-                            if (pl >= pl1 || pl >= L.cg_out) continue;
-                            const int c = pl * 8;
+                            const float4* sc4 = reinterpret_cast<const float4*>(sb + pl * 8);
+                            const float4* bi4 = reinterpret_cast<const float4*>(sb + L.np + pl * 8);
+                            const float4 s0 = sc4[0], s1 = sc4[1], b0 = bi4[0], b1 = bi4[1];
                             __half2 h[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float y0 = act(fmaf(__uint_as_float(v[k][2 * u]), sb[c + 2 * u], sb[L.np + c + 2 * u]));
-                                const float y1 = act(fmaf(__uint_as_float(v[k][2 * u + 1]), sb[c + 2 * u + 1], sb[L.np + c + 2 * u + 1]));
-                                h[u] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(y0, y1);
-                            }
-                            const uint4 pk = *reinterpret_cast<uint4*>(h);
-                            dst[pl * dpitch + 1 + t_off_units + m] = pk;
-                            if (!L.pool_t && L.nx_tail_off >= 0 && m >= tail_start && live)
-                                tout[L.nx_tail_off + pl * (2 * G * L.Wp) + (m - tail_start)] = pk;
+                            h[0] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][0]), s0.x, b0.x)), act(fmaf(__uint_as_float(v[k][1]), s0.y, b0.y)));
+                            h[1] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][2]), s0.z, b0.z)), act(fmaf(__uint_as_float(v[k][3]), s0.w, b0.w)));
+                            h[2] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][4]), s1.x, b1.x)), act(fmaf(__uint_as_float(v[k][5]), s1.y, b1.y)));
+                            h[3] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][6]), s1.z, b1.z)), act(fmaf(__uint_as_float(v[k][7]), s1.w, b1.w)));
+                            const uint4 pk = pad ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<uint4*>(h);
+                            d0[pl * dpitch] = pk;
+                            if (keep_tail) t0[pl * (2 * G * L.Wp)] = pk;
                         }
                     }
                     acc_par = par0 ^ (uint32_t)(((acc0 + n_tiles) >> 2) & 1);
@@ -452,9 +494,13 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         const uint4* src = act0 + L.tmp_base;
                         const int T2 = L.T_out / L.pool_t;
                         const int per = T2 * G * L.nx_Wp;
+                        // exact division by multiply-high (indices < 2^16): three magics per layer instead of four divisions per unit
+                        const uint32_t per_magic = 0xFFFFFFFFu / (uint32_t)per + 1u, nwp_magic = 0xFFFFFFFFu / (uint32_t)L.nx_Wp + 1u;
+                        const uint32_t gp_magic = G > 1 ? 0xFFFFFFFFu / (uint32_t)G + 1u : 0u;
                         for (int i = et; i < L.cg_out * per; i += kIncEpiWarps * 32) {
-                            const int pl = i / per, p = i - pl * per;
-                            const int f = p % L.nx_Wp, tg = p / L.nx_Wp, g = tg % G, t = tg / G;
+                            const int pl = per > 1 ? (int)__umulhi((uint32_t)i, per_magic) : i, p = i - pl * per;
+                            const int tg = (int)__umulhi((uint32_t)p, nwp_magic), f = p - tg * L.nx_Wp;
+                            const int t = G > 1 ? (int)__umulhi((uint32_t)tg, gp_magic) : tg, g = tg - t * G;
                             uint4 res = make_uint4(0, 0, 0, 0);
                             if (f < L.nx_W) {
                                 __half2 mx[4];
@@ -497,14 +543,26 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 float* red = feats + G * NI * 96;                                // [4][G][128]
                 float* hA = red + 4 * G * 128;                                   // [G][256]
                 float* hB = hA + G * 256;
-                for (int i = et; i < G * NI * 24; i += kIncEpiWarps * 32) {
-                    const int g = i / (NI * 24), r = (i / 24) % NI, c4 = (i % 24) * 4, b = grp * G + g;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < a.B) {
-                        const int row = s_cnt[8 + g] + 1 - NI + r;
-                        if (row >= 0) v = __ldcg(reinterpret_cast<const float4*>(a.feat_ring + (int64_t)b * a.feat_stride + (int64_t)(row & a.feat_mask) * 96 + c4));
+                // gather the last NI embedding rows of every stream (four independent L2 loads in flight per thread)
+                for (int i0 = et; i0 < G * NI * 24; i0 += 4 * kIncEpiWarps * 32) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kIncEpiWarps * 32;
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i < G * NI * 24) {
+                            const int g = i / (NI * 24), r = (i / 24) % NI, c4 = (i % 24) * 4, b = grp * G + g;
+                            if (b < a.B) {
+                                const int row = s_cnt[8 + g] + 1 - NI + r;
+                                if (row >= 0) v[u] = __ldcg(reinterpret_cast<const float4*>(a.feat_ring + (int64_t)b * a.feat_stride + (int64_t)(row & a.feat_mask) * 96 + c4));
+                            }
+                        }
                     }
-                    *reinterpret_cast<float4*>(feats + (g * NI + r) * 96 + c4) = v;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kIncEpiWarps * 32;
+                        if (i < G * NI * 24) *reinterpret_cast<float4*>(feats + i * 4) = v[u];
+                    }
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 for (int hh = 0; hh < a.n_heads; ++hh) {
@@ -524,12 +582,21 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             if (d < D1) {
                                 const float* wr = reinterpret_cast<const float*>(smem + a.hring_off + slot * a.hslot_bytes) + slice * 24 * D1 + d;
                                 const float* xr = feats + (off + c) * 96 + slice * 24;
-#pragma unroll 8
-                                for (int k8 = 0; k8 < 24; ++k8) {
-                                    const float w = wr[k8 * D1];
+                                // the features are read four k at a time (one broadcast 16-byte load per stream instead of
+                                // four scalar ones: the loop was shared-memory-issue bound); the k order per accumulator is unchanged
+#pragma unroll 2
+                                for (int k4 = 0; k4 < 24; k4 += 4) {
+                                    const float w0 = wr[(k4 + 0) * D1], w1 = wr[(k4 + 1) * D1];
+                                    const float w2 = wr[(k4 + 2) * D1], w3 = wr[(k4 + 3) * D1];
 #pragma unroll
                                     for (int g = 0; g < kIncMaxG; ++g)
-                                        if (g < G) acc[g] = fmaf(xr[g * NI * 96 + k8], w, acc[g]);
+                                        if (g < G) {
+                                            const float4 x = *reinterpret_cast<const float4*>(xr + g * NI * 96 + k4);
+                                            acc[g] = fmaf(x.x, w0, acc[g]);
+                                            acc[g] = fmaf(x.y, w1, acc[g]);
+                                            acc[g] = fmaf(x.z, w2, acc[g]);
+                                            acc[g] = fmaf(x.w, w3, acc[g]);
+                                        }
                                 }
                             }
                             __syncwarp();
@@ -555,15 +622,40 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     for (int l = 0; l < H.n_layers; ++l) {
                         const int D = H.dims[l + 1], K = H.dims[l];
                         if (l > 0) {
-                            const float* W = H.blob + H.w_off[l];
-                            for (int i = et; i < G * D; i += kIncEpiWarps * 32) {
-                                const int g = i / D, d = i - g * D;
-                                float acc = 0.f;
-                                // the weight loads are independent of acc: unrolled 16 deep they overlap (each is an L2 round trip)
-#pragma unroll 16
-                                for (int k = 0; k < K; ++k) acc = fmaf(cur[g * 256 + k], __ldg(W + (int64_t)k * D + d), acc);
-                                nxt[g * 256 + d] = acc + __ldg(H.blob + H.b_off[l] + d);
+                            // later layers: the producer streams W_l (K x D) through the ring in chunks of head_rows() rows.
+                            // A thread owns outputs i = et + 512 j; each accumulates over k in ascending order (as heads_kernel does).
+                            const int rows = head_rows(a.hslot_bytes, K, D);
+                            const int nown = min(4, max(0, (G * D - et + kIncEpiWarps * 32 - 1) / (kIncEpiWarps * 32)));
+                            float accl[4]; int cxo[4], dd[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int i = j < nown ? et + j * kIncEpiWarps * 32 : 0;
+                                const int g = i / D;
+                                dd[j] = i - g * D; cxo[j] = g * 256; accl[j] = 0.f;
                             }
+                            for (int k0 = 0; k0 < K; k0 += rows) {
+                                const int r = min(rows, K - k0);
+                                const int slot = hchunk_e % a.hns;
+                                mbar_wait(hfull(slot), (hf_par >> slot) & 1u);
+                                hf_par ^= 1u << slot;
+                                ++hchunk_e;
+                                const float* wr = reinterpret_cast<const float*>(smem + a.hring_off + slot * a.hslot_bytes);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    if (j >= nown) break;
+                                    const float* cx = cur + cxo[j] + k0;
+                                    const float* wc = wr + dd[j];
+                                    float sacc = accl[j];
+#pragma unroll 8
+                                    for (int k = 0; k < r; ++k) sacc = fmaf(cx[k], wc[k * D], sacc);
+                                    accl[j] = sacc;
+                                }
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(hempty(slot));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (j < nown) nxt[cxo[j] + dd[j]] = accl[j] + __ldg(H.blob + H.b_off[l] + dd[j]);
                             named_bar_sync(2, kIncEpiWarps * 32);
                             float* t = cur; cur = nxt; nxt = t;
                         }

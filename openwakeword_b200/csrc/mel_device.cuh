@@ -86,6 +86,20 @@ __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, c
 // a lone warp (the fused step kernel runs only 16 of them per SM) has NF independent dependency chains in flight.
 // Frame i: clip pointers tail[i]/body[i], frame index f[i], work buffers bufs + i*kMelFrameScratch bytes laid out as
 // a[256] float2 | b[256] float2 | pw[320] float.  db[i] receives this lane's dB value.
+// Index swizzle of the FFT work buffers in mel_frames_db: the radix-4 Stockham stores of the first two passes are strided by
+// 4 and 16 elements (8- and 4-way bank conflicts on 8-byte elements); XOR-ing bits 4..5 of the index into bits 0..1 and 2..3
+// makes every access pattern of the four passes conflict-free per half-warp.  Pure layout: the arithmetic is unchanged.
+#ifndef OWW_FFT_SWZ
+#define OWW_FFT_SWZ 1
+#endif
+__device__ __forceinline__ int fswz(int e) {
+#if OWW_FFT_SWZ
+    return e ^ (((e >> 4) & 3) * 5);
+#else
+    return e;
+#endif
+}
+
 constexpr int kMelFrameScratch = 2048 + 2048 + 1280;
 template <int NF>
 __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int prefix, const int16_t* const* body, const int* f,
@@ -108,7 +122,7 @@ __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int pr
             if (s0 + 1 < prefix) { x0 = (float)tail[i][s0]; x1 = (float)tail[i][s0 + 1]; }
             else if (s0 >= prefix) { x0 = (float)__ldg(body[i] + (s0 - prefix)); x1 = (float)__ldg(body[i] + (s0 + 1 - prefix)); }
             else { x0 = (float)tail[i][s0]; x1 = (float)__ldg(body[i]); }
-            a[i][n] = make_float2(__fmul_rn(x0, s_win[2 * n]), __fmul_rn(x1, s_win[2 * n + 1]));
+            a[i][fswz(n)] = make_float2(__fmul_rn(x0, s_win[2 * n]), __fmul_rn(x1, s_win[2 * n + 1]));
         }
     }
     __syncwarp();
@@ -123,19 +137,19 @@ __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int pr
             const int dst = (j / Ns) * Ns * 4 + k;
 #pragma unroll
             for (int i = 0; i < NF; ++i) {
-                float2 v0 = a[i][j];
-                float2 v1 = cmul(a[i][j + 64], t1);
-                float2 v2 = cmul(a[i][j + 128], t2);
-                float2 v3 = cmul(a[i][j + 192], t3);
+                float2 v0 = a[i][fswz(j)];
+                float2 v1 = cmul(a[i][fswz(j + 64)], t1);
+                float2 v2 = cmul(a[i][fswz(j + 128)], t2);
+                float2 v3 = cmul(a[i][fswz(j + 192)], t3);
                 float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
                 float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
                 float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
                 float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
                 float2 a3 = make_float2(d.y, -d.x);
-                b[i][dst] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                b[i][dst + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                b[i][dst + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                b[i][dst + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                b[i][fswz(dst)] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                b[i][fswz(dst + Ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                b[i][fswz(dst + 2 * Ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                b[i][fswz(dst + 3 * Ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
             }
         }
         __syncwarp();
@@ -147,11 +161,11 @@ __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int pr
         for (int i = 0; i < NF; ++i) {
             float p;
             if (k == 256) {
-                const float x = a[i][0].x - a[i][0].y;
+                const float x = a[i][fswz(0)].x - a[i][fswz(0)].y;
                 p = __fmul_rn(x, x);
             } else {
-                const float2 zk = a[i][k & 255];
-                const float2 zc = a[i][(256 - k) & 255];
+                const float2 zk = a[i][fswz(k & 255)];
+                const float2 zc = a[i][fswz((256 - k) & 255)];
                 const float2 xe = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
                 const float2 dd = make_float2(zk.x - zc.x, zk.y + zc.y);
                 const float2 xo = make_float2(0.5f * dd.y, -0.5f * dd.x);
