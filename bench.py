@@ -39,7 +39,7 @@ STREAMS_PER_GPU = 1024
 CHUNK = 1280
 # dram__bytes_read.sum + dram__bytes_write.sum of the CNN stage for one 1024-stream step, from the ncu --set full
 # captures summarised in profiles/README.md (bytes per step; None = not captured for that mode)
-TRAFFIC = {2: 1.177e9, 3: 3.37e7}
+TRAFFIC = {2: 1.177e9, 3: 3.41e7}
 METRIC = "80ms audio-frames/sec (concurrent streams)"
 UNIT = "frames/s"
 
@@ -319,7 +319,7 @@ def run_own_arm(args):
     kernel_name = {0: "embedding CNN stage: 20 conv_kernel + 5 pool_kernel launches (cnn_fp32.cu)",
                    2: "embedding CNN stage: tc_conv0 + 19 tc_conv_kernel + 5 tc_pool launches (cnn_tc.cu)",
                    3: "tc_inc_kernel (cnn_tc_inc.cu): the whole step in ONE launch - log-mel frontend, 20-layer tcgen05 CNN, ring "
-                      "append and heads; its duration therefore includes the frontend (~21 us) and heads (~33 us) phases"
+                      "append and heads; its duration therefore includes the frontend (~19 us) and heads (~27 us) phases"
                       if fused else "embedding CNN stage: tc_inc_kernel (fused 20-layer launch) + ring append"}[args.cnn_mode]
     dtype = "f32" if args.cnn_mode == 0 else "f16 operands / f32 accumulate (mel, BN, heads in f32)"
     value = n_total * K / (ms_dev * 1e-3)
