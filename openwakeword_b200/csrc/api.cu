@@ -122,16 +122,17 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
         return oww_fail(ctx, OWW_EINVAL, "n_chunks=%d outside [1,%d]", n_chunks, ctx->cfg.max_chunks);
     if (!ctx->mel_loaded || !ctx->emb_loaded) return oww_fail(ctx, OWW_EINVAL, "weights not loaded");
     int rc;
-    cudaEvent_t* ev = ctx->timing ? &ctx->ev[4 * (ctx->ev_steps % ctx->ev_slots)] : nullptr;
-    if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[0], s));
+    const long slot = ctx->timing ? ctx->ev_steps % ctx->ev_slots : 0;
+    cudaEvent_t* ev = ctx->timing ? &ctx->ev[4 * slot] : nullptr;
     if (n_chunks == 1 && oww_fused_step_supported(ctx)) {
-        // steady state: the whole step (frontend, CNN, ring append, heads) is ONE launch; the stage events then
-        // bracket that launch as the "cnn" stage and report zero-length mel / heads stages
+        // steady state: the whole step (frontend, CNN, ring append, heads) is ONE launch; two events bracket that
+        // launch as the "cnn" stage (an event record costs ~2.5 us of stream time, so no empty mel / heads pairs)
         if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
         if ((rc = oww_fused_step(ctx, d_pcm, pcm_stride, d_scores, out_stride, s))) return rc;
-        if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[2], s)); OWW_CUDA(ctx, cudaEventRecord(ev[3], s)); ctx->ev_steps++; }
+        if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[2], s)); ctx->ev_fused[slot] = 1; ctx->ev_steps++; }
         return OWW_OK;
     }
+    if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[0], s)); ctx->ev_fused[slot] = 0; }
     MelLaunch m{d_pcm, pcm_stride, n_chunks * OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
                 (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, B, 1, n_chunks};
     if ((rc = oww_mel_launch(ctx, m, s))) return rc;
@@ -636,7 +637,7 @@ int oww_enable_stage_timing(oww_ctx* ctx, int n_slots) {
         OWW_CUDA(ctx, cudaEventCreate(&e));
         ctx->ev.push_back(e);
     }
-    if (n_slots > 0) ctx->ev_slots = n_slots;
+    if (n_slots > 0) { ctx->ev_slots = n_slots; ctx->ev_fused.assign(n_slots, 0); }
     return OWW_OK;
 }
 
@@ -647,8 +648,9 @@ int oww_stage_ms(oww_ctx* ctx, float out_ms[3]) {
     double acc[3] = {0, 0, 0};
     for (long k = 0; k < n; ++k) {
         cudaEvent_t* ev = &ctx->ev[4 * k];
-        OWW_CUDA(ctx, cudaEventSynchronize(ev[3]));
-        for (int i = 0; i < 3; ++i) {
+        const bool fused = ctx->ev_fused[k] != 0;
+        OWW_CUDA(ctx, cudaEventSynchronize(ev[fused ? 2 : 3]));
+        for (int i = fused ? 1 : 0; i < (fused ? 2 : 3); ++i) {
             float ms = 0.f;
             OWW_CUDA(ctx, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
             acc[i] += ms;

@@ -136,6 +136,7 @@ struct oww_ctx {
     // stage timing
     bool timing = false;
     std::vector<cudaEvent_t> ev;     // 4 events per slot; step k uses slot k % ev_slots
+    std::vector<uint8_t> ev_fused;          // per timing slot: the step was one fused launch (only ev[1], ev[2] recorded)
     int ev_slots = 0;
     long ev_steps = 0;               // timed steps recorded since timing was enabled
 

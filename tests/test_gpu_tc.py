@@ -118,3 +118,54 @@ def test_tc_incremental_vs_window_modes(torch_cuda, built_library):
     assert np.abs(out[3] - out[13]).max() < 1e-6 and np.abs(feats[3] - feats[13]).max() < 1e-6
     assert d32.max() < 2e-4
     assert np.abs(out[3] - out[0]).max() < 1e-3
+
+
+@pytest.mark.gpu
+def test_fused_step_heads_with_awkward_shapes(torch_cuda, built_library):
+    """The in-kernel heads phase (first layer through the smem ring in 96-row chunks, later layers in
+    head_rows() chunks, tensors re-aligned to 16 bytes on upload) against the stand-alone heads kernel and the
+    oracle, for widths that are not multiples of 4, a single-Linear head, a wide 256-unit later layer, softmax
+    outputs and different n_in per head."""
+    from openwakeword_b200.engine import StreamEngine
+    from openwakeword_b200 import weights as W
+    from oracle import heads as oh
+    rng = np.random.default_rng(5)
+    hs = [W.synthetic_head(n_in=16, hidden=30, n_blocks=1, n_out=1, seed=3),
+          W.synthetic_head(n_in=3, hidden=7, n_blocks=2, n_out=3, layernorm=False, final="softmax", seed=4),
+          W.synthetic_head(n_in=16, hidden=128, n_blocks=0, n_out=1, seed=5),
+          W.synthetic_head(n_in=28, hidden=96, n_blocks=1, n_out=5, final="relu_softmax", seed=6)]
+    single = W.synthetic_head(n_in=16, hidden=128, n_blocks=0, n_out=1, seed=7)
+    single["layers"] = [dict(single["layers"][0])]                    # one Linear(1536, 1) + sigmoid
+    single["layers"][0]["W"] = (rng.standard_normal((1536, 1)) / 40).astype(np.float32)
+    single["layers"][0]["b"] = np.zeros(1, np.float32)
+    single["layers"][0]["ln"] = None
+    hs.append(single)
+    wide = W.synthetic_head(n_in=16, hidden=128, n_blocks=1, n_out=2, final="softmax", seed=8)
+    lw = wide["layers"]
+    lw[1]["W"] = (rng.standard_normal((128, 256)) / np.sqrt(128)).astype(np.float32)
+    lw[1]["b"] = rng.normal(0, 0.1, 256).astype(np.float32)
+    lw[1]["ln"] = (rng.uniform(0.7, 1.3, 256).astype(np.float32), rng.normal(0.1, 0.2, 256).astype(np.float32))
+    lw[2]["W"] = (rng.standard_normal((256, 2)) * 3 / 16).astype(np.float32)
+    hs.append(wide)
+    B = 19
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    pcm = np.clip(rng.normal(0, 2500, (B, 7 * 1280)), -32768, 32767).astype(np.int16)
+    out, feats = {}, {}
+    for fuse in (True, False):
+        eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=3, fuse_step=fuse)
+        out[fuse] = np.stack([eng.step_host(np.ascontiguousarray(pcm[:, k * 1280:(k + 1) * 1280]), 1).copy() for k in range(6)], 1)
+        n0 = eng.ctx.launch_count
+        last = eng.step_host(np.ascontiguousarray(pcm[:, 6 * 1280:]), 1).copy()
+        assert (eng.ctx.launch_count - n0 == 1) == fuse            # the steady-state step really is one launch when fused
+        out[fuse] = np.concatenate([out[fuse], last[:, None]], 1)
+        feats[fuse] = np.stack([eng.ctx.get_features(b, 28) for b in range(B)])
+    assert np.array_equal(feats[True], feats[False])
+    print("awkward heads, fused vs separate launches: max |score diff| =", np.abs(out[True] - out[False]).max())
+    assert np.abs(out[True] - out[False]).max() < 1e-6
+    # the last step's scores from the device features through the NumPy heads
+    col = 0
+    for h in hs:
+        n_in, n_out = h["n_in"], h["layers"][-1]["W"].shape[1]
+        ref = oh.forward(h, feats[True][:, -n_in:])
+        assert np.abs(out[True][:, -1, col:col + n_out] - ref).max() < 2e-5
+        col += n_out
