@@ -8,8 +8,8 @@ Importing the package needs neither a GPU nor the built library; constructing a 
 """
 from .registry import MODELS, FEATURE_MODELS, model_class_mappings, get_pretrained_model_paths  # noqa: F401
 from .model import Model  # noqa: F401
-from .utils import AudioFeatures, bulk_predict  # noqa: F401
+from .utils import AudioFeatures, bulk_predict, compute_features_from_generator  # noqa: F401
 
-__all__ = ["Model", "AudioFeatures", "bulk_predict", "MODELS", "FEATURE_MODELS",
+__all__ = ["Model", "AudioFeatures", "bulk_predict", "compute_features_from_generator", "MODELS", "FEATURE_MODELS",
            "model_class_mappings", "get_pretrained_model_paths"]
 __version__ = "0.1.0"

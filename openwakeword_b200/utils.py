@@ -278,10 +278,61 @@ def _read_wav(path):
         return np.frombuffer(f.readframes(f.getnframes()), dtype=np.int16)
 
 
+def _read_wavs(paths, n_threads=1):
+    """RIFF parsing is I/O bound: read the files on ``n_threads`` host threads, keep the order."""
+    if n_threads <= 1 or len(paths) < 2:
+        return [_read_wav(p) for p in paths]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=int(n_threads)) as pool:
+        return list(pool.map(_read_wav, paths))
+
+
+def compute_features_from_generator(generator, n_total, clip_duration, output_file, device="gpu", ncpu=1,
+                                    audio_features=None):
+    """Reference signature (utils.py:542-601): pull int16 batches ``[batch, clip_duration]`` from ``generator``,
+    embed them (``AudioFeatures.embed_clips``, one device call per batch) and write float32
+    ``[n, (T-76)//8+1, 96]`` to the ``.npy`` file ``output_file`` through a memmap, so the result may exceed host
+    memory.  ``n_total`` may over-estimate the number of clips: the file is cut to the rows actually written (the
+    reference trims trailing all-zero rows with ``data.trim_mmap`` - same result unless a clip embeds to exactly
+    zero).  ``device``/``ncpu`` are accepted for signature compatibility; the work runs on the B200.
+    ``audio_features`` lets a caller reuse an existing ``AudioFeatures`` (weights already on the device)."""
+    from numpy.lib.format import open_memmap
+    F = audio_features if audio_features is not None else AudioFeatures(device=device)
+    n_windows, dim = F.get_embedding_shape(clip_duration / 16000)
+    if n_windows < 1:
+        raise ValueError("clip_duration is too short for one 76-frame embedding window")
+    n_total = int(n_total)
+    fp = open_memmap(output_file, mode="w+", dtype=np.float32, shape=(n_total, n_windows, dim))
+    rows = 0
+    for k, audio in enumerate(generator):
+        audio = np.asarray(audio)
+        if k == 0 and audio.shape[0] > n_total:
+            del fp
+            os.remove(output_file)
+            raise ValueError(f"The value of 'n_total' ({n_total}) is less than the batch size ({audio.shape[0]})."
+                             " Please increase 'n_total' to be >= batch size.")
+        if rows >= n_total:
+            break
+        feats = F.embed_clips(audio, batch_size=audio.shape[0], ncpu=ncpu)[: n_total - rows]
+        fp[rows:rows + feats.shape[0]] = feats
+        rows += feats.shape[0]
+        fp.flush()
+    del fp
+    if rows < n_total:                                         # cut the file to what was produced
+        tmp = output_file + ".trim.npy"
+        src = np.load(output_file, mmap_mode="r")
+        dst = open_memmap(tmp, mode="w+", dtype=np.float32, shape=(rows, n_windows, dim))
+        for i in range(0, rows, 4096):
+            dst[i:i + 4096] = src[i:min(rows, i + 4096)]
+        dst.flush()
+        del src, dst
+        os.replace(tmp, output_file)
+
+
 def bulk_predict(file_paths, wakeword_models, prediction_function="predict_clip", ncpu=1,
                  inference_framework="b200", **kwargs):
-    """Reference signature (utils.py:467-539).  ``ncpu`` is accepted and ignored: clips are batched on
-    the GPU instead of forked across processes.  Each clip starts from a fresh state (the
+    """Reference signature (utils.py:467-539).  Clips are batched on the GPU instead of forked across ``ncpu``
+    processes; ``ncpu`` is the number of host threads that read the WAV files.  Each clip starts from a fresh state (the
     reference bleeds state across the clips of one worker).  Returns {path: list of dicts}."""
     from .model import Model
     if prediction_function != "predict_clip":
@@ -291,7 +342,7 @@ def bulk_predict(file_paths, wakeword_models, prediction_function="predict_clip"
     init_kw = {k: v for k, v in kwargs.items() if k in init_names}
     clip_kw = {k: v for k, v in kwargs.items() if k not in init_names}
     mdl = Model(wakeword_models=wakeword_models, inference_framework=inference_framework, **init_kw)
-    clips = [_read_wav(p) for p in file_paths]
+    clips = _read_wavs(file_paths, ncpu)
     out = {}
     by_len = {}
     for p, c in zip(file_paths, clips):

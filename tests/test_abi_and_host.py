@@ -173,3 +173,66 @@ def test_model_loads_reference_style_onnx_files(fake_ctx, tmp_path):
     np.testing.assert_allclose(got, c["scores"], atol=1e-5)
     with pytest.raises(ValueError):
         owb.Model(wakeword_models=[str(tmp_path / "x.tflite")], embedding_model_path=ep)
+
+
+def _oracle_embed_clips(self, x, batch_size=128, ncpu=1):
+    """AudioFeatures.embed_clips restated on the oracle (the device call needs a GPU)."""
+    from oracle import embedding as oe, mel as om
+    x = np.asarray(x)
+    if x.dtype != np.int16:
+        raise ValueError("Input data must be 16-bit integers.")
+    w = emb_weights()
+    out = []
+    for clip in x:
+        m = om.melspectrogram(clip)
+        wins = np.stack([m[8 * i:8 * i + 76] for i in range((m.shape[0] - 76) // 8 + 1)])
+        out.append(oe.embed_windows(w, wins))
+    return np.stack(out).astype(np.float32)
+
+
+def test_compute_features_from_generator(fake_ctx, monkeypatch, tmp_path):
+    """utils.py:542-601: rows land in generator order, the file is cut to what was produced, an n_total below the
+    batch size raises, surplus batches are ignored."""
+    monkeypatch.setattr(owb.AudioFeatures, "embed_clips", _oracle_embed_clips)
+    rng = np.random.default_rng(2)
+    S = 16000
+    batches = [rng.integers(-1000, 1000, (3, S)).astype(np.int16) for _ in range(3)]
+    F = owb.AudioFeatures(embedding_model_path=emb_weights())
+    n_w = F.get_embedding_shape(1.0)[0]
+    ref = _oracle_embed_clips(None, np.concatenate(batches))
+
+    f1 = str(tmp_path / "over.npy")                       # n_total over-estimates: 9 of 20 rows produced
+    owb.compute_features_from_generator(iter(batches), 20, S, f1, audio_features=F)
+    a = np.load(f1)
+    assert a.shape == (9, n_w, 96) and a.dtype == np.float32
+    np.testing.assert_array_equal(a, ref)
+
+    f2 = str(tmp_path / "under.npy")                      # n_total cuts inside the third batch
+    owb.compute_features_from_generator(iter(batches), 7, S, f2, audio_features=F)
+    np.testing.assert_array_equal(np.load(f2), ref[:7])
+
+    f3 = str(tmp_path / "bad.npy")
+    with pytest.raises(ValueError):
+        owb.compute_features_from_generator(iter(batches), 2, S, f3, audio_features=F)
+    assert not os.path.exists(f3)
+
+
+def test_threaded_wav_ingest_keeps_order(tmp_path):
+    import wave
+    from openwakeword_b200.utils import _read_wavs
+    rng = np.random.default_rng(4)
+    paths, clips = [], []
+    for i in range(9):
+        c = rng.integers(-3000, 3000, 2000 + 37 * i).astype(np.int16)
+        p = str(tmp_path / f"c{i}.wav")
+        with wave.open(p, "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(c.tobytes())
+        paths.append(p); clips.append(c)
+    for n in (1, 4):
+        got = _read_wavs(paths, n)
+        assert all(np.array_equal(g, c) for g, c in zip(got, clips))
+    bad = str(tmp_path / "stereo.wav")
+    with wave.open(bad, "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000); f.writeframes(np.zeros(64, np.int16).tobytes())
+    with pytest.raises(ValueError):
+        _read_wavs(paths + [bad], 4)
