@@ -141,13 +141,39 @@ def _cpu_worker(conn, stream_id, seed):
         conn.send(time.perf_counter() - t0)
 
 
+def usable_cores():
+    """Host cores this process may actually run on: the scheduler affinity mask, capped by a cgroup CPU quota when the
+    container has one (os.cpu_count() reports the machine's logical CPUs even under a quota, and one busy worker per
+    *reported* CPU then measures time-slicing, not the cores)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]            # cgroup v2
+        if q != "max":
+            quota = int(q) / int(per)
+    except Exception:
+        try:                                                                  # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
 class CpuArm:
-    """P persistent worker processes (P = host cores); step(n) = every worker runs n frames."""
+    """P persistent worker processes (P = usable host cores); step(n) = every worker runs n frames."""
 
     def __init__(self, procs=None):
         import multiprocessing as mp
         ctx = mp.get_context("fork")
-        self.P = procs or os.cpu_count() or 1
+        self.P = procs or usable_cores()
         self.workers = []
         for i in range(self.P):
             a, b = ctx.Pipe()
@@ -189,7 +215,8 @@ def run_reference_arm(args):
     arm.close()
     frames = arm.P * frames_each * args.steps
     v = frames / t
-    sample = f"{arm.P} single-stream oracle models x {frames_each} frames per step x {args.steps} steps"
+    sample = (f"{arm.P} single-stream oracle models (one per usable core; os.cpu_count()={os.cpu_count()}) x "
+              f"{frames_each} frames per step x {args.steps} steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -335,7 +362,8 @@ def run_own_arm(args):
             fr += arm.P * 4
         arm.close()
         cpu = {"value": fr / tt, "unit": UNIT, "cores": arm.P, "kind": "port",
-               "sample": f"{arm.P} single-stream NumPy-oracle models (1 BLAS thread each) x {fr // arm.P} frames, {tt:.1f} s; "
+               "sample": f"{arm.P} single-stream NumPy-oracle models (1 BLAS thread each, one per usable core; "
+                         f"os.cpu_count()={os.cpu_count()}) x {fr // arm.P} frames, {tt:.1f} s; "
                          "onnxruntime CPU unavailable in this image"}
 
     line = {
