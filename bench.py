@@ -258,7 +258,7 @@ def run_own_arm(args):
     def factory(n_local, lo, hi):
         return StreamEngine(bench_heads(), n_local, embedding="synthetic:0", device_index=local, max_chunks=1,
                             cnn_mode=args.cnn_mode, fuse_step=not args.no_fuse)
-    sh = owd.ShardedStreams(n_total, factory, rank=rank, world=world)
+    sh = owd.ShardedStreams(n_total, factory, rank=rank, world=world, gather=args.gather)
     eng = sh.engine
     host_pcm = synth_pcm(B, POOL, 1234 + rank)                   # [B, POOL*1280]
     # host inputs live in page-locked memory (what a capture/ingest thread would hand over); numpy views of them go
@@ -274,6 +274,8 @@ def run_own_arm(args):
         torch.cuda.synchronize()
 
     def one_step(k):
+        if sh.peer is not None:                                  # --gather peer: scores land in rank 0's memory, no NCCL call
+            return sh.step(dev_steps[k % POOL], 1)
         eng.step(dev_steps[k % POOL], 1, scores)
         return owd.gather_scores(scores, n_total)
 
@@ -375,7 +377,7 @@ def run_own_arm(args):
                    "l2": f"inputs larger than L2: {POOL} distinct PCM batches ({POOL * B * CHUNK * 2 / 1e6:.0f} MB) cycled",
                    "weights": "synthetic seed 0 (reference shapes); released .onnx weights absent",
                    "parity": parity_label(),
-                   "parallelism": f"dp{world} (streams sharded, weights replicated, 1 score all-gather/step)"},
+                   "parallelism": f"dp{world} (streams sharded, weights replicated, 1 score " + ("all-gather" if sh.peer is None else "peer-memory gather") + "/step)"},
         "clocks": clocks,
         "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": B * CHUNK * 2 * world, "d2h_bytes_per_step": B * eng.n_cols * 4 * world},
@@ -403,6 +405,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--cnn-mode", type=int, default=3, help="0 fp32 window, 2 tcgen05 window, 3 tcgen05 fused incremental")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "peer"],
+                    help="N>1: per-step score gather by NCCL all-gather (default) or by peer-memory stores + counters (rank 0 only)")
     ap.add_argument("--no-fuse", action="store_true", help="mode 3: keep mel / CNN / append / heads as separate launches (stage breakdown)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -162,6 +162,27 @@ int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int
 int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_unused);
 int oww_debug_inc_clocks_read(oww_ctx* ctx, int64_t* h_out104);
 
+/* ---- multi-GPU gather over peer memory (one process per GPU) ---------------------------------
+ * The reference has no multi-device path; SURVEY.md section 8e defines the only exchange of the sharded hot path: the
+ * per-step scores float32[B/G][n_labels] of every rank gathered on one rank.  Instead of a collective call after the
+ * step, the step's last kernel can write its scores straight into the gathering rank's memory: pass oww_step a
+ * d_scores that points into a buffer opened with oww_peer_open (stores go over NVLink), then publish a step counter
+ * with oww_peer_signal; the gathering rank orders its consumer behind oww_peer_wait.  openwakeword_b200.distributed
+ * .PeerGather drives the protocol (double-buffered slots, acknowledgement counters).
+ *   oww_peer_alloc  - cudaMalloc'd, zero-filled buffer on this handle's device + its 64-byte CUDA IPC handle
+ *   oww_peer_open   - map another process's buffer (peer access is enabled lazily); oww_peer_close unmaps it
+ *   oww_peer_signal - stream-ordered: after all earlier work of `stream`, *d_flag = value (system-scope release;
+ *                     d_flag may be local or peer-mapped)
+ *   oww_peer_wait   - stream-ordered: later work of `stream` starts once d_flags[i*stride] >= value for all i < n
+ *                     (n <= 1024).  If that takes longer than timeout_s (<= 0: 10 s) the kernel traps and the next
+ *                     CUDA call on the handle fails - a dead peer cannot hang the GPU.                              */
+int oww_peer_alloc(oww_ctx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
+int oww_peer_free(oww_ctx* ctx, void* d_ptr);
+int oww_peer_open(oww_ctx* ctx, const unsigned char handle[64], void** d_ptr);
+int oww_peer_close(oww_ctx* ctx, void* d_ptr);
+int oww_peer_signal(oww_ctx* ctx, uint64_t* d_flag, uint64_t value, void* stream);
+int oww_peer_wait(oww_ctx* ctx, const uint64_t* d_flags, int n, int stride, uint64_t value, double timeout_s, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 uint64_t oww_launch_count(const oww_ctx* ctx);       /* kernels launched by this handle so far   */
 /* n_slots > 0: every following oww_step / oww_step_host brackets its three stages (mel, embedding

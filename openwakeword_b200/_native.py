@@ -59,6 +59,12 @@ _SIGNATURES = {
     "oww_debug_inc_plan": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
     "oww_debug_inc_clocks": (C.c_int, [_P, _P]),
     "oww_debug_inc_clocks_read": (C.c_int, [_P, _P]),
+    "oww_peer_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "oww_peer_free": (C.c_int, [_P, _P]),
+    "oww_peer_open": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "oww_peer_close": (C.c_int, [_P, _P]),
+    "oww_peer_signal": (C.c_int, [_P, _P, C.c_uint64, _P]),
+    "oww_peer_wait": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint64, C.c_double, _P]),
     "oww_launch_count": (C.c_uint64, [_P]),
     "oww_enable_stage_timing": (C.c_int, [_P, C.c_int]),
     "oww_stage_ms": (C.c_int, [_P, _P]),
@@ -234,6 +240,31 @@ class Context:
         out = np.zeros(104, np.int64)
         self._check(self.lib.oww_debug_inc_clocks_read(self.h, _ptr(out)))
         return out
+
+    # ---- peer memory (multi-GPU gather without a collective; include/owwb200.h) ----
+    def peer_alloc(self, n_bytes):
+        """-> (device address, 64-byte IPC handle) of a zero-filled buffer other ranks can open."""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        self._check(self.lib.oww_peer_alloc(self.h, int(n_bytes), C.byref(p), h))
+        return int(p.value), bytes(h.raw)
+
+    def peer_free(self, addr):
+        self._check(self.lib.oww_peer_free(self.h, int(addr)))
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        self._check(self.lib.oww_peer_open(self.h, C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, addr):
+        self._check(self.lib.oww_peer_close(self.h, int(addr)))
+
+    def peer_signal(self, flag_addr, value, stream=None):
+        self._check(self.lib.oww_peer_signal(self.h, int(flag_addr), int(value), stream))
+
+    def peer_wait(self, flags_addr, n, stride, value, timeout_s=10.0, stream=None):
+        self._check(self.lib.oww_peer_wait(self.h, int(flags_addr), int(n), int(stride), int(value), float(timeout_s), stream))
 
     # ---- introspection ----
     def enable_stage_timing(self, n_slots=1):

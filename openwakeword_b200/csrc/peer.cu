@@ -1,0 +1,105 @@
+// Multi-GPU result gather without a collective call ("optionally fused"): the last kernel of a step
+// (heads phase of tc_inc_kernel, or heads_kernel) stores its scores straight into a buffer that lives on the gathering
+// rank's GPU - d_scores of oww_step is then a peer-mapped address and the stores travel over NVLink - and a one-thread
+// kernel publishes a step counter behind them.  This file holds the plumbing for that: allocations that can be shared
+// between the one-process-per-GPU ranks (CUDA IPC), and the signal / wait kernels.  No data-path NCCL call remains.
+#include "oww_internal.h"
+#include <cstring>
+
+namespace {
+
+__global__ void peer_signal_kernel(unsigned long long* flag, unsigned long long value) {
+    // stream order put this kernel after the step's last kernel: its stores are performed; make them visible system-wide
+    // before the counter (release at system scope), so a peer that acquires the counter sees the scores
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+__global__ void peer_wait_kernel(const unsigned long long* flags, int n, int stride, unsigned long long value,
+                                 long long timeout_cycles) {
+    // one lane per flag; every lane spins until its counter reaches `value`
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long* f = flags + (size_t)i * stride;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= value) break;
+        if (clock64() - t0 > timeout_cycles) __trap();      // a dead peer must surface as a launch error, not a hang
+        __nanosleep(200);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int oww_peer_alloc(oww_ctx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]) {
+    if (!ctx || !d_ptr || !handle_out || bytes == 0) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    OWW_CUDA(ctx, cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return oww_fail(ctx, OWW_ECUDA, "peer allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+    }
+    std::memcpy(handle_out, &h, 64);
+    *d_ptr = p;
+    return OWW_OK;
+}
+
+int oww_peer_free(oww_ctx* ctx, void* d_ptr) {
+    if (!ctx) return OWW_EINVAL;
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_ptr) OWW_CUDA(ctx, cudaFree(d_ptr));
+    return OWW_OK;
+}
+
+int oww_peer_open(oww_ctx* ctx, const unsigned char handle[64], void** d_ptr) {
+    if (!ctx || !handle || !d_ptr) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    OWW_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_ptr = p;
+    return OWW_OK;
+}
+
+int oww_peer_close(oww_ctx* ctx, void* d_ptr) {
+    if (!ctx) return OWW_EINVAL;
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (d_ptr) OWW_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return OWW_OK;
+}
+
+int oww_peer_signal(oww_ctx* ctx, uint64_t* d_flag, uint64_t value, void* stream) {
+    if (!ctx || !d_flag) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(d_flag), value);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+int oww_peer_wait(oww_ctx* ctx, const uint64_t* d_flags, int n, int stride, uint64_t value, double timeout_s, void* stream) {
+    if (!ctx || !d_flags) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    if (n < 1 || n > 1024 || stride < 1) return oww_fail(ctx, OWW_EINVAL, "n=%d stride=%d", n, stride);
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+    if (khz <= 0) khz = 1900000;
+    if (!(timeout_s > 0)) timeout_s = 10.0;
+    const long long cycles = (long long)(timeout_s * 1e3 * khz);
+    peer_wait_kernel<<<1, ((n + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(d_flags),
+                                                                            n, stride, value, cycles);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+}  // extern "C"

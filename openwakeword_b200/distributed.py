@@ -5,6 +5,9 @@ the path shards with NO data-path collective: rank r owns the contiguous block
 ``shard_range(n, r, world)`` of streams (or clips), weights are replicated, and the only exchange
 is one gather of ``float32[n_local, n_labels]`` per step (``gather_scores``: NCCL all-gather over
 NVLink/NVSwitch on GPU ranks, gloo in the CPU tests).  One process per GPU (torchrun).
+
+``PeerGather`` removes even that call from the step: every rank's last kernel stores its scores
+straight into the gathering rank's memory (peer-mapped over NVLink) and a counter follows them.
 """
 import os
 
@@ -58,19 +61,131 @@ def gather_scores(local_scores, n_total, group=None):
     return torch.cat([out[r * n_max:r * n_max + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
+class PeerGather:
+    """Gather of the per-step scores on rank ``root`` through peer memory - no collective call.
+
+    The root owns ``slots`` score buffers ``float32[n_total, n_cols]`` and one arrival counter per rank;
+    every rank owns one acknowledgement counter.  Step k (1, 2, ...) uses buffer ``k % slots``:
+
+      every rank   begin(k)    wait until the root has released step k - slots (this buffer's previous use)
+                   dest(k)     device address for ``oww_step``'s scores: the rank's rows of the root's buffer
+                   publish(k)  arrival counter of this rank on the root <- k (after the step's kernels)
+      root only    collect(k)  wait until every rank's counter is >= k -> address of the full [n_total, n_cols]
+                   release(k)  after the consumer's work is enqueued: every rank's acknowledgement counter <- k
+
+    All calls are stream-ordered on ``stream`` (nothing blocks the host).  ``ctx`` supplies the peer_* calls of
+    ``_native.Context``; ``exchange(obj)`` is an all-gather of small Python objects (``all_gather_object``)."""
+
+    LINE = 16                                   # counters sit on their own 128-byte lines (16 x uint64)
+
+    def __init__(self, ctx, n_total, n_cols, rank, world, exchange, root=0, slots=2, timeout_s=10.0):
+        if slots < 2:
+            raise ValueError("PeerGather needs at least two buffers (a step's scores land while the previous are read)")
+        self.ctx, self.rank, self.world, self.root = ctx, rank, world, root
+        self.n_total, self.n_cols, self.slots, self.timeout_s = n_total, n_cols, slots, timeout_s
+        self.lo, self.hi = shard_range(n_total, rank, world)
+        self._opened = []
+        self.slot_bytes = n_total * n_cols * 4
+        mine = {}
+        self.ack_local, mine["ack"] = ctx.peer_alloc(8 * self.LINE)
+        if rank == root:
+            self.scores_base, mine["scores"] = ctx.peer_alloc(slots * self.slot_bytes)
+            self.arrive_base, mine["arrive"] = ctx.peer_alloc(8 * self.LINE * world)
+        everyone = exchange(mine)
+        if rank == root:
+            self.ack_of = [self.ack_local if r == rank else self._open(everyone[r]["ack"]) for r in range(world)]
+        else:
+            self.scores_base = self._open(everyone[root]["scores"])
+            self.arrive_base = self._open(everyone[root]["arrive"])
+        self.my_arrive = self.arrive_base + 8 * self.LINE * rank
+
+    def _open(self, handle):
+        addr = self.ctx.peer_open(handle)
+        self._opened.append(addr)
+        return addr
+
+    def begin(self, k, stream=None):
+        if k > self.slots:
+            self.ctx.peer_wait(self.ack_local, 1, 1, k - self.slots, self.timeout_s, stream)
+
+    def dest(self, k):
+        return self.scores_base + (k % self.slots) * self.slot_bytes + self.lo * self.n_cols * 4
+
+    def publish(self, k, stream=None):
+        self.ctx.peer_signal(self.my_arrive, k, stream)
+
+    def collect(self, k, stream=None):
+        if self.rank != self.root:
+            raise RuntimeError("collect() is the gathering rank's call")
+        self.ctx.peer_wait(self.arrive_base, self.world, self.LINE, k, self.timeout_s, stream)
+        return self.scores_base + (k % self.slots) * self.slot_bytes
+
+    def release(self, k, stream=None):
+        if self.rank != self.root:
+            raise RuntimeError("release() is the gathering rank's call")
+        for r in range(self.world):
+            self.ctx.peer_signal(self.ack_of[r], k, stream)
+
+    def close(self):
+        for a in self._opened:
+            self.ctx.peer_close(a)
+        self._opened = []
+        self.ctx.peer_free(self.ack_local)
+        if self.rank == self.root:
+            self.ctx.peer_free(self.scores_base)
+            self.ctx.peer_free(self.arrive_base)
+
+
+class _DeviceView:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, addr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(addr), False),
+                                         "version": 3, "strides": None}
+
+
 class ShardedStreams:
     """n_total independent streams split over the ranks of the default process group.
 
     ``engine_factory(n_local, lo, hi)`` builds this rank's step engine (on GPU ranks a
     ``StreamEngine`` bound to LOCAL_RANK); ``step(local_pcm)`` runs it and gathers the scores."""
 
-    def __init__(self, n_total, engine_factory, rank=None, world=None):
+    def __init__(self, n_total, engine_factory, rank=None, world=None, gather="nccl"):
         r, w, _ = env_rank_world()
         self.rank = r if rank is None else rank
         self.world = w if world is None else world
         self.n_total = n_total
         self.lo, self.hi = shard_range(n_total, self.rank, self.world)
         self.engine = engine_factory(self.hi - self.lo, self.lo, self.hi)
+        if gather not in ("nccl", "peer"):
+            raise ValueError("gather is 'nccl' (all-gather on every rank) or 'peer' (peer-memory gather on rank 0)")
+        self.peer = None
+        self._k = 0
+        if gather == "peer" and self.world > 1:
+            import torch.distributed as dist
+
+            def exchange(obj):
+                out = [None] * self.world
+                dist.all_gather_object(out, obj)
+                return out
+            self.peer = PeerGather(self.engine.ctx, n_total, self.engine.n_cols, self.rank, self.world, exchange)
 
     def step(self, local_pcm, n_chunks=1):
-        return gather_scores(self.engine.step(local_pcm, n_chunks), self.n_total)
+        """Scores of all n_total streams: on every rank with the NCCL all-gather; with gather='peer' on rank 0 only
+        (a view of the gather buffer, valid until the step after next) and None elsewhere."""
+        if self.peer is None:
+            return gather_scores(self.engine.step(local_pcm, n_chunks), self.n_total)
+        import torch
+        pg = self.peer
+        self._k += 1
+        k = self._k
+        stream = torch.cuda.current_stream(local_pcm.device).cuda_stream
+        if self.rank == pg.root and k > 1:
+            pg.release(k - 1, stream)             # whatever the caller enqueued on the previous result is ordered before this
+        pg.begin(k, stream)
+        self.engine.step(local_pcm, n_chunks, out=pg.dest(k))
+        pg.publish(k, stream)
+        if self.rank != pg.root:
+            return None
+        addr = pg.collect(k, stream)
+        return torch.as_tensor(_DeviceView(addr, (self.n_total, self.engine.n_cols)), device=local_pcm.device)

@@ -84,3 +84,105 @@ def test_two_rank_gloo_gather_preserves_stream_order(n_total):
 def test_gather_is_identity_without_a_process_group():
     x = torch.arange(12.0).reshape(4, 3)
     assert owd.gather_scores(x, 4) is x
+
+
+# ---- PeerGather protocol on host memory: ranks are threads, "device addresses" are addresses of NumPy buffers ----------
+class _FakePeerCtx:
+    """peer_* calls of _native.Context on host memory, executed synchronously (the real ones are stream-ordered
+    kernels; the ordering constraints they must satisfy are the same)."""
+    registry = {}
+
+    def __init__(self):
+        self.keep = []
+
+    def peer_alloc(self, n_bytes):
+        import ctypes
+        buf = np.zeros(n_bytes, np.uint8)
+        self.keep.append(buf)
+        handle = (b"%060d" % len(_FakePeerCtx.registry)).ljust(64, b"\0")
+        _FakePeerCtx.registry[handle] = buf
+        return buf.ctypes.data, handle
+
+    def peer_open(self, handle):
+        return _FakePeerCtx.registry[bytes(handle)].ctypes.data
+
+    def peer_close(self, addr):
+        pass
+
+    def peer_free(self, addr):
+        pass
+
+    def peer_signal(self, flag_addr, value, stream=None):
+        import ctypes
+        ctypes.c_uint64.from_address(flag_addr).value = value
+
+    def peer_wait(self, flags_addr, n, stride, value, timeout_s=10.0, stream=None):
+        import ctypes, time
+        t0 = time.time()
+        for i in range(n):
+            while ctypes.c_uint64.from_address(flags_addr + 8 * stride * i).value < value:
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError("peer_wait")
+                time.sleep(0)
+
+
+def test_peer_gather_protocol_threads():
+    """Four ranks x 40 steps with random stalls: the root always reads the scores of the step it collected from every
+    rank (no buffer is overwritten before it was released), uneven shards, two buffers."""
+    import ctypes, threading, time, random
+    from openwakeword_b200.distributed import PeerGather, shard_range
+    world, n_total, n_cols, steps = 4, 10, 3, 40
+    barrier = threading.Barrier(world)
+    box, errors, seen = [None] * world, [], []
+
+    def expected(k, row):
+        return np.arange(n_cols, dtype=np.float32) + 100.0 * k + row
+
+    def run(rank):
+        try:
+            rnd = random.Random(rank)
+
+            def exchange(obj):
+                box[rank] = obj
+                barrier.wait()
+                out = list(box)
+                barrier.wait()
+                return out
+            pg = PeerGather(_FakePeerCtx(), n_total, n_cols, rank, world, exchange, slots=2, timeout_s=20.0)
+            lo, hi = shard_range(n_total, rank, world)
+            for k in range(1, steps + 1):
+                if rank == pg.root and k > 1:
+                    pg.release(k - 1)
+                pg.begin(k)
+                time.sleep(rnd.random() * 0.003)
+                dst = np.ctypeslib.as_array(ctypes.cast(pg.dest(k), ctypes.POINTER(ctypes.c_float)), ((hi - lo), n_cols))
+                for r in range(lo, hi):
+                    dst[r - lo] = expected(k, r)
+                pg.publish(k)
+                if rank == pg.root:
+                    addr = pg.collect(k)
+                    time.sleep(rnd.random() * 0.003)              # a slow consumer
+                    full = np.ctypeslib.as_array(ctypes.cast(addr, ctypes.POINTER(ctypes.c_float)), (n_total, n_cols)).copy()
+                    seen.append((k, full))
+            pg.close()
+        except Exception as e:                                    # noqa: BLE001
+            errors.append((rank, repr(e)))
+            try:
+                barrier.abort()
+            except Exception:
+                pass
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errors, errors
+    assert len(seen) == steps
+    for k, full in seen:
+        want = np.stack([expected(k, r) for r in range(n_total)])
+        np.testing.assert_array_equal(full, want)
+
+
+def test_peer_gather_rejects_single_buffer():
+    from openwakeword_b200.distributed import PeerGather
+    with pytest.raises(ValueError):
+        PeerGather(_FakePeerCtx(), 4, 1, 0, 1, lambda o: [o], slots=1)
