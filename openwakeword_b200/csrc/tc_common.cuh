@@ -14,9 +14,20 @@ constexpr int kStages = 4;
 constexpr int kAccStages = 2;
 constexpr int kTcThreads = 192;
 
+// -DOWW_ACT_MAX3=1: one 3-input max (FMNMX3 on sm_100) instead of two FMNMX - same result for every non-NaN input.
+// Off until it has been A/B-timed on hardware (scripts/gpu_variants.sh).
+#ifndef OWW_ACT_MAX3
+#define OWW_ACT_MAX3 0
+#endif
 __device__ __forceinline__ float act(float v) {
+#if OWW_ACT_MAX3
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(kLeak * v), "f"(v), "f"(kFloor));
+    return r;
+#else
     v = fmaxf(kLeak * v, v);
     return fmaxf(v, kFloor);
+#endif
 }
 
 // ---------------------------------------------------------------- PTX wrappers
