@@ -271,6 +271,30 @@ class Model:
             data = np.concatenate((z, data, z))
         return [self.predict(data[i:i + chunk_size], **kwargs) for i in range(0, data.shape[0] - chunk_size, chunk_size)]
 
+    def _get_positive_prediction_frames(self, file, threshold=0.5, return_type="features", **kwargs):
+        """model.py:428-478: run the WAV through ``predict`` in 1280-sample steps and collect, per label, what produced
+        a score >= ``threshold``: the head's input features ``[n_in, 96]`` at that step (``return_type="features"``) or
+        the 4 s of audio around it (``"audio"``: 3 s before, 1 s after; steps without a full 4 s are dropped).
+        Returns {label: stacked array}; labels without a hit are absent."""
+        if return_type not in ("features", "audio"):
+            raise ValueError("return_type must be 'features' or 'audio'")
+        if self.n_streams != 1:
+            raise ValueError("_get_positive_prediction_frames is single-stream")
+        data = _read_wav(file)
+        hits = defaultdict(list)
+        for i in range(0, data.shape[0] - CHUNK, CHUNK):
+            for lbl, score in self.predict(data[i:i + CHUNK], **kwargs).items():
+                if score < threshold:
+                    continue
+                if return_type == "features":
+                    parent = self.get_parent_model_from_label(lbl)
+                    hits[lbl].append(self.preprocessor.get_features(self.model_inputs[parent]))
+                else:
+                    context = data[max(0, i - 16000 * 3):i + 16000]
+                    if len(context) == 16000 * 4:
+                        hits[lbl].append(context)
+        return {lbl: np.vstack(v) for lbl, v in hits.items() if v}
+
     def predict_clips(self, clips, padding=1, feature_init=None):
         """Array-input bulk path (extension): int16 [N,S] equal-length clips, each from a
         fresh state, 1280-sample steps.  Returns a list (per clip) of lists (per step) of {label: float},

@@ -236,3 +236,70 @@ def test_threaded_wav_ingest_keeps_order(tmp_path):
         f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000); f.writeframes(np.zeros(64, np.int16).tobytes())
     with pytest.raises(ValueError):
         _read_wavs(paths + [bad], 4)
+
+
+def test_get_positive_prediction_frames(fake_ctx, tmp_path):
+    """model.py:428-478 / tests/test_models.py:323-330: frames at or above the threshold come back as the head's input
+    features (or the 4 s audio context); an unreachable threshold gives an empty dict."""
+    import wave
+    c = load_case("alexa_c1280")
+    m = _model(c)
+    rng = np.random.default_rng(8)
+    pcm = rng.integers(-1000, 1000, 16000 * 5 + 640).astype(np.int16)
+    path = str(tmp_path / "clip.wav")
+    with wave.open(path, "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000); f.writeframes(pcm.tobytes())
+    n_steps = len(range(0, pcm.shape[0] - 1280, 1280))
+    name = c["names"][0]
+    feats = m._get_positive_prediction_frames(path, threshold=0.0)
+    assert list(feats) == [name]
+    assert feats[name].shape == (n_steps, m.model_inputs[name], 96)
+    m.reset(c["feature_init"])
+    audio = m._get_positive_prediction_frames(path, threshold=0.0, return_type="audio")
+    n_full = sum(1 for i in range(0, pcm.shape[0] - 1280, 1280) if i - 48000 >= 0 and i + 16000 <= pcm.shape[0])
+    assert audio[name].shape == (n_full, 64000)
+    first = next(i for i in range(0, pcm.shape[0] - 1280, 1280) if i - 48000 >= 0)
+    np.testing.assert_array_equal(audio[name][0], pcm[first - 48000:first + 16000])
+    m.reset(c["feature_init"])
+    assert m._get_positive_prediction_frames(path, threshold=1.5) == {}
+    with pytest.raises(ValueError):
+        m._get_positive_prediction_frames(path, return_type="spectrogram")
+
+
+class _ConstVerifier:
+    """Stands in for the scikit-learn pipeline of custom_verifier_model.py: constant P(positive)."""
+
+    def __init__(self, p):
+        self.p = p
+        self.calls = 0
+
+    def predict_proba(self, feats):
+        self.calls += 1
+        assert feats.shape[0] == 1 and feats.shape[2] == 96
+        return np.array([[1.0 - self.p, self.p]])
+
+
+def test_custom_verifier_hook(fake_ctx, tmp_path):
+    """model.py:175-195,319-328: a verifier pickled per base model replaces that model's score whenever the base score
+    reaches custom_verifier_threshold; keys that match no loaded model raise."""
+    import pickle
+    c = load_case("alexa_c1280")
+    name = c["names"][0]
+    path = str(tmp_path / "verifier.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(_ConstVerifier(0.7), f)
+    m = _model(c, custom_verifier_models={name: path}, custom_verifier_threshold=0.0)
+    rng = np.random.default_rng(1)
+    scores = [m.predict(rng.integers(-1000, 1000, 1280).astype(np.int16))[name] for _ in range(8)]
+    assert scores[:5] == [0.0] * 5                          # first-five zeroing still applies (model.py:330-333)
+    assert all(abs(s - 0.7) < 1e-6 for s in scores[5:])
+    plain = _model(c)
+    rng = np.random.default_rng(1)
+    base = [plain.predict(rng.integers(-1000, 1000, 1280).astype(np.int16))[name] for _ in range(8)]
+    assert any(abs(b - 0.7) > 1e-3 for b in base[5:])        # the replacement really changed something
+    high = _model(c, custom_verifier_models={name: path}, custom_verifier_threshold=2.0)   # never reached
+    rng = np.random.default_rng(1)
+    kept = [high.predict(rng.integers(-1000, 1000, 1280).astype(np.int16))[name] for _ in range(8)]
+    assert kept == base
+    with pytest.raises(ValueError):
+        _model(c, custom_verifier_models={"not_loaded": path})
