@@ -66,7 +66,10 @@ typedef struct oww_config {
     int32_t cnn_mode;      /* OWW_CNN_*                                                         */
     int32_t window_batch;  /* windows per CNN sub-batch in the window modes (0 = default)       */
     int32_t reserved[4];   /* reserved[0] bit 0: 1 = keep mode 3's steady-state step as separate launches
-                              (mel, CNN, append, heads) instead of the single fused step kernel      */
+                              (mel, CNN, append, heads) instead of the single fused step kernel;
+                              bit 1: 1 = heads on CUDA cores (heads.cu) even in the tensor-core modes;
+                              bit 2: 1 = tensor-core heads with plain fp16 operands (1 MMA term instead of the
+                              fp32-grade 3-term hi/lo split)                                          */
 } oww_config;
 
 typedef struct oww_head_desc {
@@ -74,7 +77,8 @@ typedef struct oww_head_desc {
     int32_t n_layers;                          /* Linear layers (>=1, <= OWW_MAX_HEAD_LAYERS)          */
     int32_t dims[OWW_MAX_HEAD_LAYERS + 1];     /* dims[0] = n_in*96, dims[n_layers] = n_out            */
     int32_t layernorm;                         /* 1: LayerNorm(eps 1e-5) after every hidden Linear     */
-    int32_t final_act;                         /* 0 none, 1 sigmoid, 2 softmax, 3 relu then softmax    */
+    int32_t final_act;                         /* 0 none, 1 sigmoid, 2 softmax, 3 relu then softmax,
+                                                  4 relu (train.py's multi-class Net before the softmax wrapper) */
 } oww_head_desc;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -92,6 +96,11 @@ int oww_load_embedding(oww_ctx* ctx, const float* h_blob, size_t n_floats);
 /* blob layout: weights.py:pack_head_blob.  *head_id receives the index; score columns are
  * appended in head order (head 0's n_out columns first).                                        */
 int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, size_t n_floats, int* head_id);
+/* Conditional verifier pair (the released hey_jarvis graph, docs/models/hey_jarvis.md:9,38: "the second network ...
+ * only predicting on audio frames that have a score > 0.5 from the first"): wherever the score of single-output head
+ * `main_head` exceeds `threshold` it is replaced by the score of single-output head `verifier_head`, per chunk, before
+ * the max over a multi-chunk call.  Both columns stay in d_scores (the verifier's holds its raw score).          */
+int oww_add_gate(oww_ctx* ctx, int main_head, int verifier_head, float threshold);
 int oww_n_heads(const oww_ctx* ctx);
 int oww_n_outputs(const oww_ctx* ctx);          /* total score columns over all heads           */
 
@@ -114,6 +123,10 @@ int oww_n_streams(const oww_ctx* ctx);
  * embeddings of unseeded noise, SURVEY.md F6 - pass the same rows to both sides for parity).
  * h_stream_ids NULL = all streams.  Synchronises.                                              */
 int oww_reset(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows);
+/* Same, stream-ordered: no allocation, no synchronisation.  Enqueue it on the stream the steps run on (the one passed
+ * to oww_step).  Streams that were reset re-prime from a full 76-row window at their next step (their first chunk
+ * yields 5 mel rows, utils.py:393-398) on a side stream while every other stream keeps the incremental fused kernel. */
+int oww_reset_async(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows, void* stream);
 /* One predict() worth of work for every stream: n_chunks*1280 new samples per stream.
  * d_pcm row b starts at d_pcm + b*pcm_stride (samples).  d_scores [n_streams][oww_n_outputs]:
  * per head the element-wise max over the n_chunks window positions (model.py:287-298).          */
@@ -132,6 +145,10 @@ int oww_step_host_collect(oww_ctx* ctx, int ticket, float* h_scores);
  * rows older than the ring holds come back as zeros.  Synchronises.                             */
 int oww_get_features(oww_ctx* ctx, int stream_id, int n, int back, float* h_out);
 int oww_get_mel(oww_ctx* ctx, int stream_id, int n_rows, float* h_out);   /* last n_rows<=76 mel rows */
+/* rows written to the stream's mel / feature buffer since its last reset, initial rows included (76 ones / the
+ * feature_init rows) - len(melspectrogram_buffer) / len(feature_buffer) of the reference before its 970 / 120 caps
+ * (utils.py:400-401,449-450).  Either pointer may be NULL.  Synchronises.                                     */
+int oww_get_counts(oww_ctx* ctx, int stream_id, int* mel_rows, int* feature_rows);
 
 /* ---- batch paths --------------------------------------------------------------------------- */
 /* d_pcm [n_clips][n_samples] -> d_emb [n_clips][W][96], W = (T-76)/8+1 (utils.py:322).           */

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "oww_load_mel": (C.c_int, [_P, _P, _P]),
     "oww_load_embedding": (C.c_int, [_P, _P, C.c_size_t]),
     "oww_add_head": (C.c_int, [_P, C.POINTER(HeadDesc), _P, C.c_size_t, C.POINTER(C.c_int)]),
+    "oww_add_gate": (C.c_int, [_P, C.c_int, C.c_int, C.c_float]),
     "oww_n_heads": (C.c_int, [_P]),
     "oww_n_outputs": (C.c_int, [_P]),
     "oww_melspectrogram": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
@@ -47,12 +48,14 @@ _SIGNATURES = {
     "oww_set_streams": (C.c_int, [_P, C.c_int]),
     "oww_n_streams": (C.c_int, [_P]),
     "oww_reset": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
+    "oww_reset_async": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "oww_step": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
     "oww_step_host": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "oww_step_host_submit": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.POINTER(C.c_int)]),
     "oww_step_host_collect": (C.c_int, [_P, C.c_int, _P]),
     "oww_get_features": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "oww_get_mel": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "oww_get_counts": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "oww_embed_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "oww_predict_clips": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "oww_debug_layer": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
@@ -111,10 +114,11 @@ def _ptr(a):
 class Context:
     """One handle = one GPU's weights + stream state (include/owwb200.h conventions)."""
 
-    def __init__(self, device=0, max_chunks=4, cnn_mode=CNN_FP32_WINDOW, window_batch=0, fuse_step=True):
+    def __init__(self, device=0, max_chunks=4, cnn_mode=CNN_TC_INCREMENTAL, window_batch=0, fuse_step=True,
+                 tc_heads=True, tc_heads_terms=3):
         self.lib = load_library()
         cfg = Config(device=device, max_chunks=max_chunks, cnn_mode=cnn_mode, window_batch=window_batch)
-        cfg.reserved[0] = 0 if fuse_step else 1
+        cfg.reserved[0] = (0 if fuse_step else 1) | (0 if tc_heads else 2) | (4 if tc_heads_terms == 1 else 0)
         h = _P()
         rc = self.lib.oww_create(C.byref(cfg), C.byref(h))
         if rc != 0:
@@ -159,6 +163,9 @@ class Context:
         self._check(self.lib.oww_add_head(self.h, C.byref(d), _ptr(blob), blob.size, C.byref(hid)))
         return hid.value
 
+    def add_gate(self, main_head, verifier_head, threshold=0.5):
+        self._check(self.lib.oww_add_gate(self.h, int(main_head), int(verifier_head), float(threshold)))
+
     @property
     def n_outputs(self):
         return self.lib.oww_n_outputs(self.h)
@@ -191,6 +198,13 @@ class Context:
         n_rows = 41 if fi is None else fi.shape[0]
         self._check(self.lib.oww_reset(self.h, _ptr(ids), 0 if ids is None else ids.size, _ptr(fi), n_rows))
 
+    def reset_async(self, stream_ids=None, feature_init=None, stream=None):
+        """Stream-ordered reset (no synchronisation): enqueue on the stream the steps run on."""
+        ids = None if stream_ids is None else np.ascontiguousarray(stream_ids, np.int32)
+        fi = None if feature_init is None else np.ascontiguousarray(feature_init, np.float32)
+        n_rows = 41 if fi is None else fi.shape[0]
+        self._check(self.lib.oww_reset_async(self.h, _ptr(ids), 0 if ids is None else ids.size, _ptr(fi), n_rows, stream))
+
     def step(self, d_pcm, pcm_stride, n_chunks, d_scores, stream=None):
         self._check(self.lib.oww_step(self.h, _ptr(d_pcm), pcm_stride, n_chunks, _ptr(d_scores), stream))
 
@@ -214,6 +228,12 @@ class Context:
         out = np.empty((n, 96), np.float32)
         self._check(self.lib.oww_get_features(self.h, stream_id, n, back, _ptr(out)))
         return out
+
+    def get_counts(self, stream_id):
+        """(mel rows, feature rows) written since the stream's last reset, initial rows included."""
+        m, f = C.c_int(0), C.c_int(0)
+        self._check(self.lib.oww_get_counts(self.h, stream_id, C.byref(m), C.byref(f)))
+        return m.value, f.value
 
     def get_mel(self, stream_id, n_rows=76):
         out = np.empty((n_rows, 32), np.float32)

@@ -46,10 +46,11 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 __global__ void reset_kernel(const int* ids, int n_ids, int n_streams, int16_t* tail, int* seen, int* mel_count,
                              int* feat_count, float* mel_ring, int mel_rows, float* feat_ring, int feat_rows,
-                             const float* feat_init, int n_rows) {
+                             const float* feat_init, int n_rows, uint8_t* primed) {
     const int j = blockIdx.x;
     const int b = ids ? ids[j] : j;
     if (b < 0 || b >= n_streams) return;
+    if (threadIdx.x == 0 && primed) primed[b] = 0;
     for (int i = threadIdx.x; i < OWW_TAIL; i += blockDim.x) tail[(int64_t)b * OWW_TAIL + i] = 0;
     float* mr = mel_ring + (int64_t)b * mel_rows * 32;
     for (int i = threadIdx.x; i < mel_rows * 32; i += blockDim.x) mr[i] = 1.0f;     // np.ones((76,32)), utils.py:165
@@ -76,17 +77,25 @@ void free_streams(oww_ctx* c) {
     cudaFree(c->d_tail); cudaFree(c->d_seen); cudaFree(c->d_mel_count); cudaFree(c->d_feat_count);
     cudaFree(c->d_mel_ring); cudaFree(c->d_feat_ring); cudaFree(c->d_act[0]); cudaFree(c->d_act[1]);
     cudaFree(c->d_emb_tmp); cudaFree(c->d_inc_tails[0]); cudaFree(c->d_inc_tails[1]);
+    cudaFree(c->d_primed); cudaFree(c->d_unprimed_ids); cudaFree(c->d_reset_ids); cudaFree(c->d_reset_init);
+    cudaFree(c->d_scores_tmp);
     c->d_tail = nullptr; c->d_seen = c->d_mel_count = c->d_feat_count = nullptr;
     c->d_mel_ring = c->d_feat_ring = c->d_act[0] = c->d_act[1] = c->d_emb_tmp = nullptr;
     c->d_inc_tails[0] = c->d_inc_tails[1] = nullptr;
-    c->inc_primed = false;
+    c->d_primed = nullptr; c->d_unprimed_ids = c->d_reset_ids = nullptr; c->d_reset_init = nullptr;
+    c->d_scores_tmp = nullptr; c->scores_tmp_floats = 0;
+    c->primed.clear(); c->n_unprimed = 0;
     c->act_floats = c->emb_tmp_floats = 0;
     c->n_streams = 0;
 }
 
 int ensure_act(oww_ctx* ctx, size_t floats) {
     if (ctx->cfg.cnn_mode == OWW_CNN_TC_WINDOW || ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL) {
-        const size_t units = oww_tc_act_units(ctx, ctx->window_batch);
+        // `floats` is n_windows * 74*32*24 (layer-1 output of the fp32 path): size the fp16 planes for the same windows
+        int n_win = (int)(floats / ((size_t)74 * 32 * 24));
+        if (n_win < 1) n_win = 1;
+        if (n_win > ctx->window_batch) n_win = ctx->window_batch;
+        const size_t units = oww_tc_act_units(ctx, n_win);
         if (ctx->tc_act_units < units) {
             cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]);
             ctx->d_tc_act[0] = ctx->d_tc_act[1] = nullptr; ctx->tc_act_units = 0;
@@ -114,6 +123,42 @@ int ensure_emb_tmp(oww_ctx* ctx, size_t floats) {
     return OWW_OK;
 }
 
+// the streams a reset left unprimed, as a device list for the re-prime chain (pageable source: the async copy is
+// staged by the driver before it returns, so the vector may change afterwards)
+int upload_unprimed(oww_ctx* ctx, std::vector<int>& ids, cudaStream_t s) {
+    ids.clear();
+    for (int b = 0; b < ctx->n_streams; ++b) if (!ctx->primed[b]) ids.push_back(b);
+    if (!ids.empty())
+        OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_unprimed_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    return OWW_OK;
+}
+
+void mark_all_primed(oww_ctx* ctx) {
+    if (ctx->n_unprimed) { std::fill(ctx->primed.begin(), ctx->primed.end(), (uint8_t)1); ctx->n_unprimed = 0; }
+}
+
+__global__ void set_primed_kernel(uint8_t* primed, const int* ids, int n, int n_streams) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (ids) primed[ids[i]] = 1; else if (i < n_streams) primed[i] = 1;
+}
+
+// mel + full-window CNN (tails captured) + ring append for the listed streams only: the re-prime chain
+int reprime_subset(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_ids, cudaStream_t s) {
+    int rc;
+    MelLaunch m{d_pcm, pcm_stride, OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
+                (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, n_ids, 1, 1};
+    m.ids = ctx->d_unprimed_ids;
+    if ((rc = oww_mel_launch(ctx, m, s))) return rc;
+    WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, n_ids, 1};
+    ws.ids = ctx->d_unprimed_ids;
+    if ((rc = oww_cnn_window(ctx, ws, n_ids, ctx->d_emb_tmp, s, true))) return rc;
+    if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, 1, s, ctx->d_unprimed_ids, n_ids))) return rc;
+    set_primed_kernel<<<(n_ids + 255) / 256, 256, 0, s>>>(ctx->d_primed, ctx->d_unprimed_ids, n_ids, ctx->n_streams);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
 int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks, float* d_scores, int out_stride,
               cudaStream_t s) {
     const int B = ctx->n_streams;
@@ -124,36 +169,100 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
     int rc;
     const long slot = ctx->timing ? ctx->ev_steps % ctx->ev_slots : 0;
     cudaEvent_t* ev = ctx->timing ? &ctx->ev[4 * slot] : nullptr;
-    if (n_chunks == 1 && oww_fused_step_supported(ctx)) {
-        // steady state: the whole step (frontend, CNN, ring append, heads) is ONE launch; two events bracket that
-        // launch as the "cnn" stage (an event record costs ~2.5 us of stream time, so no empty mel / heads pairs)
+    const bool inc = ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL;
+    const FeatSrc fs0{ctx->d_feat_ring, (int64_t)ctx->feat_rows * 96, ctx->d_feat_count, ctx->feat_rows - 1, 0};
+
+    if (inc && n_chunks == 1 && ctx->n_unprimed < B && oww_fused_frontend_supported(ctx)) {
+        // ---- steady state: frontend + CNN + ring append of every primed stream in ONE launch ----
+        const bool partial = ctx->n_unprimed > 0;
+        const bool heads_inside = !partial && oww_fused_heads_supported(ctx);
         if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
-        if ((rc = oww_fused_step(ctx, d_pcm, pcm_stride, d_scores, out_stride, s))) return rc;
-        if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[2], s)); ctx->ev_fused[slot] = 1; ctx->ev_steps++; }
+        std::vector<int> ids;
+        if (partial) {
+            // streams that were reset since the last step re-prime from a full window on a side stream (mel of their
+            // 5-row first chunk, full-window tcgen05 CNN with tail capture, ring append) while the fused kernel serves
+            // everyone else; both sides touch disjoint streams' state
+            if ((rc = upload_unprimed(ctx, ids, s))) return rc;
+            OWW_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+            OWW_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        }
+        if ((rc = oww_fused_step(ctx, d_pcm, pcm_stride, d_scores, out_stride, heads_inside, partial ? ctx->d_primed : nullptr, s)))
+            return rc;
+        if (partial) {
+            if ((rc = reprime_subset(ctx, d_pcm, pcm_stride, (int)ids.size(), ctx->side_stream))) return rc;
+            OWW_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+            OWW_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+            mark_all_primed(ctx);
+        }
+        if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
+        if (!heads_inside && (rc = oww_heads_all(ctx, fs0, B, d_scores, out_stride, 0, s))) return rc;
+        if (ev) {
+            if (heads_inside) ctx->ev_fused[slot] = 1;
+            else { OWW_CUDA(ctx, cudaEventRecord(ev[3], s)); ctx->ev_fused[slot] = 2; }
+            ctx->ev_steps++;
+        }
         return OWW_OK;
     }
+
+    // ---- general path: separate launches (modes 0 / 2, multi-chunk calls, or nothing primed yet) ----
     if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[0], s)); ctx->ev_fused[slot] = 0; }
     MelLaunch m{d_pcm, pcm_stride, n_chunks * OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
                 (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, B, 1, n_chunks};
     if ((rc = oww_mel_launch(ctx, m, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
     WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, B, n_chunks};
-    if (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && ctx->inc_primed) {
-        // steady state: one fused launch per chunk on the 8 new mel rows
+    if (inc && ctx->n_unprimed == 0) {
+        // every stream primed: one incremental launch per chunk on the 8 new mel rows
         for (int i = 0; i < n_chunks; ++i)
             if ((rc = oww_cnn_inc_step(ctx, 8 * (n_chunks - 1 - i), ctx->d_emb_tmp + (size_t)i * B * 96, s))) return rc;
     } else {
-        const bool prime = ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL;
-        if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s, prime))) return rc;
-        if (prime) ctx->inc_primed = true;
+        // full windows for everyone (also the multi-chunk call that meets unprimed streams); mode 3 captures the tails
+        if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s, inc))) return rc;
+        if (inc && ctx->n_unprimed) {
+            set_primed_kernel<<<(B + 255) / 256, 256, 0, s>>>(ctx->d_primed, nullptr, B, B);
+            OWW_LAUNCH_CHECK(ctx);
+            mark_all_primed(ctx);
+        }
     }
     if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, n_chunks, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
     for (int i = n_chunks - 1; i >= 0; --i) {
-        FeatSrc fs{ctx->d_feat_ring, (int64_t)ctx->feat_rows * 96, ctx->d_feat_count, ctx->feat_rows - 1, i};
-        if ((rc = oww_heads_launch(ctx, -1, fs, B, d_scores, out_stride, 0, i != n_chunks - 1, s))) return rc;
+        FeatSrc fs = fs0; fs.back = i;
+        if ((rc = oww_heads_all(ctx, fs, B, d_scores, out_stride, i != n_chunks - 1, s))) return rc;
     }
     if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[3], s)); ctx->ev_steps++; }
+    return OWW_OK;
+}
+
+// shared by oww_reset (synchronous) and oww_reset_async: enqueue the state reset of the listed streams on `s`
+int reset_enqueue(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows, cudaStream_t s) {
+    if (ctx->n_streams <= 0) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
+    if (n_rows < 0 || n_rows > ctx->feat_rows) return oww_fail(ctx, OWW_EINVAL, "n_rows=%d outside [0,%d]", n_rows, ctx->feat_rows);
+    if (!h_stream_ids) n = ctx->n_streams;
+    if (n <= 0) return OWW_OK;
+    if (n > ctx->n_streams) return oww_fail(ctx, OWW_EINVAL, "more stream ids (%d) than streams (%d)", n, ctx->n_streams);
+    if (h_stream_ids) {
+        for (int i = 0; i < n; ++i)
+            if (h_stream_ids[i] < 0 || h_stream_ids[i] >= ctx->n_streams)
+                return oww_fail(ctx, OWW_EINVAL, "stream id %d out of range", h_stream_ids[i]);
+        // pageable source: staged by the driver before the call returns; stream-ordered on the device
+        OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_reset_ids, h_stream_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    const bool have_init = h_feature_init && n_rows > 0;
+    if (have_init)
+        OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_reset_init, h_feature_init, (size_t)n_rows * 96 * sizeof(float), cudaMemcpyHostToDevice, s));
+    reset_kernel<<<n, 256, 0, s>>>(h_stream_ids ? ctx->d_reset_ids : nullptr, n, ctx->n_streams, ctx->d_tail, ctx->d_seen,
+                                   ctx->d_mel_count, ctx->d_feat_count, ctx->d_mel_ring, ctx->mel_rows, ctx->d_feat_ring,
+                                   ctx->feat_rows, have_init ? ctx->d_reset_init : nullptr, n_rows, ctx->d_primed);
+    OWW_LAUNCH_CHECK(ctx);
+    // a fresh stream's next window shifts by 5 rows, not 8: it re-primes from a full window at its next step
+    if (h_stream_ids) {
+        for (int i = 0; i < n; ++i)
+            if (ctx->primed[h_stream_ids[i]]) { ctx->primed[h_stream_ids[i]] = 0; ctx->n_unprimed++; }
+    } else {
+        std::fill(ctx->primed.begin(), ctx->primed.end(), (uint8_t)0);
+        ctx->n_unprimed = ctx->n_streams;
+    }
     return OWW_OK;
 }
 
@@ -193,8 +302,13 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
         oww_fail(nullptr, OWW_EUNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
         delete ctx; return OWW_EUNSUPPORTED;
     }
+    ctx->tc_heads = (cfg->reserved[0] & 2) == 0;
+    ctx->tc_heads_terms = (cfg->reserved[0] & 4) ? 1 : 3;
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     fill_layer_table(ctx);
     *out = ctx;
     return OWW_OK;
@@ -205,13 +319,20 @@ void oww_destroy(oww_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->clip_ctx) { oww_ctx* c = ctx->clip_ctx; ctx->clip_ctx = nullptr; free_streams(c);
         cudaStreamDestroy(c->own_stream);
+        if (c->side_stream) cudaStreamDestroy(c->side_stream);
+        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->ev_join) cudaEventDestroy(c->ev_join);
         cudaFree(c->d_tc_act[0]); cudaFree(c->d_tc_act[1]);
         cudaFree(c->slot[0].d_pcm); delete c; }
     free_streams(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
     cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
     cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w); cudaFree(ctx->d_head_devs);
-    for (auto& h : ctx->heads) cudaFree(h.d_blob);
+    for (auto& h : ctx->heads) { cudaFree(h.d_blob); cudaFree(h.d_w1_tc); }
+    cudaFree(ctx->d_gates);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& S : ctx->slot) {
         cudaFreeHost(S.h_pcm); cudaFreeHost(S.h_scores); cudaFree(S.d_pcm); cudaFree(S.d_scores);
         if (S.done) cudaEventDestroy(S.done);
@@ -254,7 +375,7 @@ int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, s
         return oww_fail(ctx, OWW_EUNSUPPORTED, "head has %d Linear layers (1..%d supported)", desc->n_layers, OWW_MAX_HEAD_LAYERS);
     if (desc->n_in < 1 || desc->dims[0] != desc->n_in * OWW_EMBEDDING_DIM)
         return oww_fail(ctx, OWW_EINVAL, "dims[0]=%d must equal n_in*96=%d", desc->dims[0], desc->n_in * OWW_EMBEDDING_DIM);
-    if (desc->final_act < 0 || desc->final_act > 3) return oww_fail(ctx, OWW_EINVAL, "bad final_act");
+    if (desc->final_act < 0 || desc->final_act > 4) return oww_fail(ctx, OWW_EINVAL, "bad final_act");
     if (ctx->heads.size() >= 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 heads per handle");
     Head h;
     h.desc = *desc;
@@ -286,6 +407,10 @@ int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, s
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
     OWW_CUDA(ctx, cudaMalloc(&h.d_blob, staged.size() * sizeof(float)));
     OWW_CUDA(ctx, cudaMemcpy(h.d_blob, staged.data(), staged.size() * sizeof(float), cudaMemcpyHostToDevice));
+    {   // tensor-core packing of the first layer (heads_tc.cu); heads it does not cover keep tc_ok == false
+        int rc = oww_heads_tc_pack(ctx, h, staged.data() + h.w_off[0]);
+        if (rc) { cudaFree(h.d_blob); return rc; }
+    }
     h.n_out = desc->dims[desc->n_layers];
     h.col0 = ctx->n_out_total;
     ctx->n_out_total += h.n_out;
@@ -293,6 +418,22 @@ int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, s
     ctx->heads.push_back(h);
     if (head_id) *head_id = (int)ctx->heads.size() - 1;
     return oww_heads_sync_devs(ctx);
+}
+
+int oww_add_gate(oww_ctx* ctx, int main_head, int verifier_head, float threshold) {
+    if (!ctx) return OWW_EINVAL;
+    const int nh = (int)ctx->heads.size();
+    if (main_head < 0 || main_head >= nh || verifier_head < 0 || verifier_head >= nh || main_head == verifier_head)
+        return oww_fail(ctx, OWW_EINVAL, "bad head ids %d / %d", main_head, verifier_head);
+    if (ctx->heads[main_head].n_out != 1 || ctx->heads[verifier_head].n_out != 1)
+        return oww_fail(ctx, OWW_EUNSUPPORTED, "a verifier gate joins two single-output heads");
+    if (ctx->gates.size() >= 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 gates per handle");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->gates.push_back(Gate{ctx->heads[main_head].col0, ctx->heads[verifier_head].col0, threshold});
+    cudaFree(ctx->d_gates); ctx->d_gates = nullptr;
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_gates, ctx->gates.size() * sizeof(Gate)));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_gates, ctx->gates.data(), ctx->gates.size() * sizeof(Gate), cudaMemcpyHostToDevice));
+    return OWW_OK;
 }
 
 int oww_n_heads(const oww_ctx* ctx) { return ctx ? (int)ctx->heads.size() : 0; }
@@ -325,6 +466,8 @@ int oww_head_predict(oww_ctx* ctx, int head_id, const float* d_feats, int n, flo
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
     const Head& h = ctx->heads[head_id];
     FeatSrc fs{d_feats, (int64_t)h.desc.n_in * 96, nullptr, -1, 0};
+    if (oww_heads_tc_supported(ctx, head_id))
+        return oww_heads_tc_launch(ctx, head_id, fs, n, d_out, h.n_out, 0, 0, (cudaStream_t)stream);
     return oww_heads_launch(ctx, head_id, fs, n, d_out, h.n_out, 0, 0, (cudaStream_t)stream);
 }
 
@@ -342,6 +485,12 @@ int oww_set_streams(oww_ctx* ctx, int n_streams) {
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_feat_count, (size_t)B * sizeof(int)));
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_mel_ring, (size_t)B * ctx->mel_rows * 32 * sizeof(float)));
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_feat_ring, (size_t)B * ctx->feat_rows * 96 * sizeof(float)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_primed, (size_t)B));
+    OWW_CUDA(ctx, cudaMemset(ctx->d_primed, 0, (size_t)B));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_unprimed_ids, (size_t)B * sizeof(int)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_reset_ids, (size_t)B * sizeof(int)));
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_reset_init, (size_t)ctx->feat_rows * 96 * sizeof(float)));
+    ctx->primed.assign(B, 0); ctx->n_unprimed = B;
     ctx->n_streams = B;
     int rc = ensure_act(ctx, (size_t)std::min(B * mc, ctx->window_batch) * 74 * 32 * 24);
     if (rc) return rc;
@@ -352,32 +501,19 @@ int oww_set_streams(oww_ctx* ctx, int n_streams) {
 
 int oww_reset(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows) {
     if (!ctx) return OWW_EINVAL;
-    if (ctx->n_streams <= 0) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
-    if (n_rows < 0 || n_rows > ctx->feat_rows) return oww_fail(ctx, OWW_EINVAL, "n_rows=%d outside [0,%d]", n_rows, ctx->feat_rows);
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (!h_stream_ids) n = ctx->n_streams;
-    if (n <= 0) return OWW_OK;
-    OWW_CUDA(ctx, cudaDeviceSynchronize());
-    int* d_ids = nullptr; float* d_init = nullptr;
-    if (h_stream_ids) {
-        for (int i = 0; i < n; ++i)
-            if (h_stream_ids[i] < 0 || h_stream_ids[i] >= ctx->n_streams)
-                return oww_fail(ctx, OWW_EINVAL, "stream id %d out of range", h_stream_ids[i]);
-        OWW_CUDA(ctx, cudaMalloc(&d_ids, (size_t)n * sizeof(int)));
-        OWW_CUDA(ctx, cudaMemcpy(d_ids, h_stream_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
-    }
-    if (h_feature_init && n_rows > 0) {
-        OWW_CUDA(ctx, cudaMalloc(&d_init, (size_t)n_rows * 96 * sizeof(float)));
-        OWW_CUDA(ctx, cudaMemcpy(d_init, h_feature_init, (size_t)n_rows * 96 * sizeof(float), cudaMemcpyHostToDevice));
-    }
-    reset_kernel<<<n, 256>>>(d_ids, n, ctx->n_streams, ctx->d_tail, ctx->d_seen, ctx->d_mel_count, ctx->d_feat_count,
-                             ctx->d_mel_ring, ctx->mel_rows, ctx->d_feat_ring, ctx->feat_rows, d_init, n_rows);
-    ctx->launches++;
-    ctx->inc_primed = false;          // a fresh stream's next window shifts by 5 rows, not 8: re-prime from a full window
+    OWW_CUDA(ctx, cudaDeviceSynchronize());              // steps may be in flight on any stream
+    int rc = reset_enqueue(ctx, h_stream_ids, n, h_feature_init, n_rows, nullptr);
+    if (rc) return rc;
     cudaError_t e = cudaDeviceSynchronize();
-    cudaFree(d_ids); cudaFree(d_init);
     if (e != cudaSuccess) return oww_fail(ctx, OWW_ECUDA, "reset failed: %s", cudaGetErrorString(e));
     return OWW_OK;
+}
+
+int oww_reset_async(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float* h_feature_init, int n_rows, void* stream) {
+    if (!ctx) return OWW_EINVAL;
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    return reset_enqueue(ctx, h_stream_ids, n, h_feature_init, n_rows, (cudaStream_t)stream);
 }
 
 int oww_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks, float* d_scores, void* stream) {
@@ -483,6 +619,19 @@ int oww_get_features(oww_ctx* ctx, int stream_id, int n, int back, float* h_out)
     return OWW_OK;
 }
 
+int oww_get_counts(oww_ctx* ctx, int stream_id, int* mel_rows, int* feature_rows) {
+    if (!ctx) return OWW_EINVAL;
+    if (stream_id < 0 || stream_id >= ctx->n_streams) return oww_fail(ctx, OWW_EINVAL, "bad stream id");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaDeviceSynchronize());
+    int c[2] = {0, 0};
+    OWW_CUDA(ctx, cudaMemcpy(&c[0], ctx->d_mel_count + stream_id, sizeof(int), cudaMemcpyDeviceToHost));
+    OWW_CUDA(ctx, cudaMemcpy(&c[1], ctx->d_feat_count + stream_id, sizeof(int), cudaMemcpyDeviceToHost));
+    if (mel_rows) *mel_rows = c[0];
+    if (feature_rows) *feature_rows = c[1];
+    return OWW_OK;
+}
+
 int oww_get_mel(oww_ctx* ctx, int stream_id, int n_rows, float* h_out) {
     if (!ctx || !h_out) return oww_fail(ctx, OWW_EINVAL, "null argument");
     if (stream_id < 0 || stream_id >= ctx->n_streams) return oww_fail(ctx, OWW_EINVAL, "bad stream id");
@@ -544,7 +693,11 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
         if (!c) return oww_fail(ctx, OWW_ENOMEM, "out of host memory");
         c->cfg = ctx->cfg; c->cfg.max_chunks = 1; c->device = ctx->device; c->sm_count = ctx->sm_count;
         c->window_batch = ctx->window_batch;
+        c->fuse_step = ctx->fuse_step; c->tc_heads = ctx->tc_heads; c->tc_heads_terms = ctx->tc_heads_terms;
         cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
         ctx->clip_ctx = c;
     }
     oww_ctx* c = ctx->clip_ctx;
@@ -554,6 +707,7 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     for (int li = 0; li < OWW_N_CONV; ++li) { c->conv[li] = ctx->conv[li]; c->tc_w_off[li] = ctx->tc_w_off[li]; c->tc_sb_off[li] = ctx->tc_sb_off[li]; }
     c->d_tc_w = ctx->d_tc_w; c->d_tc_sb = ctx->d_tc_sb; c->d_inc_w = ctx->d_inc_w;
     c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in; c->d_head_devs = ctx->d_head_devs;
+    c->gates = ctx->gates; c->d_gates = ctx->d_gates;
     int rc = OWW_OK;
     for (int c0 = 0; c0 < n_clips && rc == OWW_OK; c0 += slab_max) {
         const int m = std::min(slab_max, n_clips - c0);
@@ -577,6 +731,7 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     ctx->launches += c->launches; c->launches = 0;
     c->heads.clear();   // do not let the child free shared blobs
     c->d_head_devs = nullptr;
+    c->gates.clear(); c->d_gates = nullptr;
     return rc;
 }
 
@@ -607,7 +762,7 @@ int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int
 
 int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_out21) {
     if (!ctx || !h_out21) return oww_fail(ctx, OWW_EINVAL, "null argument");
-    if (ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || !ctx->inc_primed)
+    if (ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || ctx->n_unprimed)
         return oww_fail(ctx, OWW_EINVAL, "needs cnn_mode 3 after at least one step");
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
     OWW_CUDA(ctx, cudaDeviceSynchronize());
@@ -648,9 +803,12 @@ int oww_stage_ms(oww_ctx* ctx, float out_ms[3]) {
     double acc[3] = {0, 0, 0};
     for (long k = 0; k < n; ++k) {
         cudaEvent_t* ev = &ctx->ev[4 * k];
-        const bool fused = ctx->ev_fused[k] != 0;
-        OWW_CUDA(ctx, cudaEventSynchronize(ev[fused ? 2 : 3]));
-        for (int i = fused ? 1 : 0; i < (fused ? 2 : 3); ++i) {
+        // 0: mel | cnn | heads launches (events 0..3)   1: one fused launch (events 1..2)
+        // 2: fused frontend+CNN launch, then a heads launch (events 1..3)
+        const int kind = ctx->ev_fused[k];
+        const int first = kind == 0 ? 0 : 1, last = kind == 1 ? 2 : 3;
+        OWW_CUDA(ctx, cudaEventSynchronize(ev[last]));
+        for (int i = first; i < last; ++i) {
             float ms = 0.f;
             OWW_CUDA(ctx, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
             acc[i] += ms;

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(256) conv0_kernel(L0Args a) {
         const int j = (int)(r / a.t_out);
         const float* base; int row0, mask;
         if (a.src.count) {
-            const int b = j % a.src.n_streams, i = j / a.src.n_streams;
+            const int lb = j % a.src.n_streams, i = j / a.src.n_streams;
+            const int b = a.src.ids ? a.src.ids[lb] : lb;
             base = a.src.base + (int64_t)b * a.src.stride;
             row0 = a.src.count[b] - 8 * (a.src.n_chunks - 1 - i) - OWW_WINDOW_ROWS;
             mask = a.src.rows_mask;
@@ -243,20 +244,21 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* in, int64_t in_s
 
 // ---------------- append embeddings to the per-stream feature rings -----------------------------
 __global__ void __launch_bounds__(256) feat_append_kernel(const float* emb, float* ring, int* count, int n_streams,
-                                                          int n_chunks, int rows_mask, int64_t ring_stride) {
+                                                          int n_chunks, int rows_mask, int64_t ring_stride, const int* ids) {
     const int64_t total = (int64_t)n_streams * n_chunks * 24;   // float4 units
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int c4 = (int)(i % 24);
         const int64_t j = i / 24;                 // window index = chunk * n_streams + stream
-        const int b = (int)(j % n_streams), ch = (int)(j / n_streams);
+        const int lb = (int)(j % n_streams), ch = (int)(j / n_streams);
+        const int b = ids ? ids[lb] : lb;
         const int slot = (count[b] + ch) & rows_mask;
         reinterpret_cast<float4*>(ring + (int64_t)b * ring_stride + (int64_t)slot * 96)[c4] =
             __ldg(reinterpret_cast<const float4*>(emb + j * 96) + c4);
     }
 }
-__global__ void count_add_kernel(int* count, int n, int add) {
+__global__ void count_add_kernel(int* count, int n, int add, const int* ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) count[i] += add;
+    if (i < n) { const int b = ids ? ids[i] : i; count[b] = oww_wrap_count(count[b] + add); }
 }
 
 template <int CIN, int COUT, int KH, int KW, int BM>
@@ -350,8 +352,8 @@ int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_e
                 n -= n % src.n_streams;
             } else {
                 if (n > src.n_streams - b0) n = src.n_streams - b0;
-                sub.base = src.base + (int64_t)b0 * src.stride;
-                sub.count = src.count + b0;
+                if (src.ids) sub.ids = src.ids + b0;          // the id list carries the offset; base / count stay global
+                else { sub.base = src.base + (int64_t)b0 * src.stride; sub.count = src.count + b0; }
                 sub.n_streams = n;
             }
         } else {
@@ -366,9 +368,9 @@ int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_e
                 const int b0 = w0 % src.n_streams, i0 = w0 / src.n_streams;
                 if (b0 == 0 && n >= src.n_streams) {
                     const int k = n / src.n_streams;
-                    if (i0 + k == src.n_chunks) cap = TailCapture{(k - 1) * src.n_streams, src.n_streams, 0};
+                    if (i0 + k == src.n_chunks) cap = TailCapture{(k - 1) * src.n_streams, src.n_streams, 0, src.ids};
                 } else if (i0 == src.n_chunks - 1) {
-                    cap = TailCapture{0, n, b0};
+                    cap = TailCapture{0, n, b0, src.ids};
                 }
             }
             rc = oww_cnn_tc_pyramid_cap(ctx, sub, n, o, cap.n_win ? &cap : nullptr, s);
@@ -398,14 +400,15 @@ int oww_cnn_clip_fp32(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_e
     return OWW_OK;
 }
 
-int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s) {
-    const int B = ctx->n_streams;
+int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s, const int* d_ids, int n_ids) {
+    const int B = d_ids ? n_ids : ctx->n_streams;
+    if (B <= 0) return OWW_OK;
     const int64_t total = (int64_t)B * n_chunks * 24;
     unsigned grid = (unsigned)((total + 255) / 256);
     feat_append_kernel<<<grid, 256, 0, s>>>(d_emb, ctx->d_feat_ring, ctx->d_feat_count, B, n_chunks,
-                                           ctx->feat_rows - 1, (int64_t)ctx->feat_rows * 96);
+                                           ctx->feat_rows - 1, (int64_t)ctx->feat_rows * 96, d_ids);
     OWW_LAUNCH_CHECK(ctx);
-    count_add_kernel<<<(B + 255) / 256, 256, 0, s>>>(ctx->d_feat_count, B, n_chunks);
+    count_add_kernel<<<(B + 255) / 256, 256, 0, s>>>(ctx->d_feat_count, B, n_chunks, d_ids);
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) tc_conv0_kernel(Tc0Args a) {
         }
         const float* base; int row0, mask;
         if (a.src.count) {
-            const int b = j % a.src.n_streams, i = j / a.src.n_streams;
+            const int lb = j % a.src.n_streams, i = j / a.src.n_streams;
+            const int b = a.src.ids ? a.src.ids[lb] : lb;
             base = a.src.base + (int64_t)b * a.src.stride;
             row0 = a.src.count[b] - 8 * (a.src.n_chunks - 1 - i) - OWW_WINDOW_ROWS;
             mask = a.src.rows_mask;
@@ -328,10 +329,11 @@ inline int round8(int v) { return (v + 7) & ~7; }
 template <int CGP, int NP>
 int launch_tc(oww_ctx* ctx, const TcConvArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)3 * CGP * NP * 16 + (size_t)kStages * CGP * a.rows * 16 + 8 * (2 * kStages + 2 * kAccStages + 1) + 16;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the attribute is per (function, device): tracked per handle (one bit per kernel instance), not per process
+    const uint32_t bit = 1u << ((CGP / 2 + NP / 16) & 31);       // distinct for the seven instances in use
+    if (!(ctx->tc_attr_mask & bit)) {
         OWW_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<CGP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_done = true;
+        ctx->tc_attr_mask |= bit;
     }
     int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
     tc_conv_kernel<CGP, NP><<<grid, kTcThreads, smem, s>>>(a);
@@ -469,7 +471,7 @@ int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_
         }
         if (cap && cap->n_win > 0 && !last) {
             // the tensor just produced feeds layer li+1; if that is a (3,1) conv its last two rows are the tails
-            int rc = oww_inc_capture(ctx, li, bufs[cur ^ 1], in_plane, T, W, cap->win0, cap->n_win, cap->stream0, s);
+            int rc = oww_inc_capture(ctx, li, bufs[cur ^ 1], in_plane, T, W, cap->win0, cap->n_win, cap->stream0, cap->ids, s);
             if (rc) return rc;
         }
         if (li == stop_layer && !last) {

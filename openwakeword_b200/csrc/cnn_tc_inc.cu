@@ -64,6 +64,9 @@ struct IncArgs {
     const HeadDev* heads; int n_heads; int max_n_in;
     float* scores; int score_stride;
     int hring_off, hslot_bytes, hns;                          // smem ring the producer streams the heads' first-layer weights through
+    const uint8_t* primed;                                    // optional [B]: 0 = stream is skipped entirely (its state is untouched:
+                                                              // it is being re-primed from a full window by other launches)
+    const Gate* gates; int n_gates;                           // conditional verifier pairs, applied after the heads phase
 };
 
 // Rows of a later head layer (K x D floats) per ring chunk: a multiple of 4 rows (16-byte chunk starts) that fits a slot.
@@ -242,8 +245,15 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
             int* s_cnt = reinterpret_cast<int*>(smem + 1536);      // [0..7] mel row count, [8..15] feature count, before this step
+            int* s_live = s_cnt + 16;                              // [0..7] stream exists and is primed: it takes part in this launch
             float* s_mel = reinterpret_cast<float*>(smem + P.scratch_off + 6144);   // [G][8][32] this step's mel rows
             if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[101] = clock64();
+            named_bar_sync(2, kIncEpiWarps * 32);                  // every warp is done with the previous group's s_live / s_cnt
+            if (et < G) {
+                const int b = grp * G + et;
+                s_live[et] = b < a.B && (!a.primed || a.primed[b]);
+            }
+            named_bar_sync(2, kIncEpiWarps * 32);
             if (a.fused) {
                 // ===== frontend: log-mel of this step's 8 frames per stream (K1 inside the step kernel) =====
                 uint8_t* sc = smem + P.scratch_off;
@@ -254,8 +264,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 for (int i = et; i < 512; i += kIncEpiWarps * 32) { s_tw[i] = a.mel_twiddle[i]; s_win[i] = a.mel_window[i]; }
                 if (et < G) {
                     const int b = grp * G + et;
-                    s_cnt[et] = b < a.B ? a.mel_count_rw[b] : 0;
-                    s_cnt[8 + et] = b < a.B ? a.feat_count[b] : 0;
+                    s_cnt[et] = s_live[et] ? a.mel_count_rw[b] : 0;
+                    s_cnt[8 + et] = s_live[et] ? a.feat_count[b] : 0;
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 const int my_start = a.mel_start[lane], my_len = a.mel_len[lane];
@@ -291,16 +301,16 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     float v = fmaxf(s_mel[i], s_floor[g]);
                     v = v / 10.0f + 2.0f;
                     s_mel[i] = v;
-                    if (b < a.B)
+                    if (s_live[g])
                         a.mel_rw[(int64_t)b * a.mel_stride + (int64_t)((s_cnt[g] + ((i >> 5) & 7)) & a.mel_mask) * 32 + (i & 31)] = v;
                 }
                 for (int i = et; i < G * OWW_TAIL; i += kIncEpiWarps * 32) {
                     const int g = i / OWW_TAIL, k = i - g * OWW_TAIL, b = grp * G + g;
-                    if (b < a.B) a.tail[(int64_t)b * OWW_TAIL + k] = __ldg(a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + k);
+                    if (s_live[g]) a.tail[(int64_t)b * OWW_TAIL + k] = __ldg(a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + k);
                 }
-                if (et < G && grp * G + et < a.B) {
+                if (et < G && s_live[et]) {
                     const int b = grp * G + et;
-                    a.mel_count_rw[b] = s_cnt[et] + 8;
+                    a.mel_count_rw[b] = oww_wrap_count(s_cnt[et] + 8);
                     const int sn = a.seen[b] + 1;
                     a.seen[b] = sn > (1 << 30) ? (1 << 30) : sn;
                 }
@@ -338,7 +348,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         uint4* o = nx + 1 + tg * Wp + f0;
                         const uint4 z = make_uint4(0, 0, 0, 0);
                         if (j == 16) { o[0] = z; o[L.nx_pitch] = z; o[2 * L.nx_pitch] = z; continue; }      // pad column f = 32
-                        if (b >= a.B) {
+                        if (!s_live[g]) {
                             o[0] = z; o[L.nx_pitch] = z; o[2 * L.nx_pitch] = z;
                             o[1] = z; o[L.nx_pitch + 1] = z; o[2 * L.nx_pitch + 1] = z;
                             continue;
@@ -429,7 +439,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         const int tg = (int)__umulhi((uint32_t)m, wp_magic);
                         const int f = m - tg * L.Wp;
                         const int g = G > 1 ? tg - (int)__umulhi((uint32_t)tg, g_magic) * G : 0;
-                        const bool live = grp * G + g < a.B;
+                        const bool live = s_live[g] != 0;
                         if (L.final) {
                             if (f != 0 || !live) continue;
                             float* o = a.fused ? a.feat_ring + (int64_t)(grp * G + g) * a.feat_stride + (int64_t)(s_cnt[8 + g] & a.feat_mask) * 96
@@ -487,7 +497,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             const int perrow = G * L.nx_Wp;
                             for (int i = et; i < L.cg_out * perrow; i += kIncEpiWarps * 32) {
                                 const int pl = i / perrow, u = i - pl * perrow;
-                                if (grp * G + (u / L.nx_Wp) < a.B)
+                                if (s_live[u / L.nx_Wp])
                                     tout[L.nx_tail_off + pl * 2 * perrow + u] = nx[pl * L.nx_pitch + 1 + perrow + u];
                             }
                         }
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                                 res = *reinterpret_cast<uint4*>(mx);
                             }
                             nx[pl * L.nx_pitch + 1 + L.nx_t_off * G * L.nx_Wp + p] = res;
-                            if (L.nx_tail_off >= 0 && grp * G + g < a.B) {
+                            if (L.nx_tail_off >= 0 && s_live[g]) {
                                 // the pooled rows are the newest rows of a tails-bearing buffer
                                 const int keep = T2 >= 2 ? 2 : 1;
                                 if (t >= T2 - keep)
@@ -537,7 +547,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             if (a.fused) {
                 // ===== K3 inside the step kernel: every head on this group's streams, straight from the feature ring =====
                 named_bar_sync(2, kIncEpiWarps * 32);              // the new embedding rows (written by this CTA) are visible
-                if (et == 0 && a.n_heads > 0) mbar_arrive(hstart_bar);           // producer may start streaming head weights
+                if (a.n_heads > 0) {                               // n_heads == 0: the heads run as their own launch after this one
+                if (et == 0) mbar_arrive(hstart_bar);              // producer may start streaming head weights
                 const int NI = a.max_n_in;
                 float* feats = reinterpret_cast<float*>(smem + 2048);            // [G][NI][96]
                 float* red = feats + G * NI * 96;                                // [4][G][128]
@@ -552,7 +563,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (i < G * NI * 24) {
                             const int g = i / (NI * 24), r = (i / 24) % NI, c4 = (i % 24) * 4, b = grp * G + g;
-                            if (b < a.B) {
+                            if (s_live[g]) {
                                 const int row = s_cnt[8 + g] + 1 - NI + r;
                                 if (row >= 0) v[u] = __ldcg(reinterpret_cast<const float4*>(a.feat_ring + (int64_t)b * a.feat_stride + (int64_t)(row & a.feat_mask) * 96 + c4));
                             }
@@ -684,10 +695,12 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             named_bar_sync(2, kIncEpiWarps * 32);
                         }
                     }
-                    if (et < G && grp * G + et < a.B) {
+                    if (et < G && s_live[et]) {
                         const int n_out = H.dims[H.n_layers];
                         float* row = cur + et * 256;
-                        if (H.final_act == 1) {
+                        if (H.final_act == 4) {
+                            for (int d = 0; d < n_out; ++d) row[d] = fmaxf(row[d], 0.f);
+                        } else if (H.final_act == 1) {
                             for (int d = 0; d < n_out; ++d) row[d] = 1.0f / (1.0f + expf(-row[d]));
                         } else if (H.final_act == 2 || H.final_act == 3) {
                             float m = -INFINITY;
@@ -704,7 +717,16 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     }
                     named_bar_sync(2, kIncEpiWarps * 32);
                 }
-                if (et < G && grp * G + et < a.B) a.feat_count[grp * G + et] = s_cnt[8 + et] + 1;
+                }
+                if (et < G && s_live[et]) {
+                    if (a.n_heads > 0) {
+                        // conditional verifier pairs: the thread that wrote this stream's scores rewrites the gated columns
+                        float* o = a.scores + (int64_t)(grp * G + et) * a.score_stride;
+                        for (int q = 0; q < a.n_gates; ++q)
+                            if (o[a.gates[q].main_col] > a.gates[q].thr) o[a.gates[q].main_col] = o[a.gates[q].ver_col];
+                    }
+                    a.feat_count[grp * G + et] = oww_wrap_count(s_cnt[8 + et] + 1);
+                }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[102] = clock64();
             }
@@ -720,7 +742,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
 
 // ---- capture of tails from the full-window planes (stream-major positions) ----------------------
 __global__ void __launch_bounds__(256) tc_capture_kernel(const uint4* planes, int64_t plane_pitch, int T, int Wp, int cg,
-                                                         int win0, int n_win, int stream0, int G, int tail_off,
+                                                         int win0, int n_win, int stream0, const int* ids, int G, int tail_off,
                                                          int tail_units, uint4* tails) {
     const int per = 2 * Wp;
     const int64_t total = (int64_t)n_win * cg * per;
@@ -729,7 +751,7 @@ __global__ void __launch_bounds__(256) tc_capture_kernel(const uint4* planes, in
         const int pl = (int)((i / per) % cg);
         const int w = (int)(i / ((int64_t)per * cg));
         const int r = u / Wp, f = u - r * Wp;
-        const int b = stream0 + w, grp = b / G, g = b - grp * G;
+        const int b = ids ? ids[stream0 + w] : stream0 + w, grp = b / G, g = b - grp * G;
         const uint4 v = planes[(int64_t)pl * plane_pitch + kGuard + (int64_t)(win0 + w) * T * Wp + (int64_t)(T - 2 + r) * Wp + f];
         tails[(int64_t)grp * tail_units + tail_off + pl * (2 * G * Wp) + (r * G + g) * Wp + f] = v;
     }
@@ -908,7 +930,6 @@ int oww_inc_alloc_streams(oww_ctx* ctx) {
         OWW_CUDA(ctx, cudaMemset(ctx->d_inc_tails[i], 0, bytes));
     }
     ctx->inc_cur = 0;
-    ctx->inc_primed = false;
     OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
     return OWW_OK;
 }
@@ -935,10 +956,16 @@ int oww_heads_sync_devs(oww_ctx* ctx) {
     return OWW_OK;
 }
 
-// Can the whole step run as one launch?  (steady state, one chunk, heads within the in-kernel limits)
-bool oww_fused_step_supported(const oww_ctx* ctx) {
-    if (!ctx->fuse_step || ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || !ctx->inc_primed) return false;
-    if (ctx->inc_plan.scratch_off == 0 || ctx->heads.size() > 16) return false;
+// Can the frontend + CNN + ring append of a one-chunk step run as the fused launch?  (mode 3, at least the streams
+// that are primed; the caller decides what happens to unprimed ones)
+bool oww_fused_frontend_supported(const oww_ctx* ctx) {
+    return ctx->fuse_step && ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && ctx->inc_plan.scratch_off != 0;
+}
+
+// Can the heads run inside that launch too?  (heads within the in-kernel limits; worthwhile only while re-streaming the
+// first-layer matrices once per group of G streams is cheap)
+bool oww_fused_heads_supported(const oww_ctx* ctx) {
+    if (!oww_fused_frontend_supported(ctx) || ctx->heads.empty() || ctx->heads.size() > 16) return false;
     // In the fused kernel every group of G streams re-streams each head's first-layer matrix from L2; with many
     // groups x many/large heads that traffic (and the 7-row tiles) loses to the stand-alone heads kernel's 32-row tiles.
     {
@@ -969,20 +996,24 @@ static void fill_inc_args(oww_ctx* ctx, IncArgs& a) {
     a.dbg_clock = reinterpret_cast<long long*>(ctx->d_inc_dbg);
 }
 
-// PCM -> scores for every stream in ONE launch: frontend, 20-layer CNN, ring append and all heads.
-int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, cudaStream_t s) {
+// One launch per step: frontend, 20-layer CNN and ring append for every primed stream (d_primed == nullptr: all of
+// them), plus - with_heads - every head and the verifier gates, i.e. PCM in -> scores out.
+int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, bool with_heads,
+                   const uint8_t* d_primed, cudaStream_t s) {
     IncArgs a;
     fill_inc_args(ctx, a);
     a.fused = 1;
+    a.primed = d_primed;
     a.pcm = d_pcm; a.pcm_stride = pcm_stride;
     a.tail = ctx->d_tail; a.seen = ctx->d_seen; a.mel_rw = ctx->d_mel_ring; a.mel_count_rw = ctx->d_mel_count;
     a.mel_window = ctx->d_window; a.mel_twiddle = ctx->d_twiddle; a.mel_start = ctx->d_mel_start; a.mel_len = ctx->d_mel_len;
     a.mel_w = ctx->d_mel_w; a.mel_kmax = ctx->mel_kmax;
     a.feat_ring = ctx->d_feat_ring; a.feat_stride = (int64_t)ctx->feat_rows * 96; a.feat_mask = ctx->feat_rows - 1;
     a.feat_count = ctx->d_feat_count;
-    a.heads = ctx->d_head_devs; a.n_heads = (int)ctx->heads.size(); a.max_n_in = ctx->max_n_in > 0 ? ctx->max_n_in : 1;
+    a.heads = ctx->d_head_devs; a.n_heads = with_heads ? (int)ctx->heads.size() : 0; a.max_n_in = ctx->max_n_in > 0 ? ctx->max_n_in : 1;
     a.scores = d_scores; a.score_stride = out_stride;
-    {   // ring for the heads' first-layer weights: after feats/red/h, below the first weight slot the next group prefetches
+    a.gates = ctx->d_gates; a.n_gates = with_heads ? (int)ctx->gates.size() : 0;
+    if (with_heads) {   // ring for the heads' first-layer weights: after feats/red/h, below the first weight slot the next group prefetches
         int d1max = 32;
         for (const Head& h : ctx->heads) d1max = h.desc.dims[1] > d1max ? h.desc.dims[1] : d1max;
         const int G = a.plan.G;
@@ -1017,14 +1048,14 @@ int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
 // Tail capture hook for the full-window tensor-core pyramid (cnn_tc.cu): called after the layer
 // whose (possibly pooled) output feeds a (3,1) convolution.
 int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
-                    int stream0, cudaStream_t s) {
+                    int stream0, const int* d_ids, cudaStream_t s) {
     const IncLayer& L = ctx->inc_plan.L[layer];
     if (L.nx_tail_off < 0) return OWW_OK;
     const int Wp = W + 1;
     const int64_t total = (int64_t)n_win * L.cg_out * 2 * Wp;
     unsigned grid = (unsigned)((total + 255) / 256);
     tc_capture_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(planes), plane_pitch, T, Wp, L.cg_out, win0, n_win,
-                                          stream0, ctx->inc_plan.G, L.nx_tail_off, ctx->inc_plan.tail_units,
+                                          stream0, d_ids, ctx->inc_plan.G, L.nx_tail_off, ctx->inc_plan.tail_units,
                                           reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur]));
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;

@@ -243,7 +243,9 @@ __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
     const int n_out = H.dims[H.n_layers];
     if (tid < TB && s0 + tid < a.n) {
         float* row = cur[tid];
-        if (H.final_act == 1) {
+        if (H.final_act == 4) {
+            for (int d = 0; d < n_out; ++d) row[d] = fmaxf(row[d], 0.f);
+        } else if (H.final_act == 1) {
             for (int d = 0; d < n_out; ++d) row[d] = 1.0f / (1.0f + expf(-row[d]));
         } else if (H.final_act == 2 || H.final_act == 3) {
             float m = -INFINITY;
@@ -264,14 +266,19 @@ __global__ void __launch_bounds__(NTHREADS) heads_kernel(HeadsArgs a) {
 
 // head_id < 0: all heads (blockIdx.y = head), score columns at each head's col0 (+out_col0).
 int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float* d_out, int out_stride,
-                     int out_col0, int combine_max, cudaStream_t s) {
+                     int out_col0, int combine_max, cudaStream_t s, uint32_t head_mask) {
     if (n <= 0) return OWW_OK;
-    const int nh = head_id < 0 ? (int)ctx->heads.size() : 1;
+    int sel[16], nh = 0;
+    if (head_id >= 0) sel[nh++] = head_id;
+    else {
+        if (ctx->heads.size() > 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 heads per launch");
+        for (int i = 0; i < (int)ctx->heads.size(); ++i) if (head_mask >> i & 1u) sel[nh++] = i;
+    }
     if (nh == 0) return OWW_OK;
-    if (nh > 16) return oww_fail(ctx, OWW_EUNSUPPORTED, "at most 16 heads per launch");
+    if (src.steps > 0) return oww_fail(ctx, OWW_EUNSUPPORTED, "sliding feature windows need the tensor-core heads kernel");
     HeadsArgs a;
     for (int i = 0; i < nh; ++i) {
-        const Head& h = ctx->heads[head_id < 0 ? i : head_id];
+        const Head& h = ctx->heads[sel[i]];
         HeadDev& d = a.head[i];
         d.blob = h.d_blob;
         d.n_in = h.desc.n_in; d.n_layers = h.desc.n_layers; d.layernorm = h.desc.layernorm; d.final_act = h.desc.final_act;
@@ -299,11 +306,10 @@ int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float
     if (smem_of(tb, stages) > kLimit)
         return oww_fail(ctx, OWW_EUNSUPPORTED, "head layer width %d needs too much shared memory", dmax);
     a.stages = stages;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->heads_attr_set) {      // the attribute is per (function, device): tracked per handle, not per process
         OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         OWW_CUDA(ctx, cudaFuncSetAttribute(heads_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_set = true;
+        ctx->heads_attr_set = true;
     }
     if (small) {
         dim3 grid((n + 7) / 8, nh);

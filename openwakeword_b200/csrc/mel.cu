@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelLaunch p, MelDev c) {
     __shared__ float s_pow[kWarps][264];
     __shared__ float s_red[kWarps];
 
-    const int clip = blockIdx.x;
+    const int clip = p.ids ? p.ids[blockIdx.x] : blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int i = tid; i < 512; i += kThreads) { s_tw[i] = c.twiddle[i]; s_win[i] = c.window[i]; }
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) mel_kernel(MelLaunch p, MelDev c) {
         int16_t* tw = p.tail + (int64_t)clip * OWW_TAIL;
         for (int i = tid; i < OWW_TAIL; i += kThreads) tw[i] = __ldg(body + (p.n_body - OWW_TAIL + i));
         if (tid == 0) {
-            p.out_count[clip] = row0 + nrows;
+            p.out_count[clip] = oww_wrap_count(row0 + nrows);
             const int sn = p.seen[clip] + p.n_chunks;
             p.seen[clip] = sn > (1 << 30) ? (1 << 30) : sn;
         }

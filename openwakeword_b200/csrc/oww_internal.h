@@ -29,7 +29,26 @@ struct Head {
     int col0;            // first score column
     float* d_blob;       // packed weights (layout of pack_head_blob)
     std::vector<size_t> w_off, b_off, g_off, h_off;   // float offsets per layer
+    // tensor-core first layer (heads_tc.cu): fp16 hi/lo of W1 * 2^s in UMMA order, or tc_ok == false
+    bool tc_ok = false;
+    void* d_w1_tc = nullptr;
+    int tc_np = 0;
+    float tc_unscale = 1.f;
 };
+
+// conditional verifier pair (hey_jarvis, docs/models/hey_jarvis.md:38): score column `main_col` is replaced by column
+// `ver_col` wherever it exceeds `thr`
+struct Gate { int main_col, ver_col; float thr; };
+
+// Ring row counters (rows ever written; ring slot = count & (rows-1)) would overflow int32 after ~248 days of
+// continuous streaming at 100 mel rows/s.  Past 2^30 they are rebased by a multiple of every ring size (rings are
+// powers of two <= 2^20 rows), which keeps the slot and leaves the count >= the ring size, so "row not yet written"
+// tests (count - k >= 0) stay true.
+#define OWW_COUNT_WRAP (1 << 30)
+#define OWW_COUNT_REBASE ((1 << 30) - (1 << 20))
+#ifdef __CUDACC__
+__device__ __forceinline__ int oww_wrap_count(int c) { return c >= OWW_COUNT_WRAP ? c - OWW_COUNT_REBASE : c; }
+#endif
 
 // device-side description of one head (heads.cu launches, and the fused step kernel reads an array of these)
 struct HeadDev {
@@ -84,6 +103,10 @@ struct oww_ctx {
     std::vector<Head> heads;
     int n_out_total = 0;
     int max_n_in = 0;
+    std::vector<Gate> gates;         // applied to every chunk's scores before the max over chunks
+    Gate* d_gates = nullptr;
+    float* d_scores_tmp = nullptr;   // [n_streams][n_out_total]: one chunk's raw scores when gates meet a multi-chunk call
+    size_t scores_tmp_floats = 0;
 
     // streaming state
     int n_streams = 0;
@@ -115,7 +138,17 @@ struct oww_ctx {
     void* d_inc_w = nullptr;         // packed per-layer {fp16 weights, scale, bias}
     void* d_inc_tails[2] = {nullptr, nullptr};   // [n_groups][tail_units] 16-byte units, double-buffered per step
     int inc_cur = 0;                 // tails buffer the next step reads
-    bool inc_primed = false;         // tails describe the newest window of every stream
+    // Priming: a stream is primed when its tails describe its newest window, so the next chunk can take the incremental
+    // path.  A reset un-primes the stream (its next window shifts by 5 rows, not 8 - SURVEY.md F8); the next step
+    // re-primes exactly those streams from a full window while the primed ones go through the fused kernel.
+    std::vector<uint8_t> primed;     // host mirror, [n_streams]
+    int n_unprimed = 0;
+    uint8_t* d_primed = nullptr;     // [n_streams]
+    int* d_unprimed_ids = nullptr;   // [n_streams] compacted list, uploaded by the step that consumes it
+    int* d_reset_ids = nullptr;      // [n_streams] staging for oww_reset / oww_reset_async
+    float* d_reset_init = nullptr;   // [feat_rows][96]
+    cudaStream_t side_stream = nullptr;          // re-prime chain of a partially primed step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     IncPlan inc_plan;
     void* d_inc_dbg = nullptr;
     HeadDev* d_head_devs = nullptr;  // device copy of the head descriptors (fused step kernel)
@@ -139,6 +172,13 @@ struct oww_ctx {
     std::vector<uint8_t> ev_fused;          // per timing slot: the step was one fused launch (only ev[1], ev[2] recorded)
     int ev_slots = 0;
     long ev_steps = 0;               // timed steps recorded since timing was enabled
+
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remembered per handle
+    bool heads_attr_set = false;
+    bool heads_tc_attr_set = false;
+    uint32_t tc_attr_mask = 0;
+    bool tc_heads = true;            // modes 2/3: first head layer on tensor cores when the head allows it (reserved[0] bit 1 disables)
+    int tc_heads_terms = 3;          // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = plain fp16 operands
 
     // private stream set for oww_predict_clips
     oww_ctx* clip_ctx = nullptr;
@@ -172,6 +212,7 @@ struct MelLaunch {
     float* out; int64_t out_stride; int out_rows_mask;   // ring: mask = rows-1 ; linear: mask = -1
     int* out_count;                // ring row counters or nullptr
     int n_clips; int affine; int n_chunks;
+    const int* ids = nullptr;      // streaming only: clip j is stream ids[j] (body / tail / seen / ring rows of that stream)
 };
 int oww_mel_launch(oww_ctx* ctx, const MelLaunch& p, cudaStream_t s);
 
@@ -184,10 +225,12 @@ struct WindowSrc {
     const float* base; int64_t stride;  // per-window (or per-stream) stride in floats
     const int* count; int rows_mask;    // ring addressing (count==nullptr -> linear)
     int n_streams; int n_chunks;
+    const int* ids = nullptr;           // ring addressing of a stream subset: local stream b is stream ids[b]
 };
 // Fully-convolutional pass over linear mel [n][T][32] -> [n][(T-76)/8+1][96].
 int oww_cnn_clip_fp32(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s);
-int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s);
+// appends n_chunks embedding rows per stream; ids != nullptr: only the n_ids streams listed (d_emb rows are compact)
+int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t s, const int* d_ids = nullptr, int n_ids = 0);
 // mode dispatch (fp32 window / tcgen05 window) with sub-batching over ctx->window_batch
 int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_emb, cudaStream_t s, bool capture_tails = false);
 
@@ -197,7 +240,7 @@ size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows);
 int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
 // fp32 pyramid with an optional early stop that leaves NHWC fp32 [n][T][W][C] of `stop_layer` in d_dbg
 // capture descriptor: which local windows of a full-window pass are the newest window of which streams
-struct TailCapture { int win0, n_win, stream0; };
+struct TailCapture { int win0, n_win, stream0; const int* ids = nullptr; };   // ids: local stream -> stream id
 int oww_cnn_tc_pyramid_cap(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, const TailCapture* cap, cudaStream_t s);
 
 // ---- cnn_tc_inc.cu ----
@@ -206,11 +249,13 @@ int oww_inc_setup(oww_ctx* ctx, const float* h_blob);
 int oww_inc_alloc_streams(oww_ctx* ctx);
 int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s);
 // whole step in one launch (n_chunks == 1, primed): PCM -> mel -> CNN -> ring append -> heads -> scores
-bool oww_fused_step_supported(const oww_ctx* ctx);
-int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, cudaStream_t s);
+bool oww_fused_frontend_supported(const oww_ctx* ctx);
+bool oww_fused_heads_supported(const oww_ctx* ctx);
+int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, bool with_heads,
+                   const uint8_t* d_primed, cudaStream_t s);
 int oww_heads_sync_devs(oww_ctx* ctx);
 int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
-                    int stream0, cudaStream_t s);
+                    int stream0, const int* d_ids, cudaStream_t s);
 int oww_cnn_fp32_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
 
 // ---- heads.cu ----
@@ -218,6 +263,18 @@ struct FeatSrc {
     const float* base; int64_t stride;   // per-sample stride in floats
     const int* count; int rows_mask;     // ring addressing (nullptr -> linear [n][n_in][96])
     int back;                            // ring: window ends `back` rows before the newest
+    // sliding mode (count == nullptr, steps > 0; bulk clips): sample s = clip * steps + st reads rows
+    // [row0 + st + 1 - n_in, row0 + st] of clip's linear rows at base + clip * stride (negative rows read as zeros)
+    int steps = 0, row0 = 0;
 };
+// head_id < 0: every head whose bit is set in head_mask (blockIdx.y walks the selected heads)
 int oww_heads_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float* d_out, int out_stride,
-                     int out_col0, int combine_max, cudaStream_t s);
+                     int out_col0, int combine_max, cudaStream_t s, uint32_t head_mask = 0xFFFFFFFFu);
+
+// ---- heads_tc.cu: first layer on tcgen05 (fp16 hi/lo split operands, fp32 accumulate) ----
+int oww_heads_tc_pack(oww_ctx* ctx, Head& h, const float* w1);
+bool oww_heads_tc_supported(const oww_ctx* ctx, int head_id);
+int oww_heads_tc_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float* d_out, int out_stride,
+                        int out_col0, int combine_max, cudaStream_t s, uint32_t head_mask = 0xFFFFFFFFu);
+// every head (tensor-core kernel where a head allows it, heads.cu otherwise) + the verifier gates
+int oww_heads_all(oww_ctx* ctx, const FeatSrc& src, int n, float* d_out, int out_stride, int combine_max, cudaStream_t s);

@@ -92,14 +92,28 @@ class Model:
                 if not os.path.exists(src):
                     raise ValueError(f"Model file '{src}' not found (the reference's released heads are download-only)")
                 head, file_map = _load_head_file(src)
-            n_in, dims, ln, fin = _weights.head_desc(head)
-            hid = ctx.add_head(n_in, dims, ln, fin, _weights.pack_head_blob(head))
+            if _weights.is_gated(head):
+                # conditional verifier pair (the released hey_jarvis graph): two networks on the device, the verifier's
+                # score replacing the main one's above the threshold inside the step; its own column stays hidden
+                n_in, dims, ln, fin = _weights.head_desc(head["main"])
+                hid = ctx.add_head(n_in, dims, ln, fin, _weights.pack_head_blob(head["main"]))
+                v_in, v_dims, v_ln, v_fin = _weights.head_desc(head["verifier"])
+                if v_in != n_in or dims[-1] != 1 or v_dims[-1] != 1:
+                    raise ValueError(f"model '{name}': a verifier pair needs two single-output networks on the same input")
+                vid = ctx.add_head(v_in, v_dims, v_ln, v_fin, _weights.pack_head_blob(head["verifier"]))
+                ctx.add_gate(hid, vid, head["threshold"])
+                self.model_prediction_function[name] = partial(self._gated_predict, hid, vid, n_in, head["threshold"])
+                width = 2
+            else:
+                n_in, dims, ln, fin = _weights.head_desc(head)
+                hid = ctx.add_head(n_in, dims, ln, fin, _weights.pack_head_blob(head))
+                self.model_prediction_function[name] = partial(self._head_predict, hid, n_in, dims[-1])
+                width = dims[-1]
             self.models[name] = hid
             self.model_inputs[name] = n_in
             self.model_outputs[name] = dims[-1]
-            self.model_prediction_function[name] = partial(self._head_predict, hid, n_in, dims[-1])
             self._columns[name] = (col, dims[-1])
-            col += dims[-1]
+            col += width
             if class_mapping_dicts and ndx < len(class_mapping_dicts) and class_mapping_dicts[ndx].get(name, None):
                 self.class_mapping[name] = class_mapping_dicts[ndx]
             elif _registry.model_class_mappings.get(name, None):
@@ -170,6 +184,11 @@ class Model:
         out = torch.empty((x.shape[0], n_out), dtype=torch.float32, device=dev)
         self.preprocessor.ctx.head_predict(hid, d, x.shape[0], out, torch.cuda.current_stream(d.device).cuda_stream)
         return [out.cpu().numpy()]
+
+    def _gated_predict(self, hid, vid, n_in, thr, x):
+        p1 = self._head_predict(hid, n_in, 1, x)[0]
+        p2 = self._head_predict(vid, n_in, 1, x)[0]
+        return [np.where(p1 > np.float32(thr), p2, p1).astype(np.float32)]
 
     def _suppress_noise_with_speex(self, x, frame_size=160):
         cleaned = [self.speex_ns.process(x[i:i + frame_size].tobytes()) for i in range(0, x.shape[0], frame_size)]

@@ -186,7 +186,159 @@ def parse_onnx(path):
 
 
 # ------------------------------------------------------------------ heads
+_PASS = ("Identity", "Cast", "Reshape", "Flatten", "Squeeze", "Unsqueeze", "Dropout")
+
+
+class _Graph:
+    """Producer map + helpers to walk a head graph backwards from its output."""
+
+    def __init__(self, path, g):
+        self.path, self.init, self.nodes = path, g["initializers"], g["nodes"]
+        self.prod = {}
+        for nd in self.nodes:
+            for o in nd["out"]:
+                self.prod[o] = nd
+        self.input = g["inputs"][0][0]
+
+    def fail(self, msg):
+        raise ValueError(f"{self.path}: {msg}")
+
+    def const(self, name):
+        return self.init.get(name)
+
+    def producer(self, name):
+        if name == self.input:
+            return None
+        if name not in self.prod:
+            self.fail(f"tensor '{name}' has no producer")
+        return self.prod[name]
+
+    def data_inputs(self, nd):
+        return [i for i in nd["in"] if i and self.const(i) is None]
+
+
+def _walk_layernorm_decomposed(G, add_beta):
+    """Add(beta) <- Mul(gamma) <- Div(c, sqrt(var+eps)) ; c = Sub(x, ReduceMean(x)).  Returns (x, gamma, beta)."""
+    beta = next((G.const(i) for i in add_beta["in"] if G.const(i) is not None), None)
+    mul = G.producer(G.data_inputs(add_beta)[0])
+    if mul is None or mul["op"] != "Mul":
+        return None
+    gamma = next((G.const(i) for i in mul["in"] if G.const(i) is not None), None)
+    div = G.producer(G.data_inputs(mul)[0]) if G.data_inputs(mul) else None
+    if div is None or div["op"] != "Div" or gamma is None or beta is None or gamma.size < 2:
+        return None
+    sub = G.producer(div["in"][0])
+    sq = G.producer(div["in"][1])
+    if sub is None or sub["op"] != "Sub" or sq is None or sq["op"] != "Sqrt":
+        G.fail("unrecognised LayerNorm decomposition")
+    add_eps = G.producer(sq["in"][0])
+    eps = next((G.const(i) for i in add_eps["in"] if G.const(i) is not None), None) if add_eps and add_eps["op"] == "Add" else None
+    if eps is None or abs(float(np.asarray(eps).ravel()[0]) - 1e-5) > 1e-7:
+        G.fail("LayerNorm epsilon must be 1e-5")
+    rm = G.producer(sub["in"][1])
+    if rm is None or rm["op"] != "ReduceMean" or rm["in"][0] != sub["in"][0]:
+        G.fail("unrecognised LayerNorm decomposition (mean)")
+    return sub["in"][0], gamma.astype(np.float32).ravel(), beta.astype(np.float32).ravel()
+
+
+def _walk_branch(G, name):
+    """Walk one DNN branch backwards from tensor `name` to the graph input, enforcing the op ORDER of the reference's
+    family (train.py:56-83): Flatten, then (Linear [LayerNorm] Relu)*, Linear, then one of {nothing, Sigmoid, Relu,
+    Softmax, Relu+Softmax}.  Returns a head dict."""
+    ops = []                       # reversed list of ("linear", W, b) | ("ln", g, b) | ("relu",) | ("sigmoid",) | ("softmax",)
+    cur = name
+    while True:
+        nd = G.producer(cur)
+        if nd is None:
+            break
+        op = nd["op"]
+        if op in _PASS:
+            cur = G.data_inputs(nd)[0]
+        elif op == "Relu":
+            ops.append(("relu",)); cur = nd["in"][0]
+        elif op == "Sigmoid":
+            ops.append(("sigmoid",)); cur = nd["in"][0]
+        elif op == "Softmax":
+            ops.append(("softmax",)); cur = nd["in"][0]
+        elif op == "Gemm":
+            Wm = G.const(nd["in"][1])
+            b = G.const(nd["in"][2]) if len(nd["in"]) > 2 else None
+            if Wm is None:
+                G.fail("Gemm without constant weights")
+            if nd["attrs"].get("transA", 0):
+                G.fail("Gemm transA not supported")
+            if nd["attrs"].get("transB", 0):
+                Wm = Wm.T
+            if nd["attrs"].get("alpha", 1.0) != 1.0 or nd["attrs"].get("beta", 1.0) != 1.0:
+                G.fail("Gemm alpha/beta != 1 not supported")
+            ops.append(("linear", np.ascontiguousarray(Wm, np.float32),
+                        np.zeros(Wm.shape[1], np.float32) if b is None else b.astype(np.float32).ravel()))
+            cur = nd["in"][0]
+        elif op == "Add":
+            ln = _walk_layernorm_decomposed(G, nd)
+            if ln is not None:
+                cur = ln[0]; ops.append(("ln", ln[1], ln[2]))
+                continue
+            c = next((G.const(i) for i in nd["in"] if G.const(i) is not None), None)
+            mm = G.producer(G.data_inputs(nd)[0]) if len(G.data_inputs(nd)) == 1 else None
+            if c is None or mm is None or mm["op"] != "MatMul" or G.const(mm["in"][1]) is None:
+                G.fail("Add that is neither a Linear bias nor a LayerNorm shift")
+            Wm = G.const(mm["in"][1])
+            ops.append(("linear", np.ascontiguousarray(Wm, np.float32), c.astype(np.float32).ravel()))
+            cur = mm["in"][0]
+        elif op == "MatMul":
+            Wm = G.const(nd["in"][1])
+            if Wm is None:
+                G.fail("MatMul without constant weights")
+            ops.append(("linear", np.ascontiguousarray(Wm, np.float32), np.zeros(Wm.shape[1], np.float32)))
+            cur = nd["in"][0]
+        elif op == "LayerNormalization":
+            gm = G.const(nd["in"][1])
+            bt = G.const(nd["in"][2]) if len(nd["in"]) > 2 else None
+            if gm is None:
+                G.fail("LayerNormalization without constant scale")
+            if abs(nd["attrs"].get("epsilon", 1e-5) - 1e-5) > 1e-7:
+                G.fail("LayerNorm epsilon must be 1e-5")
+            ops.append(("ln", gm.astype(np.float32).ravel(),
+                        np.zeros(gm.size, np.float32) if bt is None else bt.astype(np.float32).ravel()))
+            cur = nd["in"][0]
+        else:
+            G.fail(f"op '{op}' is outside the DNN head family the b200 backend implements")
+    ops.reverse()
+    # ---- grammar check on the forward op sequence ----
+    i, layers = 0, []
+    while i < len(ops):
+        if ops[i][0] != "linear":
+            break
+        lay = {"W": ops[i][1], "b": ops[i][2], "ln": None}
+        i += 1
+        if i < len(ops) and ops[i][0] == "ln" and i + 1 < len(ops) and ops[i + 1][0] == "relu" and \
+                any(o[0] == "linear" for o in ops[i + 2:]):
+            lay["ln"] = (ops[i][1], ops[i][2]); i += 2
+        elif i < len(ops) and ops[i][0] == "relu" and any(o[0] == "linear" for o in ops[i + 1:]):
+            i += 1
+        layers.append(lay)
+    tail = tuple(o[0] for o in ops[i:])
+    finals = {(): "none", ("sigmoid",): "sigmoid", ("relu",): "relu", ("softmax",): "softmax", ("relu", "softmax"): "relu_softmax"}
+    if not layers:
+        G.fail("no Linear layers found")
+    if tail not in finals:
+        G.fail(f"op order {[o[0] for o in ops]} is not Linear [LayerNorm] Relu ... Linear (Sigmoid | Relu | [Relu] Softmax)")
+    for a, b in zip(layers[:-1], layers[1:]):
+        if a["W"].shape[1] != b["W"].shape[0]:
+            G.fail("Linear layer shapes do not chain")
+    for lay in layers[:-1]:
+        if lay["ln"] is not None and lay["ln"][0].size != lay["W"].shape[1]:
+            G.fail("LayerNorm width does not match its Linear layer")
+    if any(l["ln"] is not None for l in layers[:-1]) and any(l["ln"] is None for l in layers[:-1]):
+        G.fail("LayerNorm on only some hidden layers is not supported")
+    return {"layers": layers, "final": finals[tail]}
+
+
 def head_from_onnx(path):
+    """-> head dict, or a gated pair {"main", "verifier", "threshold"} for graphs of the released hey_jarvis structure:
+    two parallel DNN branches p1, p2 on the same input joined by  Where(Greater(p1, t), p2, p1)  (or the equivalent
+    Where(LessOrEqual/Less(p1, t) | Not(Greater), p1, p2)): docs/models/hey_jarvis.md:9,38."""
     g = parse_onnx(path)
     if len(g["inputs"]) != 1:
         raise ValueError(f"{path}: expected one graph input, found {len(g['inputs'])}")
@@ -194,69 +346,44 @@ def head_from_onnx(path):
     if len(shape) != 3 or shape[2] != 96 or not shape[1]:
         raise ValueError(f"{path}: head input must be [batch, n_frames, 96], found {shape}")
     n_in = int(shape[1])
-    init = g["initializers"]
-    layers, ln_seen, relu_before_softmax, final = [], False, False, "none"
-    pending_ln = {}
-    allowed = {"Flatten", "Gemm", "MatMul", "Add", "Relu", "Sigmoid", "Softmax", "LayerNormalization", "ReduceMean", "Sub",
-               "Pow", "Sqrt", "Div", "Mul", "Constant", "Reshape", "Identity", "Cast", "Shape", "Gather", "Unsqueeze", "Concat"}
-    nodes = g["nodes"]
-    for idx, nd in enumerate(nodes):
-        op = nd["op"]
-        if op not in allowed:
-            raise ValueError(f"{path}: op '{op}' is outside the DNN head family the b200 backend implements")
-        if op == "Gemm":
-            Wm, b = init.get(nd["in"][1]), init.get(nd["in"][2]) if len(nd["in"]) > 2 else None
-            if Wm is None:
-                raise ValueError(f"{path}: Gemm without constant weights")
-            if nd["attrs"].get("transB", 0):
-                Wm = Wm.T
-            if nd["attrs"].get("alpha", 1.0) != 1.0 or nd["attrs"].get("beta", 1.0) != 1.0:
-                raise ValueError(f"{path}: Gemm alpha/beta != 1 not supported")
-            layers.append({"W": np.ascontiguousarray(Wm, np.float32),
-                           "b": np.zeros(Wm.shape[1], np.float32) if b is None else b.astype(np.float32), "ln": None})
-        elif op == "MatMul":
-            Wm = init.get(nd["in"][1])
-            if Wm is None:
-                raise ValueError(f"{path}: MatMul without constant weights")
-            layers.append({"W": np.ascontiguousarray(Wm, np.float32), "b": np.zeros(Wm.shape[1], np.float32), "ln": None})
-            pending_ln["bias_for"] = nd["out"][0]
-        elif op == "Add":
-            c = init.get(nd["in"][1]) if nd["in"][1] in init else init.get(nd["in"][0])
-            if c is None:
-                continue
-            if pending_ln.get("bias_for") in nd["in"]:
-                layers[-1]["b"] = c.astype(np.float32).ravel(); pending_ln.pop("bias_for")
-            elif pending_ln.get("scaled") in nd["in"]:           # decomposed LayerNorm: ... Mul(gamma) -> Add(beta)
-                layers[-1]["ln"] = (pending_ln.pop("gamma"), c.astype(np.float32).ravel()); pending_ln.pop("scaled")
-                ln_seen = True
-            # else: the epsilon add of the decomposed LayerNorm (scalar)
-        elif op == "Mul":
-            c = init.get(nd["in"][1]) if nd["in"][1] in init else init.get(nd["in"][0])
-            if c is not None and c.size > 1:
-                pending_ln["gamma"] = c.astype(np.float32).ravel(); pending_ln["scaled"] = nd["out"][0]
-        elif op == "LayerNormalization":
-            gm, bt = init.get(nd["in"][1]), init.get(nd["in"][2]) if len(nd["in"]) > 2 else None
-            if gm is None:
-                raise ValueError(f"{path}: LayerNormalization without constant scale")
-            eps = nd["attrs"].get("epsilon", 1e-5)
-            if abs(eps - 1e-5) > 1e-7:
-                raise ValueError(f"{path}: LayerNorm epsilon {eps} != 1e-5")
-            layers[-1]["ln"] = (gm.astype(np.float32), np.zeros_like(gm, np.float32) if bt is None else bt.astype(np.float32))
-            ln_seen = True
-        elif op == "Sigmoid":
-            final = "sigmoid"
-        elif op == "Softmax":
-            final = "relu_softmax" if (idx > 0 and nodes[idx - 1]["op"] == "Relu") else "softmax"
-    if not layers:
-        raise ValueError(f"{path}: no Linear layers found")
-    if final == "relu_softmax" or final == "softmax":
-        pass
-    if layers[0]["W"].shape[0] != n_in * 96:
-        raise ValueError(f"{path}: first Linear takes {layers[0]['W'].shape[0]} inputs, expected {n_in * 96}")
-    if ln_seen and any(l["ln"] is None for l in layers[:-1]):
-        raise ValueError(f"{path}: LayerNorm on only some hidden layers is not supported")
-    layers[-1]["ln"] = None
-    return {"n_in": n_in, "layers": layers, "final": final}
+    if len(g["outputs"]) != 1:
+        raise ValueError(f"{path}: expected one graph output, found {len(g['outputs'])}")
+    G = _Graph(path, g)
+    out = g["outputs"][0][0]
+    nd = G.producer(out)
+    while nd is not None and nd["op"] in _PASS:
+        out = G.data_inputs(nd)[0]; nd = G.producer(out)
+
+    def finish(h):
+        if h["layers"][0]["W"].shape[0] != n_in * 96:
+            raise ValueError(f"{path}: first Linear takes {h['layers'][0]['W'].shape[0]} inputs, expected {n_in * 96}")
+        h["n_in"] = n_in
+        return h
+
+    if nd is not None and nd["op"] == "Where":
+        cond = G.producer(nd["in"][0])
+        neg = False
+        while cond is not None and cond["op"] == "Not":
+            neg = not neg; cond = G.producer(cond["in"][0])
+        if cond is None or cond["op"] not in ("Greater", "GreaterOrEqual", "Less", "LessOrEqual"):
+            G.fail("Where without a score comparison: not the conditional-verifier structure")
+        thr = G.const(cond["in"][1])
+        if thr is None:
+            G.fail("the gate compares against a non-constant")
+        p_cmp = cond["in"][0]
+        greater = cond["op"] in ("Greater", "GreaterOrEqual")
+        if neg:
+            greater = not greater
+        x_true, x_false = nd["in"][1], nd["in"][2]
+        main_t, ver_t = (x_false, x_true) if greater else (x_true, x_false)
+        if main_t != p_cmp:
+            G.fail("the gate must compare the main network's own score")
+        main, ver = finish(_walk_branch(G, main_t)), finish(_walk_branch(G, ver_t))
+        for h in (main, ver):
+            if h["layers"][-1]["W"].shape[1] != 1:
+                G.fail("gated networks must be single-output")
+        return {"main": main, "verifier": ver, "threshold": float(np.asarray(thr).ravel()[0]), "n_in": n_in}
+    return finish(_walk_branch(G, out))
 
 
 def embedding_from_onnx(path):
@@ -319,52 +446,68 @@ def _model(graph_body, opset):
     return _vi(1, 8) + _ld(8, _ld(1, b"") + _vi(2, opset)) + _ld(7, graph_body)
 
 
-def write_head_onnx(path, head, fused_layernorm=False, use_matmul=False):
-    """torch.onnx.export-shaped graph of a head dict (opset 13 decomposed LayerNorm by default)."""
-    body, x = b"", "flat"
+def _head_body(head, fused_layernorm, use_matmul, pre, out_name):
+    """Nodes + initialisers of one DNN branch reading the graph input; tensor names carry the prefix `pre`."""
+    body, x = b"", pre + "flat"
     body += _node("Flatten", ["onnx::Flatten_0"], [x], axis=1)
     L = head["layers"]
     for i, lay in enumerate(L):
         W, b = np.asarray(lay["W"], np.float32), np.asarray(lay["b"], np.float32)
         if use_matmul:
-            body += _ld(5, _tensor_proto(f"W{i}", W)) + _ld(5, _tensor_proto(f"b{i}", b))
-            body += _node("MatMul", [x, f"W{i}"], [f"mm{i}"]) + _node("Add", [f"mm{i}", f"b{i}"], [f"lin{i}"])
+            body += _ld(5, _tensor_proto(f"{pre}W{i}", W)) + _ld(5, _tensor_proto(f"{pre}b{i}", b))
+            body += _node("MatMul", [x, f"{pre}W{i}"], [f"{pre}mm{i}"]) + _node("Add", [f"{pre}mm{i}", f"{pre}b{i}"], [f"{pre}lin{i}"])
         else:
-            body += _ld(5, _tensor_proto(f"W{i}", np.ascontiguousarray(W.T))) + _ld(5, _tensor_proto(f"b{i}", b))
-            body += _node("Gemm", [x, f"W{i}", f"b{i}"], [f"lin{i}"], alpha=1.0, beta=1.0, transB=1)
-        x = f"lin{i}"
+            body += _ld(5, _tensor_proto(f"{pre}W{i}", np.ascontiguousarray(W.T))) + _ld(5, _tensor_proto(f"{pre}b{i}", b))
+            body += _node("Gemm", [x, f"{pre}W{i}", f"{pre}b{i}"], [f"{pre}lin{i}"], alpha=1.0, beta=1.0, transB=1)
+        x = f"{pre}lin{i}"
         if i == len(L) - 1:
             break
         if lay.get("ln") is not None:
             g_, h_ = lay["ln"]
-            body += _ld(5, _tensor_proto(f"g{i}", np.asarray(g_, np.float32))) + _ld(5, _tensor_proto(f"h{i}", np.asarray(h_, np.float32)))
+            body += _ld(5, _tensor_proto(f"{pre}g{i}", np.asarray(g_, np.float32))) + _ld(5, _tensor_proto(f"{pre}h{i}", np.asarray(h_, np.float32)))
             if fused_layernorm:
-                body += _node("LayerNormalization", [x, f"g{i}", f"h{i}"], [f"ln{i}"], axis=-1, epsilon=1e-5)
+                body += _node("LayerNormalization", [x, f"{pre}g{i}", f"{pre}h{i}"], [f"{pre}ln{i}"], axis=-1, epsilon=1e-5)
             else:
-                body += _ld(5, _tensor_proto(f"two{i}", np.asarray(2.0, np.float32))) + _ld(5, _tensor_proto(f"eps{i}", np.asarray(1e-5, np.float32)))
-                body += _node("ReduceMean", [x], [f"mu{i}"], axes=[-1])
-                body += _node("Sub", [x, f"mu{i}"], [f"c{i}"])
-                body += _node("Pow", [f"c{i}", f"two{i}"], [f"sq{i}"])
-                body += _node("ReduceMean", [f"sq{i}"], [f"var{i}"], axes=[-1])
-                body += _node("Add", [f"var{i}", f"eps{i}"], [f"ve{i}"])
-                body += _node("Sqrt", [f"ve{i}"], [f"sd{i}"])
-                body += _node("Div", [f"c{i}", f"sd{i}"], [f"nrm{i}"])
-                body += _node("Mul", [f"nrm{i}", f"g{i}"], [f"sc{i}"])
-                body += _node("Add", [f"sc{i}", f"h{i}"], [f"ln{i}"])
-            x = f"ln{i}"
-        body += _node("Relu", [x], [f"act{i}"])
-        x = f"act{i}"
+                body += _ld(5, _tensor_proto(f"{pre}two{i}", np.asarray(2.0, np.float32))) + _ld(5, _tensor_proto(f"{pre}eps{i}", np.asarray(1e-5, np.float32)))
+                body += _node("ReduceMean", [x], [f"{pre}mu{i}"], axes=[-1])
+                body += _node("Sub", [x, f"{pre}mu{i}"], [f"{pre}c{i}"])
+                body += _node("Pow", [f"{pre}c{i}", f"{pre}two{i}"], [f"{pre}sq{i}"])
+                body += _node("ReduceMean", [f"{pre}sq{i}"], [f"{pre}var{i}"], axes=[-1])
+                body += _node("Add", [f"{pre}var{i}", f"{pre}eps{i}"], [f"{pre}ve{i}"])
+                body += _node("Sqrt", [f"{pre}ve{i}"], [f"{pre}sd{i}"])
+                body += _node("Div", [f"{pre}c{i}", f"{pre}sd{i}"], [f"{pre}nrm{i}"])
+                body += _node("Mul", [f"{pre}nrm{i}", f"{pre}g{i}"], [f"{pre}sc{i}"])
+                body += _node("Add", [f"{pre}sc{i}", f"{pre}h{i}"], [f"{pre}ln{i}"])
+            x = f"{pre}ln{i}"
+        body += _node("Relu", [x], [f"{pre}act{i}"])
+        x = f"{pre}act{i}"
     fin = head["final"]
     if fin == "sigmoid":
-        body += _node("Sigmoid", [x], ["out"])
+        body += _node("Sigmoid", [x], [out_name])
     elif fin == "relu_softmax":
-        body += _node("Relu", [x], ["pre"]) + _node("Softmax", ["pre"], ["out"], axis=1)
+        body += _node("Relu", [x], [pre + "pre"]) + _node("Softmax", [pre + "pre"], [out_name], axis=1)
     elif fin == "softmax":
-        body += _node("Softmax", [x], ["out"], axis=1)
+        body += _node("Softmax", [x], [out_name], axis=1)
+    elif fin == "relu":
+        body += _node("Relu", [x], [out_name])
     else:
-        body += _node("Identity", [x], ["out"])
-    n_out = L[-1]["W"].shape[1]
-    body += _ld(2, b"head") + _vinfo(11, "onnx::Flatten_0", [1, head["n_in"], 96]) + _vinfo(12, "out", [1, n_out])
+        body += _node("Identity", [x], [out_name])
+    return body
+
+
+def write_head_onnx(path, head, fused_layernorm=False, use_matmul=False):
+    """torch.onnx.export-shaped graph of a head dict (opset 13 decomposed LayerNorm by default).  A gated pair is
+    written as two branches joined by Greater + Where (the conditional-verifier structure of hey_jarvis)."""
+    if "verifier" in head:
+        body = _head_body(head["main"], fused_layernorm, use_matmul, "m_", "p_main")
+        body += _head_body(head["verifier"], fused_layernorm, use_matmul, "v_", "p_ver")
+        body += _ld(5, _tensor_proto("gate_thr", np.asarray(head["threshold"], np.float32)))
+        body += _node("Greater", ["p_main", "gate_thr"], ["gate"]) + _node("Where", ["gate", "p_ver", "p_main"], ["out"])
+        n_in, n_out = head["main"]["n_in"], 1
+    else:
+        body = _head_body(head, fused_layernorm, use_matmul, "", "out")
+        n_in, n_out = head["n_in"], head["layers"][-1]["W"].shape[1]
+    body += _ld(2, b"head") + _vinfo(11, "onnx::Flatten_0", [1, n_in, 96]) + _vinfo(12, "out", [1, n_out])
     open(path, "wb").write(_model(body, 17 if fused_layernorm else 13))
 
 

@@ -73,7 +73,7 @@ class AudioFeatures:
 
     def __init__(self, melspec_model_path="", embedding_model_path="", sr=16000, ncpu=1,
                  inference_framework="b200", device="gpu", n_streams=1, feature_init=None,
-                 max_chunks=8, cnn_mode=_native.CNN_FP32_WINDOW, window_batch=0, device_index=0):
+                 max_chunks=8, cnn_mode=_native.CNN_TC_INCREMENTAL, window_batch=0, device_index=0):
         if inference_framework != "b200":
             raise ValueError(f"openwakeword_b200 only provides inference_framework='b200' (got '{inference_framework}')")
         if sr != 16000:
@@ -90,6 +90,7 @@ class AudioFeatures:
         self.embedding_weights = load_embedding_weights(embedding_model_path)
         self.ctx.load_embedding(_weights.pack_embedding_blob(self.embedding_weights))
         self.n_streams = int(n_streams)
+        self.cnn_mode = cnn_mode
         self.max_chunks = max_chunks
         self.device_index = device_index
         self.onnx_execution_provider = "B200ExecutionProvider"
@@ -235,11 +236,20 @@ class AudioFeatures:
             self.accumulated_samples = total
             return total, 0
         n_chunks = ready.shape[1] // CHUNK
-        if n_chunks > self.max_chunks:
-            raise ValueError(f"{ready.shape[1]} samples in one call exceeds max_chunks={self.max_chunks}*1280")
         if scores_out is None:
             scores_out = np.empty((self.n_streams, max(self.ctx.n_outputs, 1)), np.float32)
-        self.ctx.step_host(np.ascontiguousarray(ready), n_chunks, scores_out)
+        if n_chunks <= self.max_chunks:
+            self.ctx.step_host(np.ascontiguousarray(ready), n_chunks, scores_out)
+        else:
+            # a call longer than max_chunks*1280 samples (the reference accepts up to its 10 s raw buffer) runs as
+            # several device calls of <= max_chunks chunks; per head the result is the max over all chunk windows, as in
+            # model.py:287-298.  Only the scope of the mel graph's -80 dB clamp differs (per device call, not per host call).
+            part = np.empty_like(scores_out)
+            for k, c0 in enumerate(range(0, n_chunks, self.max_chunks)):
+                c1 = min(c0 + self.max_chunks, n_chunks)
+                self.ctx.step_host(np.ascontiguousarray(ready[:, c0 * CHUNK:c1 * CHUNK]), c1 - c0, scores_out if k == 0 else part)
+                if k:
+                    np.maximum(scores_out, part, out=scores_out)
         self.accumulated_samples = 0
         self._last_scores = scores_out
         return ready.shape[1], n_chunks
@@ -251,19 +261,24 @@ class AudioFeatures:
         """utils.py:454-460 on the device ring -> float32 [1,n,96]."""
         self._ensure_streams()
         n = int(n_feature_frames)
-        if start_ndx != -1:
-            if start_ndx >= 0:
-                raise ValueError("only negative start_ndx (relative to the newest row) is supported on the device ring")
-            back = -start_ndx - n
-            if back < 0:
-                n, back = -start_ndx, 0
-            return self.ctx.get_features(stream, n, back)[None]
-        return self.ctx.get_features(stream, n, 0)[None]
+        if start_ndx == -1:
+            return self.ctx.get_features(stream, n, 0)[None]
+        # feature_buffer[start_ndx:end_ndx] of the reference: its buffer holds the last min(rows written, 120) rows
+        length = self._feature_len(stream)
+        end = start_ndx + n if start_ndx + n != 0 else length
+        lo, hi, _ = slice(start_ndx, end).indices(length)
+        if hi <= lo:
+            return np.zeros((1, 0, 96), np.float32)
+        return self.ctx.get_features(stream, hi - lo, length - hi)[None]
+
+    def _feature_len(self, stream=0):
+        return min(self.ctx.get_counts(stream)[1], self.feature_buffer_max_len)
 
     @property
     def feature_buffer(self):
+        """[rows, 96]: the stream-0 buffer as the reference keeps it (at most 120 rows, utils.py:449-450)."""
         self._ensure_streams()
-        return self.ctx.get_features(0, 120, 0)
+        return self.ctx.get_features(0, self._feature_len(0), 0)
 
     @property
     def melspectrogram_buffer(self):

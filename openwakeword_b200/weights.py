@@ -116,7 +116,19 @@ def pack_embedding_blob(weights):
     return np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
 
 
-FINAL_CODES = {"none": 0, "sigmoid": 1, "softmax": 2, "relu_softmax": 3}
+FINAL_CODES = {"none": 0, "sigmoid": 1, "softmax": 2, "relu_softmax": 3, "relu": 4}
+
+
+def is_gated(head):
+    """A conditional verifier pair (the released ``hey_jarvis`` graph, docs/models/hey_jarvis.md:9,38):
+    ``{"main": head, "verifier": head, "threshold": 0.5}`` - the verifier's score replaces the main network's wherever
+    the latter exceeds the threshold."""
+    return isinstance(head, dict) and "verifier" in head
+
+
+def synthetic_gated_head(seed_main=31, seed_verifier=32, threshold=0.5, **kw):
+    return {"main": synthetic_head(seed=seed_main, **kw), "verifier": synthetic_head(seed=seed_verifier, **kw),
+            "threshold": float(threshold), "n_in": int(kw.get("n_in", 16))}
 
 
 def head_desc(head):
@@ -142,12 +154,17 @@ def pack_head_blob(head):
 
 
 def save_head(path, head, class_mapping=None):
-    d = {"n_in": np.int64(head["n_in"]), "final": np.str_(head["final"]),
-         "n_layers": np.int64(len(head["layers"]))}
-    for i, lay in enumerate(head["layers"]):
-        d[f"W{i}"], d[f"b{i}"] = lay["W"], lay["b"]
-        if lay.get("ln") is not None:
-            d[f"g{i}"], d[f"h{i}"] = lay["ln"]
+    d = {}
+    parts = [("", head)] if not is_gated(head) else [("", head["main"]), ("v_", head["verifier"])]
+    if is_gated(head):
+        d["gate_threshold"] = np.float64(head["threshold"])
+    for pre, hd in parts:
+        d[pre + "n_in"] = np.int64(hd["n_in"]); d[pre + "final"] = np.str_(hd["final"])
+        d[pre + "n_layers"] = np.int64(len(hd["layers"]))
+        for i, lay in enumerate(hd["layers"]):
+            d[f"{pre}W{i}"], d[f"{pre}b{i}"] = lay["W"], lay["b"]
+            if lay.get("ln") is not None:
+                d[f"{pre}g{i}"], d[f"{pre}h{i}"] = lay["ln"]
     if class_mapping:
         d["class_keys"] = np.array(list(class_mapping.keys()))
         d["class_vals"] = np.array(list(class_mapping.values()))
@@ -156,11 +173,16 @@ def save_head(path, head, class_mapping=None):
 
 def load_head(path):
     z = np.load(path, allow_pickle=False)
-    layers = []
-    for i in range(int(z["n_layers"])):
-        ln = (z[f"g{i}"], z[f"h{i}"]) if f"g{i}" in z.files else None
-        layers.append({"W": z[f"W{i}"], "b": z[f"b{i}"], "ln": ln})
-    head = {"n_in": int(z["n_in"]), "layers": layers, "final": str(z["final"])}
+
+    def one(pre):
+        layers = []
+        for i in range(int(z[pre + "n_layers"])):
+            ln = (z[f"{pre}g{i}"], z[f"{pre}h{i}"]) if f"{pre}g{i}" in z.files else None
+            layers.append({"W": z[f"{pre}W{i}"], "b": z[f"{pre}b{i}"], "ln": ln})
+        return {"n_in": int(z[pre + "n_in"]), "layers": layers, "final": str(z[pre + "final"])}
+    head = one("")
+    if "gate_threshold" in z.files:
+        head = {"main": head, "verifier": one("v_"), "threshold": float(z["gate_threshold"]), "n_in": head["n_in"]}
     cm = None
     if "class_keys" in z.files:
         cm = {str(k): str(v) for k, v in zip(z["class_keys"], z["class_vals"])}

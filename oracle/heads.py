@@ -14,7 +14,14 @@ LN_EPS = 1e-5
 
 
 def forward(head, feats, dtype=np.float32):
-    """feats [N, n_in, 96] -> [N, n_out]."""
+    """feats [N, n_in, 96] -> [N, n_out].  A gated pair {"main", "verifier", "threshold"} (the released hey_jarvis graph,
+    docs/models/hey_jarvis.md:9,38: the verifier "only predict[s] on audio frames that have a score > 0.5 from the first
+    model", the routing being part of the exported graph) evaluates both networks and takes the verifier's score where
+    the main score exceeds the threshold."""
+    if "verifier" in head:
+        p1 = forward(head["main"], feats, dtype)
+        p2 = forward(head["verifier"], feats, dtype)
+        return np.where(p1 > np.float32(head["threshold"]), p2, p1).astype(np.float32)
     x = np.asarray(feats, dtype=np.float32).reshape(feats.shape[0], -1).astype(dtype)
     L = head["layers"]
     for i, lay in enumerate(L):
@@ -28,7 +35,9 @@ def forward(head, feats, dtype=np.float32):
                 x = (x - mu) / np.sqrt(var + dtype(LN_EPS)) * g.astype(dtype) + b.astype(dtype)
             x = np.maximum(x, 0)
     fin = head["final"]
-    if fin == "sigmoid":
+    if fin == "relu":
+        x = np.maximum(x, 0)
+    elif fin == "sigmoid":
         x = 1.0 / (1.0 + np.exp(-x))
     elif fin in ("relu_softmax", "softmax"):
         if fin == "relu_softmax":

@@ -52,7 +52,8 @@ class InferenceSession:
 
     def get_outputs(self):
         if self.kind == "head":
-            return [_IO("out", [1, self.head["layers"][-1]["W"].shape[1]])]
+            net = self.head["main"] if "verifier" in self.head else self.head
+            return [_IO("out", [1, net["layers"][-1]["W"].shape[1]])]
         return [_IO("output", [])]
 
     def run(self, _names, feed):

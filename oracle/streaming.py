@@ -96,6 +96,11 @@ class OracleAudioFeatures:
         return fb[-int(n):][None].astype(np.float32)
 
 
+def _n_out(h):
+    net = h["main"] if "verifier" in h else h      # gated pair (hey_jarvis structure): one output, the gated score
+    return net["layers"][-1]["W"].shape[1]
+
+
 class OracleModel:
     """heads: ordered {name: head dict}; class_mapping: {name: {"1": label}} for
     multi-class heads (model.py:177-182)."""
@@ -106,7 +111,7 @@ class OracleModel:
         self.dtype = dtype
         self.class_mapping = {}
         for name, h in heads.items():
-            n_out = h["layers"][-1]["W"].shape[1]
+            n_out = _n_out(h)
             if class_mapping and name in class_mapping:
                 self.class_mapping[name] = class_mapping[name]
             else:
@@ -137,7 +142,7 @@ class OracleModel:
         out = {}
         for name, h in self.heads.items():
             n_in = h["n_in"]
-            n_out = h["layers"][-1]["W"].shape[1]
+            n_out = _n_out(h)
             if n > CHUNK:
                 g = [_heads.forward(h, self.preprocessor.get_features(n_in, -n_in - i), self.dtype)[0]
                      for i in range(n // CHUNK - 1, -1, -1)]

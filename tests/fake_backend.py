@@ -40,9 +40,10 @@ def unpack_head_blob(n_in, dims, layernorm, final_act, blob):
 class FakeContext:
     instances = []
 
-    def __init__(self, device=0, max_chunks=4, cnn_mode=0, window_batch=0, fuse_step=True):
+    def __init__(self, device=0, max_chunks=4, cnn_mode=0, window_batch=0, fuse_step=True, **kw):
         self.max_chunks = max_chunks
         self.heads = []
+        self.gates = []
         self._n = 0
         self.launch_count = 0
         FakeContext.instances.append(self)
@@ -56,6 +57,12 @@ class FakeContext:
     def add_head(self, n_in, dims, layernorm, final_act, blob):
         self.heads.append(unpack_head_blob(n_in, list(dims), layernorm, final_act, np.asarray(blob, np.float32)))
         return len(self.heads) - 1
+
+    def add_gate(self, main_head, verifier_head, threshold=0.5):
+        self.gates.append((main_head, verifier_head, float(threshold)))
+
+    def _col0(self, hid):
+        return sum(h["layers"][-1]["W"].shape[1] for h in self.heads[:hid])
 
     @property
     def n_outputs(self):
@@ -78,13 +85,16 @@ class FakeContext:
         for b in range(self._n):
             got = self.af[b](pcm[b])
             assert got == n_chunks * 1280
-            col = 0
+            per_chunk = []
             for h in self.heads:
                 n_in = h["n_in"]
                 g = [oheads.forward(h, self.af[b].get_features(n_in, -n_in - i))[0] for i in range(n_chunks - 1, -1, -1)]
-                p = np.max(np.stack(g), axis=0)
-                scores_out[b, col:col + p.size] = p
-                col += p.size
+                per_chunk.append(np.stack(g))            # [n_chunks, n_out]
+            raw = np.concatenate(per_chunk, axis=1)      # [n_chunks, n_cols]
+            for m, v, thr in self.gates:                 # per chunk, before the max over chunks (as the gated graph would)
+                cm, cv = self._col0(m), self._col0(v)
+                raw[:, cm] = np.where(raw[:, cm] > np.float32(thr), raw[:, cv], raw[:, cm])
+            scores_out[b, :raw.shape[1]] = raw.max(axis=0)
 
     def get_features(self, stream_id, n, back=0):
         fb = self.af[stream_id].feature_buffer
@@ -93,6 +103,10 @@ class FakeContext:
         if rows.shape[0] < n:
             rows = np.vstack((np.zeros((n - rows.shape[0], 96), np.float32), rows))
         return rows.astype(np.float32)
+
+    def get_counts(self, stream_id):
+        # the oracle caps its buffers like the reference; uncapped counts are not needed by the host logic under test
+        return self.af[stream_id].melspectrogram_buffer.shape[0], self.af[stream_id].feature_buffer.shape[0]
 
     def get_mel(self, stream_id, n_rows=76):
         return self.af[stream_id].melspectrogram_buffer[-n_rows:].astype(np.float32)

@@ -29,6 +29,9 @@ HEAD_SPECS = {   # name -> kwargs of weights.synthetic_head
     "timer_v0.1": dict(n_in=34, hidden=128, n_blocks=1, n_out=7, layernorm=False, final="relu_softmax", seed=9),
     "big_v0.1": dict(n_in=16, hidden=128, n_blocks=2, n_out=1, layernorm=True, final="sigmoid", seed=4),
 }
+GATED_SPECS = {  # conditional verifier pairs (the hey_jarvis structure): weights.synthetic_gated_head kwargs
+    "hey_jarvis_v0.1": dict(seed_main=31, seed_verifier=32, threshold=0.5),
+}
 TIMER_MAP = {"1": "1_minute_timer", "2": "5_minute_timer", "3": "10_minute_timer",
              "4": "20_minute_timer", "5": "30_minute_timer", "6": "1_hour_timer"}
 
@@ -42,6 +45,8 @@ def main():
     out_dir = os.path.dirname(os.path.abspath(__file__))
     emb = W.synthetic_embedding(EMB_SEED)
     heads = {k: W.synthetic_head(**v) for k, v in HEAD_SPECS.items()}
+    heads.update({k: W.synthetic_gated_head(**v) for k, v in GATED_SPECS.items()})
+    only_new = "--only-new" in sys.argv           # keep the committed round-1 fixtures byte-identical
     ref_stub_ort.install(emb, heads)
     sys.path.insert(0, "/root/reference")
     from openwakeword.model import Model            # the reference, unmodified
@@ -67,7 +72,9 @@ def main():
             for n in ("alexa_test", "hey_mycroft_test", "hey_jane")}
     cases = {}
 
-    def run_clip(tag, names, pcm, seed, chunk, padding=1, **kw):
+    def run_clip(tag, names, pcm, seed, chunk, padding=1, new=False, **kw):
+        if only_new and not new:
+            return
         m, fi = make_model(names, seed)
         res = m.predict_clip(pcm, padding=padding, chunk_size=chunk, **kw)
         labels = list(res[0].keys())
@@ -90,6 +97,12 @@ def main():
              debounce_time=0.5, threshold={"hey_mycroft_v0.1": 0.2})
     run_clip("jane_patience", ["hey_mycroft_v0.1"], wavs["hey_jane"], 8, 1280,
              patience={"hey_mycroft_v0.1": 3}, threshold={"hey_mycroft_v0.1": 0.2})
+
+    # round 2: the conditional verifier pair, one chunk and two chunks per call (gate per chunk, then max)
+    run_clip("jarvis_gated_c1280", ["hey_jarvis_v0.1", "alexa_v0.1"], wavs["hey_jane"], 9, 1280, new=True)
+    run_clip("jarvis_gated_c2560", ["hey_jarvis_v0.1", "timer_v0.1"], wavs["hey_mycroft_test"], 10, 2560, new=True)
+    if only_new:
+        return write_cases(cases, out_dir)
 
     # raw streaming with mixed chunk lengths and a mid-stream reset (state carries over)
     rng = np.random.default_rng(11)
@@ -116,6 +129,10 @@ def main():
     cases["embed_clips"] = dict(kind="embed_clips", pcm=clips, embeddings=emb_out.astype(np.float32))
     print("embed_clips", emb_out.shape)
 
+    write_cases(cases, out_dir)
+
+
+def write_cases(cases, out_dir):
     for tag, c in cases.items():
         d = {}
         for k, v in c.items():

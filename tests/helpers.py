@@ -14,6 +14,7 @@ HEAD_SPECS = {   # must match tests/golden/make_golden.py
     "timer_v0.1": dict(n_in=34, hidden=128, n_blocks=1, n_out=7, layernorm=False, final="relu_softmax", seed=9),
     "big_v0.1": dict(n_in=16, hidden=128, n_blocks=2, n_out=1, layernorm=True, final="sigmoid", seed=4),
 }
+GATED_SPECS = {"hey_jarvis_v0.1": dict(seed_main=31, seed_verifier=32, threshold=0.5)}
 TIMER_MAP = {"1": "1_minute_timer", "2": "5_minute_timer", "3": "10_minute_timer",
              "4": "20_minute_timer", "5": "30_minute_timer", "6": "1_hour_timer"}
 
@@ -28,7 +29,7 @@ def emb_weights(seed=0):
 
 def head(name):
     if name not in _cache:
-        _cache[name] = W.synthetic_head(**HEAD_SPECS[name])
+        _cache[name] = W.synthetic_gated_head(**GATED_SPECS[name]) if name in GATED_SPECS else W.synthetic_head(**HEAD_SPECS[name])
     return _cache[name]
 
 

@@ -20,8 +20,19 @@ def torch_cuda():
     return torch
 
 
+MODES = [0, 3]        # fp32 CUDA-core window path (bit-faithful check) and the default tcgen05 fused incremental path
+
+
 @pytest.fixture(scope="module")
 def af(torch_cuda, built_library):
+    """fp32 graph kernels (cnn_mode 0): the tight per-graph tolerances below are for this path."""
+    from openwakeword_b200 import AudioFeatures
+    return AudioFeatures(embedding_model_path=emb_weights(), feature_init=np.zeros((41, 96), np.float32), cnn_mode=0)
+
+
+@pytest.fixture(scope="module")
+def af_default(torch_cuda, built_library):
+    """what a user gets: cnn_mode 3 (tcgen05, fp16 operands / fp32 accumulate)."""
     from openwakeword_b200 import AudioFeatures
     return AudioFeatures(embedding_model_path=emb_weights(), feature_init=np.zeros((41, 96), np.float32))
 
@@ -79,6 +90,21 @@ def test_embedding_windows_vs_oracle(af):
         assert np.abs(got - ref).max() < 5e-4, np.abs(got - ref).max()
 
 
+def test_default_mode_is_tc_and_embedding_windows_within_fp16_budget(af_default):
+    """The default handle runs the tcgen05 kernels; stateless window embeddings stay within the fp16-operand budget
+    (measured 3.4e-3 on |x| <= 5; gate 8e-3 = ~2x)."""
+    from oracle import embedding
+    from openwakeword_b200 import _native
+    assert af_default.cnn_mode == _native.CNN_TC_INCREMENTAL
+    rng = np.random.default_rng(1)
+    wins = rng.normal(8, 2.5, (130, 76, 32)).astype(np.float32)
+    got = np.atleast_2d(af_default.embedding_model_predict(wins[..., None]))
+    ref = embedding.embed_windows(emb_weights(), wins)
+    d = np.abs(got - ref).max()
+    print("default (tc) max |emb - oracle| =", d)
+    assert d < 8e-3
+
+
 def test_heads_vs_oracle(torch_cuda, built_library):
     import openwakeword_b200 as owb
     from oracle import heads
@@ -96,26 +122,29 @@ def test_heads_vs_oracle(torch_cuda, built_library):
             assert np.abs(got - ref).max() < 1e-5, (name, np.abs(got - ref).max())
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("tag", golden_cases("predict_clip"))
-def test_predict_clip_golden(torch_cuda, built_library, tag):
+def test_predict_clip_golden(torch_cuda, built_library, tag, mode):
     import openwakeword_b200 as owb
     c = load_case(tag)
     specs = [{"name": n, "head": head(n), "class_mapping": class_mapping([n]).get(n)} for n in c["names"]]
     m = owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(int(c["emb_seed"])),
-                  feature_init=c["feature_init"], max_chunks=8)
+                  feature_init=c["feature_init"], max_chunks=8, cnn_mode=mode)
     res = m.predict_clip(c["pcm"], padding=int(c["padding"]), chunk_size=int(c["chunk"]), **c["kw"])
     assert list(res[0].keys()) == c["labels"]
     got = np.array([[r[l] for l in c["labels"]] for r in res], dtype=np.float32)
     d = np.abs(got - c["scores"]).max()
-    print(tag, "max |score - golden| =", d)
+    print(tag, "mode", mode, "max |score - golden| =", d)
     assert d < SCORE_TOL
 
 
-def test_stream_mixed_golden_and_buffers(torch_cuda, built_library):
+@pytest.mark.parametrize("mode", MODES)
+def test_stream_mixed_golden_and_buffers(torch_cuda, built_library, mode):
     import openwakeword_b200 as owb
     c = load_case("stream_mixed")
     specs = [{"name": n, "head": head(n), "class_mapping": class_mapping([n]).get(n)} for n in c["names"]]
-    m = owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(), feature_init=c["feature_init"], max_chunks=8)
+    m = owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(), feature_init=c["feature_init"], max_chunks=8,
+                  cnn_mode=mode)
     pos, rows = 0, []
     for n in c["lens"]:
         r = m.predict(c["pcm"][pos:pos + n])
@@ -123,7 +152,7 @@ def test_stream_mixed_golden_and_buffers(torch_cuda, built_library):
         rows.append([r[l] for l in c["labels"]])
     assert np.abs(np.array(rows, np.float32) - c["scores"]).max() < SCORE_TOL
     assert np.abs(m.preprocessor.melspectrogram_buffer - c["mel_tail"]).max() < 5e-3
-    assert np.abs(m.preprocessor.get_features(34)[0] - c["feat_tail"]).max() < 2e-3
+    assert np.abs(m.preprocessor.get_features(34)[0] - c["feat_tail"]).max() < (2e-3 if mode == 0 else 8e-3)
 
 
 def test_embed_clips_golden_and_shapes(af):
@@ -137,7 +166,8 @@ def test_embed_clips_golden_and_shapes(af):
         af.embed_clips(np.zeros((2, 4000), np.int16))       # < 76 mel frames (utils.py:313-314)
 
 
-def test_many_streams_vs_oracle_with_resets_and_multichunk(torch_cuda, built_library):
+@pytest.mark.parametrize("mode", MODES)
+def test_many_streams_vs_oracle_with_resets_and_multichunk(torch_cuda, built_library, mode):
     """37 streams (ragged last CTA tile), different signal mixes, 1- and 3-chunk steps, a per-stream reset."""
     from openwakeword_b200.engine import StreamEngine
     from oracle import streaming, heads as oheads
@@ -145,7 +175,7 @@ def test_many_streams_vs_oracle_with_resets_and_multichunk(torch_cuda, built_lib
     B = 37
     hs = [head("alexa_v0.1"), head("timer_v0.1")]
     fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
-    eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, max_chunks=3)
+    eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, max_chunks=3, cnn_mode=mode)
     oracles = [streaming.OracleAudioFeatures(emb_weights(), feature_init=fi) for _ in range(B)]
     plan = [1, 1, 3, 1, 2, 1, 1]
     pcm = _mixes(rng, B, sum(plan) * 1280)
@@ -169,7 +199,7 @@ def test_many_streams_vs_oracle_with_resets_and_multichunk(torch_cuda, built_lib
     assert worst < SCORE_TOL
     for b in (0, 5, 36):
         assert np.abs(eng.ctx.get_mel(b, 76) - oracles[b].melspectrogram_buffer[-76:]).max() < 5e-3
-        assert np.abs(eng.ctx.get_features(b, 40) - oracles[b].feature_buffer[-40:]).max() < 2e-3
+        assert np.abs(eng.ctx.get_features(b, 40) - oracles[b].feature_buffer[-40:]).max() < (2e-3 if mode == 0 else 8e-3)
 
 
 def test_predict_clips_equals_predict_clip_after_reset(torch_cuda, built_library):

@@ -56,18 +56,21 @@ def test_tc_layers_vs_oracle(torch_cuda, built_library, n):
         scale = np.abs(ref).max()
         print(f"layer {li:2d} shape {ref.shape} max|ref| {scale:7.3f} max err {err.max():.4e} mean err {err.mean():.3e}")
         assert np.isfinite(got).all(), f"layer {li} has non-finite values"
-        assert err.max() < 2e-2 * max(scale, 1.0), f"layer {li}: max err {err.max()}"
+        # measured on B200 (round 1): worst max err 1.7e-3 x scale, mean err <= 4.3e-4 -> gates at ~2x
+        assert err.max() < 4e-3 * max(scale, 1.0), f"layer {li}: max err {err.max()}"
+        assert err.mean() < 9e-4, f"layer {li}: mean err {err.mean()}"
         worst_rel = max(worst_rel, err.max() / max(scale, 1.0))
     emb = torch.empty((n, 96), dtype=torch.float32, device="cuda")
     ctx.embed_windows(d, n, emb)
     torch.cuda.synchronize()
     e = np.abs(emb.cpu().numpy() - embedding.embed_windows(emb_weights(), wins))
     print("embedding max err", e.max(), "worst relative layer err", worst_rel)
-    assert e.max() < 3e-2
+    assert e.max() < 7e-3                       # measured 3.4e-3
 
 
 def test_tc_scores_vs_fp32_and_oracle(torch_cuda, built_library):
     from openwakeword_b200.engine import StreamEngine
+    from oracle import streaming, heads as oheads
     rng = np.random.default_rng(9)
     B, steps = 300, 6
     hs = [head("alexa_v0.1"), head("hey_mycroft_v0.1"), head("timer_v0.1"), head("big_v0.1")]
@@ -82,6 +85,17 @@ def test_tc_scores_vs_fp32_and_oracle(torch_cuda, built_library):
     d = np.abs(res[0] - res[TC])
     print("max |score_tc - score_fp32| =", d.max(), " mean", d.mean())
     assert d.max() < 1e-3
+    # and both against the oracle on a sample of streams
+    worst = {0: 0.0, TC: 0.0}
+    for b in list(range(0, B, 13)):
+        o = streaming.OracleAudioFeatures(emb_weights(), feature_init=fi)
+        for s in range(steps):
+            o(pcm[b, s * 1280:(s + 1) * 1280])
+            ref = np.concatenate([oheads.forward(h, o.get_features(h["n_in"]))[0] for h in hs])
+            for mode in (0, TC):
+                worst[mode] = max(worst[mode], float(np.abs(ref - res[mode][b, s]).max()))
+    print("max |score - oracle|: fp32", worst[0], " tc", worst[TC])
+    assert worst[0] < 2e-5 and worst[TC] < 1e-3
 
 
 def test_tc_incremental_vs_window_modes(torch_cuda, built_library):
@@ -169,3 +183,131 @@ def test_fused_step_heads_with_awkward_shapes(torch_cuda, built_library):
         ref = oh.forward(h, feats[True][:, -n_in:])
         assert np.abs(out[True][:, -1, col:col + n_out] - ref).max() < 2e-5
         col += n_out
+
+
+def _mixes(rng, n, length):
+    """SURVEY.md 8d signal mixes: +-1000 noise, full scale, gated bursts (onset inside a call), silence, tone."""
+    out = np.empty((n, length), np.int16)
+    for i in range(n):
+        k = i % 5
+        if k == 0:
+            x = rng.integers(-1000, 1000, length)
+        elif k == 1:
+            x = rng.uniform(-1, 1, length) * 32767
+        elif k == 2:
+            x = rng.normal(0, 8000, length) * ((np.arange(length) // 4000) % 2)
+        elif k == 3:
+            x = np.zeros(length)
+        else:
+            t = np.arange(length); x = 12000 * np.sin(2 * np.pi * 440 * t / 16000) + rng.normal(0, 20, length)
+        out[i] = np.clip(x, -32768, 32767).astype(np.int16)
+    return out
+
+
+@pytest.mark.parametrize("B,n_heads,max_launches", [(1024, 1, 1), (2048, 1, 1), (8192, 3, 5)])
+def test_fused_step_bench_configs_vs_oracle(torch_cuda, built_library, B, n_heads, max_launches):
+    """The configurations bench.py measures, checked against the ORACLE (not against another CUDA mode):
+    cnn_mode 3 with the fused step kernel at B = 1024 (147 groups of G = 7, ragged last group of 2, one round on 148
+    SMs), B = 2048 (two rounds, ragged last group of 4) and B = 8192 (configs[2]'s stream count, many rounds).
+    14 calls: steady one-chunk steps (ONE launch each - asserted), a 2-chunk call, a mid-run reset of a stream subset
+    (re-prime through the full-window kernels), then steady state again.  Scores of >= 64 sampled streams (first
+    group, last ragged group, the reset streams, random others) must match the NumPy oracle within 1e-3, the mel ring
+    within 5e-3 and the feature ring within the fp16-operand budget."""
+    from openwakeword_b200.engine import StreamEngine
+    from oracle import streaming, heads as oheads
+    rng = np.random.default_rng(100 + B)
+    hs = [head("alexa_v0.1"), head("timer_v0.1"), head("big_v0.1")][:n_heads]
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    plan = [1, 1, 1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1, 1]
+    reset_at = 9
+    base = _mixes(rng, 40, sum(plan) * 1280)
+    pick = rng.integers(0, 40, B)
+    pcm = base[pick]                                            # [B, T] (40 distinct signals, scattered)
+    G = 7
+    last_group = list(range((B - 1) // G * G, B))
+    reset_ids = sorted(set([3, B // 2, B - 1] + list(rng.integers(0, B, 5))))
+    sample = sorted(set(list(range(G)) + last_group + reset_ids + list(rng.integers(0, B, 64))))
+    assert len(sample) >= 64
+    eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, max_chunks=2)      # default mode = 3, fused
+    oracles = {b: streaming.OracleAudioFeatures(emb_weights(), feature_init=fi) for b in sample}
+    pos, worst, steady_steps = 0, 0.0, 0
+    for si, nch in enumerate(plan):
+        if si == reset_at:
+            eng.reset(fi, stream_ids=reset_ids)
+            for b in reset_ids:
+                oracles[b].reset(feature_init=fi)
+        x = np.ascontiguousarray(pcm[:, pos:pos + nch * 1280])
+        pos += nch * 1280
+        n0 = eng.ctx.launch_count
+        got = eng.step_host(x, nch)
+        steady_steps += int(eng.ctx.launch_count - n0 <= max_launches)
+        for b in sample:
+            assert oracles[b](x[b]) == nch * 1280
+            ref = []
+            for h in hs:
+                g = [oheads.forward(h, oracles[b].get_features(h["n_in"], -h["n_in"] - i))[0] for i in range(nch - 1, -1, -1)]
+                ref.append(np.max(np.stack(g), axis=0))
+            d = float(np.abs(np.concatenate(ref) - got[b]).max())
+            assert d < 1e-3, (si, b, d)
+            worst = max(worst, d)
+    print(f"B={B}: max |score - oracle| over {len(sample)} sampled streams x {len(plan)} calls = {worst:.3e}; "
+          f"{steady_steps} of {len(plan)} calls took <= {max_launches} launch(es)")
+    # the steady-state one-chunk steps really ran as the fused step kernel (one launch; with head sets too large for
+    # the in-kernel heads phase: fused frontend+CNN launch + heads): all but the first call after each (re)prime
+    # and the 2-chunk call
+    assert steady_steps >= len(plan) - 4
+    for b in (0, last_group[-1], reset_ids[0]):
+        assert np.abs(eng.ctx.get_mel(b, 76) - oracles[b].melspectrogram_buffer[-76:]).max() < 5e-3
+        assert np.abs(eng.ctx.get_features(b, 40) - oracles[b].feature_buffer[-40:]).max() < 8e-3
+
+
+def _gain_head(gain, seed=1):
+    """alexa-shaped head whose last Linear is scaled by `gain` with the bias re-centred, so the scores keep straddling
+    0.5 (maximum sigmoid slope) while the logit's sensitivity to embedding error grows with the gain."""
+    from openwakeword_b200 import weights as W
+    h = W.synthetic_head(n_in=16, hidden=64, n_blocks=1, n_out=1, layernorm=True, final="sigmoid", seed=seed)
+    last = h["layers"][-1]
+    last["W"] = (last["W"] * gain).astype(np.float32)
+    last["b"] = (last["b"] * gain).astype(np.float32)
+    return h
+
+
+# worst |score - oracle| allowed per (cnn_mode, gain): the fp32 path must hold 5e-4 everywhere; the fp16-operand
+# tcgen05 path is budgeted at 2x its measured error (filled from the first hardware run, see DESIGN.md section 3)
+GAIN_BUDGET = {0: {1: 5e-4, 2: 5e-4, 4: 5e-4, 8: 5e-4, 16: 5e-4},
+               3: {1: 1e-3, 2: 2e-3, 4: 4e-3, 8: 8e-3, 16: 1.6e-2}}
+
+
+@pytest.mark.parametrize("mode", [0, 3])
+def test_gain_sweep_precision_headroom(torch_cuda, built_library, mode):
+    """Adversarial-gain parity: heads whose last Linear is scaled x1..x16 (scores near 0.5), all on one handle, streamed
+    for 24 steps on 56 streams (8 groups of 7) against the oracle.  Prints the worst error per gain - the table
+    DESIGN.md section 3 quotes - and holds each path to its budget."""
+    from openwakeword_b200.engine import StreamEngine
+    from oracle import streaming, heads as oheads
+    rng = np.random.default_rng(77)
+    gains = [1, 2, 4, 8, 16]
+    hs = [_gain_head(g) for g in gains]
+    B, steps = 56, 24
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    pcm = _mixes(rng, B, steps * 1280)
+    pcm[3::5] = np.clip(rng.normal(0, 2500, (len(pcm[3::5]), steps * 1280)), -32768, 32767).astype(np.int16)   # no silence rows
+    eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=mode)
+    oracles = [streaming.OracleAudioFeatures(emb_weights(), feature_init=fi) for _ in range(B)]
+    worst = np.zeros(len(gains))
+    near = np.zeros(len(gains), int)
+    for s in range(steps):
+        x = np.ascontiguousarray(pcm[:, s * 1280:(s + 1) * 1280])
+        got = eng.step_host(x, 1)
+        for b in range(B):
+            oracles[b](x[b])
+            f = oracles[b].get_features(16)
+            for j, h in enumerate(hs):
+                ref = oheads.forward(h, f)[0, 0]
+                worst[j] = max(worst[j], abs(float(ref) - float(got[b, j])))
+                near[j] += int(0.2 < ref < 0.8)
+    for g, w, n in zip(gains, worst, near):
+        print(f"cnn_mode {mode} gain x{g:<2d}: max |score - oracle| = {w:.3e}   ({n} of {B * steps} reference scores in (0.2, 0.8))")
+    assert near[0] > B * steps // 10, "the sweep must exercise the steep part of the sigmoid"
+    for g, w in zip(gains, worst):
+        assert w <= GAIN_BUDGET[mode][g], (mode, g, w)
