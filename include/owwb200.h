@@ -160,6 +160,18 @@ int oww_embed_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sampl
 int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_samples, int pad_samples,
                       const float* h_feature_init, int n_rows, float* d_scores, void* stream);
 
+/* ---- score metrics on the device (openwakeword/metrics.py:24-100) --------------------------------
+ * d_scores holds n_series score sequences of n_frames float32 each, series i at d_scores + i*series_stride.
+ * oww_metrics_false_positives: h_counts[i][j] = get_false_positives(series i, h_thresholds[j], grouping_window)
+ * with the reference's grouping rule (restated in oracle/metrics.py); generate_roc_curve_fprs is this count at
+ * np.linspace(0.01, 0.99, n_points) divided by the hours the series spans.
+ * oww_metrics_count_ge: h_counts[j] = number of the n scores >= h_thresholds[j] (generate_roc_curve_tprs * len).
+ * Comparisons are done in double, as NumPy does for float32 scores against np.float64 thresholds.  Both synchronise. */
+int oww_metrics_false_positives(oww_ctx* ctx, const float* d_scores, int64_t series_stride, int n_series, int n_frames,
+                                const double* h_thresholds, int n_thresholds, int grouping_window, int32_t* h_counts, void* stream);
+int oww_metrics_count_ge(oww_ctx* ctx, const float* d_scores, int64_t n, const double* h_thresholds, int n_thresholds,
+                         uint64_t* h_counts, void* stream);
+
 /* ---- parity instrumentation --------------------------------------------------------------- */
 /* Runs the embedding CNN on d_windows [n][76][32] (n <= window_batch) up to and including conv
  * layer `layer` (0..18) and its max-pool, and writes that activation as NHWC float32

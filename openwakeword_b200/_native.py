@@ -68,6 +68,8 @@ _SIGNATURES = {
     "oww_peer_close": (C.c_int, [_P, _P]),
     "oww_peer_signal": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "oww_peer_wait": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint64, C.c_double, _P]),
+    "oww_metrics_false_positives": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "oww_metrics_count_ge": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P]),
     "oww_launch_count": (C.c_uint64, [_P]),
     "oww_enable_stage_timing": (C.c_int, [_P, C.c_int]),
     "oww_stage_ms": (C.c_int, [_P, _P]),
@@ -285,6 +287,24 @@ class Context:
 
     def peer_wait(self, flags_addr, n, stride, value, timeout_s=10.0, stream=None):
         self._check(self.lib.oww_peer_wait(self.h, int(flags_addr), int(n), int(stride), int(value), float(timeout_s), stream))
+
+    # ---- metrics (device-resident scores) ----
+    def metrics_false_positives(self, d_scores, series_stride, n_series, n_frames, thresholds, grouping_window=50, stream=None):
+        thr = np.ascontiguousarray(thresholds, np.float64)
+        out = np.zeros((n_series, thr.size), np.int32)
+        self._check(self.lib.oww_metrics_false_positives(self.h, _ptr(d_scores), int(series_stride), int(n_series), int(n_frames),
+                                                         _ptr(thr), thr.size, int(grouping_window), _ptr(out), stream))
+        return out
+
+    def metrics_count_ge(self, d_scores, n, thresholds, stream=None):
+        thr = np.ascontiguousarray(thresholds, np.float64)
+        out = np.zeros(thr.size, np.uint64)
+        for j0 in range(0, thr.size, 64):
+            t = np.ascontiguousarray(thr[j0:j0 + 64])
+            o = np.zeros(t.size, np.uint64)
+            self._check(self.lib.oww_metrics_count_ge(self.h, _ptr(d_scores), int(n), _ptr(t), t.size, _ptr(o), stream))
+            out[j0:j0 + 64] = o
+        return out
 
     # ---- introspection ----
     def enable_stage_timing(self, n_slots=1):

@@ -153,10 +153,7 @@ int reprime_subset(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n
     WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, n_ids, 1};
     ws.ids = ctx->d_unprimed_ids;
     if ((rc = oww_cnn_window(ctx, ws, n_ids, ctx->d_emb_tmp, s, true))) return rc;
-    if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, 1, s, ctx->d_unprimed_ids, n_ids))) return rc;
-    set_primed_kernel<<<(n_ids + 255) / 256, 256, 0, s>>>(ctx->d_primed, ctx->d_unprimed_ids, n_ids, ctx->n_streams);
-    OWW_LAUNCH_CHECK(ctx);
-    return OWW_OK;
+    return oww_feat_append(ctx, ctx->d_emb_tmp, 1, s, ctx->d_unprimed_ids, n_ids);
 }
 
 int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks, float* d_scores, int out_stride,
@@ -192,6 +189,10 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
             if ((rc = reprime_subset(ctx, d_pcm, pcm_stride, (int)ids.size(), ctx->side_stream))) return rc;
             OWW_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
             OWW_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+            // only now (the fused kernel has finished reading the flags) do the re-primed streams count as primed
+            const int n_ids = (int)ids.size();
+            set_primed_kernel<<<(n_ids + 255) / 256, 256, 0, s>>>(ctx->d_primed, ctx->d_unprimed_ids, n_ids, ctx->n_streams);
+            OWW_LAUNCH_CHECK(ctx);
             mark_all_primed(ctx);
         }
         if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));

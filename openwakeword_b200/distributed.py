@@ -144,11 +144,29 @@ class _DeviceView:
                                          "version": 3, "strides": None}
 
 
+class GatheredScores:
+    """Result of an overlapped gather: ``wait()`` orders the current CUDA stream behind the collective and returns the
+    ``[n_total, n_cols]`` tensor (valid until the step after next reuses the buffer)."""
+
+    def __init__(self, tensor, work):
+        self._t, self._w = tensor, work
+
+    def wait(self):
+        if self._w is not None:
+            self._w.wait()
+        return self._t
+
+
 class ShardedStreams:
     """n_total independent streams split over the ranks of the default process group.
 
     ``engine_factory(n_local, lo, hi)`` builds this rank's step engine (on GPU ranks a
-    ``StreamEngine`` bound to LOCAL_RANK); ``step(local_pcm)`` runs it and gathers the scores."""
+    ``StreamEngine`` bound to LOCAL_RANK); ``step(local_pcm)`` runs it and gathers the scores.
+
+    ``gather``: ``"nccl"`` - all-gather on the compute stream after every step (every rank gets the scores);
+    ``"nccl-overlap"`` - the all-gather of step k runs on a side stream while the compute stream already works on
+    step k+1 (two score buffers; ``step`` returns a ``GatheredScores`` whose ``wait()`` yields the tensor);
+    ``"peer"`` - peer-memory stores into rank 0's buffer, no collective (experimental until run on hardware)."""
 
     def __init__(self, n_total, engine_factory, rank=None, world=None, gather="nccl"):
         r, w, _ = env_rank_world()
@@ -157,10 +175,14 @@ class ShardedStreams:
         self.n_total = n_total
         self.lo, self.hi = shard_range(n_total, self.rank, self.world)
         self.engine = engine_factory(self.hi - self.lo, self.lo, self.hi)
-        if gather not in ("nccl", "peer"):
-            raise ValueError("gather is 'nccl' (all-gather on every rank) or 'peer' (peer-memory gather on rank 0)")
+        if gather not in ("nccl", "nccl-overlap", "peer"):
+            raise ValueError("gather is 'nccl', 'nccl-overlap' (side-stream all-gather) or 'peer' (peer-memory gather on rank 0)")
         self.peer = None
         self._k = 0
+        self._ov = None
+        self.gather_kind = "none (single rank)" if self.world == 1 else gather
+        if self.world > 1 and gather == "nccl-overlap" and n_total % self.world != 0:
+            self.gather_kind = gather = "nccl"                    # uneven shards need the padded path
         if gather == "peer" and self.world > 1:
             import torch.distributed as dist
 
@@ -169,10 +191,37 @@ class ShardedStreams:
                 dist.all_gather_object(out, obj)
                 return out
             self.peer = PeerGather(self.engine.ctx, n_total, self.engine.n_cols, self.rank, self.world, exchange)
+        self._overlap = gather == "nccl-overlap" and self.world > 1
+
+    def _overlap_state(self, dev):
+        import torch
+        if self._ov is None:
+            n_loc, L = self.hi - self.lo, self.engine.n_cols
+            self._ov = {"side": torch.cuda.Stream(device=dev),
+                        "loc": [torch.empty((n_loc, L), dtype=torch.float32, device=dev) for _ in range(2)],
+                        "out": [torch.empty((self.n_total, L), dtype=torch.float32, device=dev) for _ in range(2)],
+                        "work": [None, None], "ev": [torch.cuda.Event(), torch.cuda.Event()]}
+        return self._ov
 
     def step(self, local_pcm, n_chunks=1):
-        """Scores of all n_total streams: on every rank with the NCCL all-gather; with gather='peer' on rank 0 only
-        (a view of the gather buffer, valid until the step after next) and None elsewhere."""
+        """Scores of all n_total streams: on every rank with the NCCL all-gather ('nccl-overlap': a ``GatheredScores``);
+        with gather='peer' on rank 0 only (a view of the gather buffer, valid until the step after next) and None elsewhere."""
+        if self.world == 1:
+            return self.engine.step(local_pcm, n_chunks)
+        if self._overlap:
+            import torch
+            import torch.distributed as dist
+            ov = self._overlap_state(local_pcm.device)
+            i = self._k & 1
+            self._k += 1
+            if ov["work"][i] is not None:
+                ov["work"][i].wait()                              # compute stream: buffer i has been gathered (no host block)
+            self.engine.step(local_pcm, n_chunks, out=ov["loc"][i])
+            ov["ev"][i].record()
+            with torch.cuda.stream(ov["side"]):
+                ov["side"].wait_event(ov["ev"][i])
+                ov["work"][i] = dist.all_gather_into_tensor(ov["out"][i], ov["loc"][i], async_op=True)
+            return GatheredScores(ov["out"][i], ov["work"][i])
         if self.peer is None:
             return gather_scores(self.engine.step(local_pcm, n_chunks), self.n_total)
         import torch
@@ -189,3 +238,10 @@ class ShardedStreams:
             return None
         addr = pg.collect(k, stream)
         return torch.as_tensor(_DeviceView(addr, (self.n_total, self.engine.n_cols)), device=local_pcm.device)
+
+    def flush(self):
+        """Order the current CUDA stream behind every outstanding overlapped gather."""
+        if self._ov is not None:
+            for w in self._ov["work"]:
+                if w is not None:
+                    w.wait()

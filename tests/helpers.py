@@ -41,6 +41,8 @@ def golden_cases(kind=None):
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         z = np.load(p, allow_pickle=False)
+        if "kind" not in z.files:          # not a hot-path case file (e.g. metrics.npz)
+            continue
         if kind is None or str(z["kind"]) == kind:
             out.append(os.path.splitext(os.path.basename(p))[0])
     return out

@@ -119,7 +119,8 @@ def test_heads_vs_oracle(torch_cuda, built_library):
             got = m.model_prediction_function[name](f)[0]
             ref = heads.forward(head(name), f)
             assert got.shape == ref.shape == (n, m.model_outputs[name])
-            assert np.abs(got - ref).max() < 1e-5, (name, np.abs(got - ref).max())
+            # default handle: first layer on tcgen05 with the fp16 hi/lo split (fp32-grade, measured 1.2e-5)
+            assert np.abs(got - ref).max() < 2e-5, (name, np.abs(got - ref).max())
 
 
 @pytest.mark.parametrize("mode", MODES)

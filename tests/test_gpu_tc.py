@@ -129,7 +129,9 @@ def test_tc_incremental_vs_window_modes(torch_cuda, built_library):
     print("fused step vs separate launches: max |score diff| =", np.abs(out[3] - out[13]).max(),
           " max |feat diff| =", np.abs(feats[3] - feats[13]).max())
     assert np.abs(feats[3] - feats[2]).max() < 2e-3
-    assert np.abs(out[3] - out[13]).max() < 1e-6 and np.abs(feats[3] - feats[13]).max() < 1e-6
+    # same embeddings bit for bit; the scores differ only by the heads' arithmetic (in-kernel fp32 FMA chain when fused,
+    # tcgen05 hi/lo-split first layer when the heads run as their own launch): fp32 round-off
+    assert np.array_equal(feats[3], feats[13]) and np.abs(out[3] - out[13]).max() < 2e-5
     assert d32.max() < 2e-4
     assert np.abs(out[3] - out[0]).max() < 1e-3
 
@@ -175,7 +177,7 @@ def test_fused_step_heads_with_awkward_shapes(torch_cuda, built_library):
         feats[fuse] = np.stack([eng.ctx.get_features(b, 28) for b in range(B)])
     assert np.array_equal(feats[True], feats[False])
     print("awkward heads, fused vs separate launches: max |score diff| =", np.abs(out[True] - out[False]).max())
-    assert np.abs(out[True] - out[False]).max() < 1e-6
+    assert np.abs(out[True] - out[False]).max() < 2e-5       # in-kernel fp32 heads vs tensor-core / heads.cu launch
     # the last step's scores from the device features through the NumPy heads
     col = 0
     for h in hs:
@@ -311,3 +313,97 @@ def test_gain_sweep_precision_headroom(torch_cuda, built_library, mode):
     assert near[0] > B * steps // 10, "the sweep must exercise the steep part of the sigmoid"
     for g, w in zip(gains, worst):
         assert w <= GAIN_BUDGET[mode][g], (mode, g, w)
+
+
+def test_tc_heads_vs_oracle_and_cuda_core_heads(torch_cuda, built_library):
+    """heads_tc.cu (first layer as a tcgen05 GEMM on fp16 hi/lo split operands, fp32 accumulate) against the oracle and
+    against heads.cu on the same features: stateless (linear source; sample counts that leave a ragged last 128-row
+    tile), widths 30 / 64 / 128 with padding to N = 32 / 64 / 128, n_in 3 / 16 / 34, softmax / sigmoid / relu finals.
+    The 3-term split must be fp32-grade (2e-5); the 1-term variant is held to the fp16 budget."""
+    torch = torch_cuda
+    from openwakeword_b200 import _native, weights as W
+    from oracle import heads as oh
+    rng = np.random.default_rng(12)
+    relu_head = W.synthetic_head(n_in=16, hidden=64, n_blocks=1, n_out=4, layernorm=False, final="relu_softmax", seed=13)
+    relu_head["final"] = "relu"
+    hs = [head("alexa_v0.1"), head("timer_v0.1"), head("big_v0.1"),
+          W.synthetic_head(n_in=16, hidden=30, n_blocks=1, n_out=1, seed=3),
+          W.synthetic_head(n_in=3, hidden=7, n_blocks=2, n_out=3, layernorm=False, final="softmax", seed=4),
+          relu_head]
+    worst = {}
+    for terms, tc in ((3, True), (1, True), (3, False)):
+        ctx = _native.Context(cnn_mode=3, tc_heads=tc, tc_heads_terms=terms)
+        ctx.load_mel()
+        ctx.load_embedding(W.pack_embedding_blob(emb_weights()))
+        ids = [ctx.add_head(*W.head_desc(h), W.pack_head_blob(h)) for h in hs]
+        w = 0.0
+        for n in (1, 130, 700):
+            for hid, h in zip(ids, hs):
+                f = rng.normal(0.3, 1.5, (n, h["n_in"], 96)).astype(np.float32)
+                f[::7] *= 4.0                                             # a few large-magnitude rows
+                d = torch.from_numpy(f).cuda()
+                n_out = h["layers"][-1]["W"].shape[1]
+                out = torch.full((n, n_out), -7.0, dtype=torch.float32, device="cuda")
+                ctx.head_predict(hid, d, n, out)
+                torch.cuda.synchronize()
+                ref = oh.forward(h, f)
+                w = max(w, float(np.abs(out.cpu().numpy() - ref).max()))
+        worst[(terms, tc)] = w
+        ctx.close()
+    print("max |score - oracle|: tc 3-term", worst[(3, True)], " tc 1-term", worst[(1, True)], " cuda-core", worst[(3, False)])
+    assert worst[(3, False)] < 1e-5
+    assert worst[(3, True)] < 2e-5
+    assert worst[(1, True)] < 2e-3
+
+
+def test_partial_reset_keeps_the_fused_kernel_and_matches_oracle(torch_cuda, built_library):
+    """Per-stream priming: one stream of 1024 is reset before EVERY step (stream-ordered oww_reset_async on the step's
+    stream).  The reset stream re-primes from a full window on the side stream while the other 1023 stay on the fused
+    kernel - checked by parity with the oracle for the reset streams, their group neighbours and random others, and by
+    the step time (< 0.25 ms per step here; the full-window path for all 1024 streams costs ~0.85 ms)."""
+    torch = torch_cuda
+    from openwakeword_b200.engine import StreamEngine
+    from oracle import streaming, heads as oheads
+    rng = np.random.default_rng(31)
+    B, steps = 1024, 16
+    hs = [head("alexa_v0.1")]
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    base = _mixes(rng, 40, steps * 1280)
+    pcm = base[rng.integers(0, 40, B)]
+    eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi)
+    reset_of_step = [int(x) for x in rng.integers(0, B, steps)]
+    reset_of_step[5] = reset_of_step[4]                                   # the same stream twice in a row
+    reset_of_step[9] = B - 1                                              # a stream of the ragged last group
+    sample = sorted(set(reset_of_step + [r ^ 1 for r in reset_of_step] + [0, 7, B - 2] + list(rng.integers(0, B, 16))))
+    orc = {b: streaming.OracleAudioFeatures(emb_weights(), feature_init=fi) for b in sample}
+    dev = [torch.from_numpy(np.ascontiguousarray(pcm[:, s * 1280:(s + 1) * 1280])).cuda() for s in range(steps)]
+    for s in range(3):                                                    # prime everything first
+        got = eng.step(dev[s], 1)
+        torch.cuda.synchronize()
+        for b in sample:
+            orc[b](pcm[b, s * 1280:(s + 1) * 1280])
+    worst = 0.0
+    t_steps = []
+    for s in range(3, steps):
+        r = reset_of_step[s]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.reset_async(fi, stream_ids=[r])
+        got = eng.step(dev[s], 1)
+        e1.record()
+        torch.cuda.synchronize()
+        t_steps.append(e0.elapsed_time(e1))
+        orc[r].reset(feature_init=fi)
+        g = got.cpu().numpy()
+        for b in sample:
+            orc[b](pcm[b, s * 1280:(s + 1) * 1280])
+            ref = oheads.forward(hs[0], orc[b].get_features(16))[0]
+            d = float(np.abs(ref - g[b]).max())
+            assert d < 1e-3, (s, b, d)
+            worst = max(worst, d)
+    ms = float(np.median(t_steps))
+    print(f"one-of-{B} reset per step: max |score - oracle| = {worst:.3e}; median step {ms:.3f} ms (reset + step)")
+    assert ms < 0.25
+    for b in (reset_of_step[-1], B - 1, 0):
+        assert np.abs(eng.ctx.get_mel(b, 76) - orc[b].melspectrogram_buffer[-76:]).max() < 5e-3
+        assert np.abs(eng.ctx.get_features(b, 30) - orc[b].feature_buffer[-30:]).max() < 8e-3
