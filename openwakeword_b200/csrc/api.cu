@@ -46,11 +46,33 @@ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 __global__ void reset_kernel(const int* ids, int n_ids, int n_streams, int16_t* tail, int* seen, int* mel_count,
                              int* feat_count, float* mel_ring, int mel_rows, float* feat_ring, int feat_rows,
-                             const float* feat_init, int n_rows, uint8_t* primed) {
+                             const float* feat_init, int n_rows, ResetTails rt) {
     const int j = blockIdx.x;
     const int b = ids ? ids[j] : j;
     if (b < 0 || b >= n_streams) return;
-    if (threadIdx.x == 0 && primed) primed[b] = 0;
+    if (rt.tails) {
+        // mode 3: the stream's conv tails become those of the all-ones window (its history after a reset), scattered from
+        // the compact per-stream template into the group layout [(r*G + g)*Wp + f] of each tails-bearing tensor
+        const int grp = b / rt.G, g = b - grp * rt.G;
+        uint4* dst = rt.tails + (int64_t)grp * rt.tail_units;
+        for (int k = 0; k < rt.n_tab; ++k) {
+            const int off1 = rt.tab[k].x, offG = rt.tab[k].y, cg = rt.tab[k].z, Wp = rt.tab[k].w;
+            for (int i = threadIdx.x; i < cg * 2 * Wp; i += blockDim.x) {
+                const int pl = i / (2 * Wp), u = i - pl * 2 * Wp, r = u / Wp, f = u - r * Wp;
+                dst[offG + pl * (2 * rt.G * Wp) + (r * rt.G + g) * Wp + f] = rt.tmpl[off1 + i];
+            }
+        }
+        // incremental late layers: tails rows of the buffers the next step (and, for single-row tensors, the one after) reads
+        for (int k = 0; k < rt.n_late; ++k) {
+            const ResetLate& T = rt.late[k];
+            for (int i = threadIdx.x; i < T.n_planes * 2 * T.Wp; i += blockDim.x) {
+                const int pl = i / (2 * T.Wp), u = i - pl * 2 * T.Wp, r = u / T.Wp, f = u - r * T.Wp;
+                const uint4 v = T.tmpl[i];
+                T.now[(int64_t)pl * T.plane + 8 + ((int64_t)b * T.T_buf + r) * T.Wp + f] = v;
+                if (T.next && r == 1) T.next[(int64_t)pl * T.plane + 8 + ((int64_t)b * T.T_buf + 0) * T.Wp + f] = v;
+            }
+        }
+    }
     for (int i = threadIdx.x; i < OWW_TAIL; i += blockDim.x) tail[(int64_t)b * OWW_TAIL + i] = 0;
     float* mr = mel_ring + (int64_t)b * mel_rows * 32;
     for (int i = threadIdx.x; i < mel_rows * 32; i += blockDim.x) mr[i] = 1.0f;     // np.ones((76,32)), utils.py:165
@@ -73,18 +95,28 @@ __global__ void gather_chunk_kernel(const int16_t* pcm, int n_clips, int n_sampl
     }
 }
 
+}  // namespace
+// Tails of the all-ones window per tails-bearing tensor, in the compact G = 1 layout, computed once per weight set by
+// the full-window tcgen05 kernels (cnn_tc.cu) - the state every freshly reset stream starts from (its mel history IS
+// ones(76,32), utils.py:165, and a constant history is shift invariant, so no per-stream re-priming pass is needed).
+int oww_inc_build_template(oww_ctx* ctx);
+namespace {
+
 void free_streams(oww_ctx* c) {
     cudaFree(c->d_tail); cudaFree(c->d_seen); cudaFree(c->d_mel_count); cudaFree(c->d_feat_count);
     cudaFree(c->d_mel_ring); cudaFree(c->d_feat_ring); cudaFree(c->d_act[0]); cudaFree(c->d_act[1]);
     cudaFree(c->d_emb_tmp); cudaFree(c->d_inc_tails[0]); cudaFree(c->d_inc_tails[1]);
-    cudaFree(c->d_primed); cudaFree(c->d_unprimed_ids); cudaFree(c->d_reset_ids); cudaFree(c->d_reset_init);
+    cudaFree(c->d_reset_ids); cudaFree(c->d_reset_init);
     cudaFree(c->d_scores_tmp);
+    for (auto& X : c->late_x) for (auto& b : X.buf) { cudaFree(b); b = nullptr; }
+    cudaFree(c->d_late_tmp[0]); c->d_late_tmp[0] = nullptr;
+    cudaFree(c->d_late_template); c->d_late_template = nullptr;
+    c->late_active = false;
     c->d_tail = nullptr; c->d_seen = c->d_mel_count = c->d_feat_count = nullptr;
     c->d_mel_ring = c->d_feat_ring = c->d_act[0] = c->d_act[1] = c->d_emb_tmp = nullptr;
     c->d_inc_tails[0] = c->d_inc_tails[1] = nullptr;
-    c->d_primed = nullptr; c->d_unprimed_ids = c->d_reset_ids = nullptr; c->d_reset_init = nullptr;
+    c->d_reset_ids = nullptr; c->d_reset_init = nullptr;
     c->d_scores_tmp = nullptr; c->scores_tmp_floats = 0;
-    c->primed.clear(); c->n_unprimed = 0;
     c->act_floats = c->emb_tmp_floats = 0;
     c->n_streams = 0;
 }
@@ -123,39 +155,6 @@ int ensure_emb_tmp(oww_ctx* ctx, size_t floats) {
     return OWW_OK;
 }
 
-// the streams a reset left unprimed, as a device list for the re-prime chain (pageable source: the async copy is
-// staged by the driver before it returns, so the vector may change afterwards)
-int upload_unprimed(oww_ctx* ctx, std::vector<int>& ids, cudaStream_t s) {
-    ids.clear();
-    for (int b = 0; b < ctx->n_streams; ++b) if (!ctx->primed[b]) ids.push_back(b);
-    if (!ids.empty())
-        OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_unprimed_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-    return OWW_OK;
-}
-
-void mark_all_primed(oww_ctx* ctx) {
-    if (ctx->n_unprimed) { std::fill(ctx->primed.begin(), ctx->primed.end(), (uint8_t)1); ctx->n_unprimed = 0; }
-}
-
-__global__ void set_primed_kernel(uint8_t* primed, const int* ids, int n, int n_streams) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (ids) primed[ids[i]] = 1; else if (i < n_streams) primed[i] = 1;
-}
-
-// mel + full-window CNN (tails captured) + ring append for the listed streams only: the re-prime chain
-int reprime_subset(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_ids, cudaStream_t s) {
-    int rc;
-    MelLaunch m{d_pcm, pcm_stride, OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
-                (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, n_ids, 1, 1};
-    m.ids = ctx->d_unprimed_ids;
-    if ((rc = oww_mel_launch(ctx, m, s))) return rc;
-    WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, n_ids, 1};
-    ws.ids = ctx->d_unprimed_ids;
-    if ((rc = oww_cnn_window(ctx, ws, n_ids, ctx->d_emb_tmp, s, true))) return rc;
-    return oww_feat_append(ctx, ctx->d_emb_tmp, 1, s, ctx->d_unprimed_ids, n_ids);
-}
-
 int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chunks, float* d_scores, int out_stride,
               cudaStream_t s) {
     const int B = ctx->n_streams;
@@ -169,31 +168,16 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
     const bool inc = ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL;
     const FeatSrc fs0{ctx->d_feat_ring, (int64_t)ctx->feat_rows * 96, ctx->d_feat_count, ctx->feat_rows - 1, 0};
 
-    if (inc && n_chunks == 1 && ctx->n_unprimed < B && oww_fused_frontend_supported(ctx)) {
-        // ---- steady state: frontend + CNN + ring append of every primed stream in ONE launch ----
-        const bool partial = ctx->n_unprimed > 0;
-        const bool heads_inside = !partial && oww_fused_heads_supported(ctx);
+    if (inc && n_chunks == 1 && oww_fused_frontend_supported(ctx)) {
+        // ---- one chunk: frontend + CNN + ring append of every stream in ONE launch (fresh streams included: a reset
+        //      leaves the tails of the all-ones window behind, see reset_kernel) ----
+        const bool heads_inside = oww_fused_heads_supported(ctx);
         if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
-        std::vector<int> ids;
-        if (partial) {
-            // streams that were reset since the last step re-prime from a full window on a side stream (mel of their
-            // 5-row first chunk, full-window tcgen05 CNN with tail capture, ring append) while the fused kernel serves
-            // everyone else; both sides touch disjoint streams' state
-            if ((rc = upload_unprimed(ctx, ids, s))) return rc;
-            OWW_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
-            OWW_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-        }
-        if ((rc = oww_fused_step(ctx, d_pcm, pcm_stride, d_scores, out_stride, heads_inside, partial ? ctx->d_primed : nullptr, s)))
-            return rc;
-        if (partial) {
-            if ((rc = reprime_subset(ctx, d_pcm, pcm_stride, (int)ids.size(), ctx->side_stream))) return rc;
-            OWW_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
-            OWW_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
-            // only now (the fused kernel has finished reading the flags) do the re-primed streams count as primed
-            const int n_ids = (int)ids.size();
-            set_primed_kernel<<<(n_ids + 255) / 256, 256, 0, s>>>(ctx->d_primed, ctx->d_unprimed_ids, n_ids, ctx->n_streams);
-            OWW_LAUNCH_CHECK(ctx);
-            mark_all_primed(ctx);
+        if ((rc = oww_fused_step(ctx, d_pcm, pcm_stride, d_scores, out_stride, heads_inside, s))) return rc;
+        if (ctx->late_active) {
+            // cut plan: conv layers >= split_from run as their own launches (split operands) and the embedding is appended here
+            if ((rc = oww_late_chain(ctx, ctx->d_emb_tmp, s))) return rc;
+            if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, 1, s))) return rc;
         }
         if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
         if (!heads_inside && (rc = oww_heads_all(ctx, fs0, B, d_scores, out_stride, 0, s))) return rc;
@@ -205,25 +189,20 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
         return OWW_OK;
     }
 
-    // ---- general path: separate launches (modes 0 / 2, multi-chunk calls, or nothing primed yet) ----
+    // ---- general path: separate launches (modes 0 / 2, multi-chunk calls, --no-fuse) ----
     if (ev) { OWW_CUDA(ctx, cudaEventRecord(ev[0], s)); ctx->ev_fused[slot] = 0; }
     MelLaunch m{d_pcm, pcm_stride, n_chunks * OWW_SAMPLES_PER_CHUNK, ctx->d_tail, ctx->d_seen, ctx->d_mel_ring,
                 (int64_t)ctx->mel_rows * 32, ctx->mel_rows - 1, ctx->d_mel_count, B, 1, n_chunks};
     if ((rc = oww_mel_launch(ctx, m, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[1], s));
     WindowSrc ws{ctx->d_mel_ring, (int64_t)ctx->mel_rows * 32, ctx->d_mel_count, ctx->mel_rows - 1, B, n_chunks};
-    if (inc && ctx->n_unprimed == 0) {
-        // every stream primed: one incremental launch per chunk on the 8 new mel rows
+    if (inc) {
+        // one incremental launch per chunk on the 8 mel rows that chunk added (a fresh stream's first chunk added 5:
+        // the three rows before them are ones of its initial ring, which is what the step then reads)
         for (int i = 0; i < n_chunks; ++i)
             if ((rc = oww_cnn_inc_step(ctx, 8 * (n_chunks - 1 - i), ctx->d_emb_tmp + (size_t)i * B * 96, s))) return rc;
     } else {
-        // full windows for everyone (also the multi-chunk call that meets unprimed streams); mode 3 captures the tails
-        if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s, inc))) return rc;
-        if (inc && ctx->n_unprimed) {
-            set_primed_kernel<<<(B + 255) / 256, 256, 0, s>>>(ctx->d_primed, nullptr, B, B);
-            OWW_LAUNCH_CHECK(ctx);
-            mark_all_primed(ctx);
-        }
+        if ((rc = oww_cnn_window(ctx, ws, B * n_chunks, ctx->d_emb_tmp, s, false))) return rc;
     }
     if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, n_chunks, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
@@ -252,18 +231,31 @@ int reset_enqueue(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float*
     const bool have_init = h_feature_init && n_rows > 0;
     if (have_init)
         OWW_CUDA(ctx, cudaMemcpyAsync(ctx->d_reset_init, h_feature_init, (size_t)n_rows * 96 * sizeof(float), cudaMemcpyHostToDevice, s));
+    ResetTails rt;
+    std::memset(&rt, 0, sizeof(rt));
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL) {
+        if (!ctx->tails_template_valid) { int rc = oww_inc_build_template(ctx); if (rc) return rc; }
+        rt.tails = reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur]);      // the buffer the next step reads
+        rt.tmpl = reinterpret_cast<const uint4*>(ctx->d_tails_template);
+        rt.G = ctx->inc_plan.G; rt.tail_units = ctx->inc_plan.tail_units; rt.n_tab = ctx->n_tail_tab;
+        for (int k = 0; k < ctx->n_tail_tab; ++k) rt.tab[k] = ctx->tail_tab[k];
+        if (ctx->late_active) {
+            const long k = ctx->late_step;                      // index of the next chunk any stream processes
+            for (int l = ctx->split_from; l < OWW_N_CONV; ++l) {
+                const oww_ctx::LateTensor& X = ctx->late_x[l];
+                if (X.tmpl_off < 0) continue;
+                ResetLate& T = rt.late[rt.n_late++];
+                T.now = reinterpret_cast<uint4*>(X.buf[k % X.n_buf]);
+                T.next = X.n_buf == 3 ? reinterpret_cast<uint4*>(X.buf[(k + 1) % 3]) : nullptr;
+                T.tmpl = reinterpret_cast<const uint4*>(ctx->d_late_template) + X.tmpl_off;
+                T.plane = X.plane; T.T_buf = X.T_buf; T.Wp = X.W + 1; T.n_planes = 2 * X.cg;
+            }
+        }
+    }
     reset_kernel<<<n, 256, 0, s>>>(h_stream_ids ? ctx->d_reset_ids : nullptr, n, ctx->n_streams, ctx->d_tail, ctx->d_seen,
                                    ctx->d_mel_count, ctx->d_feat_count, ctx->d_mel_ring, ctx->mel_rows, ctx->d_feat_ring,
-                                   ctx->feat_rows, have_init ? ctx->d_reset_init : nullptr, n_rows, ctx->d_primed);
+                                   ctx->feat_rows, have_init ? ctx->d_reset_init : nullptr, n_rows, rt);
     OWW_LAUNCH_CHECK(ctx);
-    // a fresh stream's next window shifts by 5 rows, not 8: it re-primes from a full window at its next step
-    if (h_stream_ids) {
-        for (int i = 0; i < n; ++i)
-            if (ctx->primed[h_stream_ids[i]]) { ctx->primed[h_stream_ids[i]] = 0; ctx->n_unprimed++; }
-    } else {
-        std::fill(ctx->primed.begin(), ctx->primed.end(), (uint8_t)0);
-        ctx->n_unprimed = ctx->n_streams;
-    }
     return OWW_OK;
 }
 
@@ -304,12 +296,10 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
         delete ctx; return OWW_EUNSUPPORTED;
     }
     ctx->tc_heads = (cfg->reserved[0] & 2) == 0;
+    ctx->split_from = (cfg->reserved[1] >= 2 && cfg->reserved[1] <= OWW_N_CONV) ? cfg->reserved[1] : 11;
     ctx->tc_heads_terms = (cfg->reserved[0] & 4) ? 1 : 3;
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     fill_layer_table(ctx);
     *out = ctx;
     return OWW_OK;
@@ -320,20 +310,16 @@ void oww_destroy(oww_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->clip_ctx) { oww_ctx* c = ctx->clip_ctx; ctx->clip_ctx = nullptr; free_streams(c);
         cudaStreamDestroy(c->own_stream);
-        if (c->side_stream) cudaStreamDestroy(c->side_stream);
-        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-        if (c->ev_join) cudaEventDestroy(c->ev_join);
+        cudaFree(c->d_tails_template);
         cudaFree(c->d_tc_act[0]); cudaFree(c->d_tc_act[1]);
         cudaFree(c->slot[0].d_pcm); delete c; }
     free_streams(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
     cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
+    cudaFree(ctx->d_tc_w3); cudaFree(ctx->d_tc_sb3);
     cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w); cudaFree(ctx->d_head_devs);
     for (auto& h : ctx->heads) { cudaFree(h.d_blob); cudaFree(h.d_w1_tc); }
-    cudaFree(ctx->d_gates);
-    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    cudaFree(ctx->d_gates); cudaFree(ctx->d_tails_template);
     for (auto& S : ctx->slot) {
         cudaFreeHost(S.h_pcm); cudaFreeHost(S.h_scores); cudaFree(S.d_pcm); cudaFree(S.d_scores);
         if (S.done) cudaEventDestroy(S.done);
@@ -365,6 +351,7 @@ int oww_load_embedding(oww_ctx* ctx, const float* h_blob, size_t n_floats) {
         L.d_bias = ctx->d_emb_blob + off; off += L.cout;
     }
     ctx->emb_loaded = true;
+    ctx->tails_template_valid = false;                 // depends on the weights: rebuilt at the next reset
     int rc = oww_tc_pack_weights(ctx, h_blob);
     if (rc) return rc;
     return oww_inc_setup(ctx, h_blob);
@@ -409,7 +396,7 @@ int oww_add_head(oww_ctx* ctx, const oww_head_desc* desc, const float* h_blob, s
     OWW_CUDA(ctx, cudaMalloc(&h.d_blob, staged.size() * sizeof(float)));
     OWW_CUDA(ctx, cudaMemcpy(h.d_blob, staged.data(), staged.size() * sizeof(float), cudaMemcpyHostToDevice));
     {   // tensor-core packing of the first layer (heads_tc.cu); heads it does not cover keep tc_ok == false
-        int rc = oww_heads_tc_pack(ctx, h, staged.data() + h.w_off[0]);
+        int rc = oww_heads_tc_pack(ctx, h, staged.data());
         if (rc) { cudaFree(h.d_blob); return rc; }
     }
     h.n_out = desc->dims[desc->n_layers];
@@ -486,16 +473,13 @@ int oww_set_streams(oww_ctx* ctx, int n_streams) {
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_feat_count, (size_t)B * sizeof(int)));
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_mel_ring, (size_t)B * ctx->mel_rows * 32 * sizeof(float)));
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_feat_ring, (size_t)B * ctx->feat_rows * 96 * sizeof(float)));
-    OWW_CUDA(ctx, cudaMalloc(&ctx->d_primed, (size_t)B));
-    OWW_CUDA(ctx, cudaMemset(ctx->d_primed, 0, (size_t)B));
-    OWW_CUDA(ctx, cudaMalloc(&ctx->d_unprimed_ids, (size_t)B * sizeof(int)));
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_reset_ids, (size_t)B * sizeof(int)));
     OWW_CUDA(ctx, cudaMalloc(&ctx->d_reset_init, (size_t)ctx->feat_rows * 96 * sizeof(float)));
-    ctx->primed.assign(B, 0); ctx->n_unprimed = B;
     ctx->n_streams = B;
     int rc = ensure_act(ctx, (size_t)std::min(B * mc, ctx->window_batch) * 74 * 32 * 24);
     if (rc) return rc;
     if ((rc = ensure_emb_tmp(ctx, (size_t)B * mc * 96))) return rc;
+    if (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && (rc = oww_late_alloc(ctx))) return rc;
     if (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && (rc = oww_inc_alloc_streams(ctx))) return rc;
     return oww_reset(ctx, nullptr, B, nullptr, OWW_INIT_FEATURE_ROWS);
 }
@@ -696,17 +680,17 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
         c->window_batch = ctx->window_batch;
         c->fuse_step = ctx->fuse_step; c->tc_heads = ctx->tc_heads; c->tc_heads_terms = ctx->tc_heads_terms;
         cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
-        cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
         ctx->clip_ctx = c;
     }
     oww_ctx* c = ctx->clip_ctx;
     c->mel_loaded = ctx->mel_loaded; c->d_window = ctx->d_window; c->d_twiddle = ctx->d_twiddle;
     c->d_mel_start = ctx->d_mel_start; c->d_mel_len = ctx->d_mel_len; c->d_mel_w = ctx->d_mel_w; c->mel_kmax = ctx->mel_kmax;
+    if (c->emb_loaded != ctx->emb_loaded || c->d_inc_w != ctx->d_inc_w) c->tails_template_valid = false;
     c->emb_loaded = ctx->emb_loaded;
     for (int li = 0; li < OWW_N_CONV; ++li) { c->conv[li] = ctx->conv[li]; c->tc_w_off[li] = ctx->tc_w_off[li]; c->tc_sb_off[li] = ctx->tc_sb_off[li]; }
     c->d_tc_w = ctx->d_tc_w; c->d_tc_sb = ctx->d_tc_sb; c->d_inc_w = ctx->d_inc_w;
+    c->d_tc_w3 = ctx->d_tc_w3; c->d_tc_sb3 = ctx->d_tc_sb3; c->split_from = ctx->split_from;
+
     c->heads = ctx->heads; c->n_out_total = ctx->n_out_total; c->max_n_in = ctx->max_n_in; c->d_head_devs = ctx->d_head_devs;
     c->gates = ctx->gates; c->d_gates = ctx->d_gates;
     int rc = OWW_OK;
@@ -753,7 +737,7 @@ int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int
     oww_ctx local;                       // ctx may be NULL: the plan depends only on the fixed layer table
     if (!ctx) { fill_layer_table(&local); ctx = &local; }
     IncPlan P;
-    int rc = oww_inc_build_plan(ctx, group, n_streams, &P);
+    int rc = oww_inc_build_plan(ctx, group, n_streams, OWW_N_CONV, &P);
     if (rc) return rc;
     const int n = (int)(sizeof(IncPlan) / sizeof(int32_t));
     if (max_ints < n) return oww_fail(ctx, OWW_EINVAL, "need room for %d ints", n);
@@ -763,8 +747,8 @@ int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int
 
 int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_out21) {
     if (!ctx || !h_out21) return oww_fail(ctx, OWW_EINVAL, "null argument");
-    if (ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || ctx->n_unprimed)
-        return oww_fail(ctx, OWW_EINVAL, "needs cnn_mode 3 after at least one step");
+    if (ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || ctx->n_streams <= 0)
+        return oww_fail(ctx, OWW_EINVAL, "needs cnn_mode 3 with streams allocated");
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
     OWW_CUDA(ctx, cudaDeviceSynchronize());
     if (!ctx->d_inc_dbg) OWW_CUDA(ctx, cudaMalloc(&ctx->d_inc_dbg, 104 * sizeof(int64_t)));

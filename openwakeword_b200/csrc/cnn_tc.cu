@@ -20,13 +20,15 @@
 // 1 = TMEM allocator + single-thread MMA issuer, 2..5 = epilogue.  Persistent CTAs, grid = #SMs.
 #include "oww_internal.h"
 #include "tc_common.cuh"
+#include <cmath>
+#include <cstring>
 
 namespace {
 
 // ---------------------------------------------------------------- layer 0 (CUDA cores) -> fp16 planes
 struct Tc0Args {
     WindowSrc src;
-    int n_windows;
+    int n_windows; int T_out;         // output rows per window (input rows - 2): 74 for the 76-row window
     const float* w; const float* scale; const float* bias;
     __half* out; int64_t plane;       // units per plane
 };
@@ -37,7 +39,8 @@ __global__ void __launch_bounds__(256) tc_conv0_kernel(Tc0Args a) {
     for (int i = threadIdx.x; i < 9 * 24; i += 256) s_w[i] = a.w[i];
     if (threadIdx.x < 24) { s_s[threadIdx.x] = a.scale[threadIdx.x]; s_b[threadIdx.x] = a.bias[threadIdx.x]; }
     __syncthreads();
-    constexpr int T = 74, Wp = 33;
+    constexpr int Wp = 33;
+    const int T = a.T_out;
     const int64_t total = (int64_t)a.n_windows * T * Wp;
     for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < total; p += (int64_t)gridDim.x * 256) {
         const int f = (int)(p % Wp);
@@ -111,14 +114,29 @@ struct TcConvArgs {
     int apply_act;
     int64_t p_in;                           // n*T*(W+1)
     int n_tiles;
+    int out_split;                          // 1: write fp16 hi planes [0, cg_out) and lo planes [cg_out, 2 cg_out) (y = hi + lo)
+    int64_t rows_out;                       // final layer: embedding rows per window (T_out valid rows; fully convolutional clips)
+    // incremental late layers (cnn_tc_late.cu): the output rows land at row offset out_toff inside buffers that hold
+    // out_T rows per stream (tails in front), and are mirrored into up to two further buffers where they will serve as
+    // tails of later steps.  out_T == 0: plain layout (out_T = T_out, no offset, no mirrors).
+    int out_T, out_toff;
+    __half* out_b[2]; int out_b_toff[2];    // mirrors (nullptr = unused); same plane pitch as `out`
 };
 
-template <int CGP, int NP>
+// TERMS = 1: fp16 operands.  TERMS = 3: split operands - the input holds hi planes [0, cg_in) and lo planes
+// [cg_in, 2 cg_in), the weights hi and lo blocks of W * 2^s (2^-s folded into `scale`), and every K step issues
+// hi*hi + lo*hi + hi*lo into the same fp32 accumulator: the product is fp32-grade (~2^-21), at 3x the MMAs, 2x the
+// operand bytes and half the pipeline stages.
+template <int CGP, int NP, int TERMS>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int W_BYTES = 3 * CGP * NP * 16;
+    constexpr int kSplit = TERMS == 3 ? 2 : 1;
+    constexpr int kStages = TERMS == 3 ? 2 : 4;
+    constexpr int W_TERM = 3 * CGP * NP * 16;
+    constexpr int W_BYTES = kSplit * W_TERM;
     uint8_t* w_smem = smem;
-    const int stage_bytes = CGP * a.rows * 16;
+    const int term_bytes = CGP * a.rows * 16;
+    const int stage_bytes = kSplit * term_bytes;
     uint8_t* a_smem = smem + W_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + kStages * stage_bytes);
     // bars: [0..S) full, [S..2S) empty, [2S..2S+A) tmem_full, [..+A) tmem_empty, then w_full
@@ -140,8 +158,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
     }
     // zero the pad planes of every A stage once (never overwritten by the bulk copies)
     if (a.cg_in < CGP) {
-        for (int s = 0; s < kStages; ++s) {
-            uint4* pz = reinterpret_cast<uint4*>(a_smem + s * stage_bytes + a.cg_in * a.rows * 16);
+        for (int s = 0; s < kStages * kSplit; ++s) {
+            uint4* pz = reinterpret_cast<uint4*>(a_smem + s * term_bytes + a.cg_in * a.rows * 16);
             for (int i = threadIdx.x; i < (CGP - a.cg_in) * a.rows; i += kTcThreads) pz[i] = make_uint4(0, 0, 0, 0);
         }
     }
@@ -164,11 +182,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
             const uint32_t plane_bytes = (uint32_t)a.rows * 16u;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
-                mbar_expect_tx(full_bar(stage), plane_bytes * a.cg_in);
+                mbar_expect_tx(full_bar(stage), plane_bytes * a.cg_in * kSplit);
                 const int64_t u0 = kGuard + (int64_t)tile * 128 - a.lo;
-                for (int g = 0; g < a.cg_in; ++g)
-                    bulk_g2s(smem_u32(a_smem + stage * stage_bytes + g * plane_bytes),
-                             reinterpret_cast<const uint4*>(a.in) + g * a.in_plane + u0, plane_bytes, full_bar(stage));
+                for (int t = 0; t < kSplit; ++t)
+                    for (int g = 0; g < a.cg_in; ++g)
+                        bulk_g2s(smem_u32(a_smem + stage * stage_bytes + t * term_bytes + g * plane_bytes),
+                                 reinterpret_cast<const uint4*>(a.in) + (int64_t)(t * a.cg_in + g) * a.in_plane + u0, plane_bytes, full_bar(stage));
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -191,10 +210,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 for (int j = 0; j < 3; ++j) {
 #pragma unroll
                     for (int q = 0; q < CGP / 2; ++q) {
-                        const uint64_t ad = make_desc(a_addr + (uint32_t)(2 * q * a.rows + a.tap_off[j]) * 16u, lbo_a, 128u);
-                        const uint64_t bd = make_desc(w_addr + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
-                        tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
-                        accumulate = 1;
+#pragma unroll
+                        for (int t = 0; t < TERMS; ++t) {        // (hi,hi) (lo,hi) (hi,lo)
+                            const uint32_t a_t = a_addr + (t == 1 ? (uint32_t)term_bytes : 0u);
+                            const uint32_t w_t = w_addr + (t == 2 ? (uint32_t)W_TERM : 0u);
+                            const uint64_t ad = make_desc(a_t + (uint32_t)(2 * q * a.rows + a.tap_off[j]) * 16u, lbo_a, 128u);
+                            const uint64_t bd = make_desc(w_t + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
+                            tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
+                            accumulate = 1;
+                        }
                     }
                 }
                 tc_commit(empty_bar(stage));
@@ -232,7 +256,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
             if (t >= a.T_out) continue;
             if (a.out_f32) {
                 if (f != 0) continue;
-                float* o = a.out_f32 + (int64_t)n * 96;
+                float* o = a.out_f32 + ((int64_t)n * a.rows_out + t) * 96;
 #pragma unroll
                 for (int c = 0; c < 96 && c < NP; c += 4) {
                     float4 r4;
@@ -244,23 +268,39 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 }
                 continue;
             }
-            const int64_t po = (int64_t)n * per_out + (int64_t)t * Wp + f;
+            const int64_t po = a.out_T ? (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_toff) * Wp + f
+                                       : (int64_t)n * per_out + (int64_t)t * Wp + f;
             uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + po;
             const bool pad = f == a.W;
 #pragma unroll
             for (int g = 0; g < NP / 8; ++g) {
-                __half2 h[4];
+                __half2 h[4], l[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int c = g * 8 + u * 2;
                     float y0 = fmaf(__uint_as_float(v[c]), __ldg(a.scale + c), __ldg(a.bias + c));
                     float y1 = fmaf(__uint_as_float(v[c + 1]), __ldg(a.scale + c + 1), __ldg(a.bias + c + 1));
                     if (a.apply_act) { y0 = act(y0); y1 = act(y1); }
-                    h[u] = pad ? __floats2half2_rn(0.f, 0.f) : __floats2half2_rn(y0, y1);
+                    if (pad) { y0 = 0.f; y1 = 0.f; }
+                    const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+                    h[u] = __halves2half2(h0, h1);
+                    l[u] = __floats2half2_rn(y0 - __half2float(h0), y1 - __half2float(h1));
                 }
                 if (g < a.cg_out) {
                     o[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
                     if (po == 0) o[(int64_t)g * a.out_plane - 1] = make_uint4(0, 0, 0, 0);   // front guard (position -1)
+                    if (a.out_split) {
+                        o[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
+                        if (po == 0) o[(int64_t)(a.cg_out + g) * a.out_plane - 1] = make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (a.out_b[k]) {
+                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[k]) + kGuard + (int64_t)n * a.out_T * Wp +
+                                        (int64_t)(t + a.out_b_toff[k]) * Wp + f;
+                            ob[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
+                            if (a.out_split) ob[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
+                        }
                 }
             }
         }
@@ -274,8 +314,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
 }
 
 // ---------------------------------------------------------------- max-pool on fp16 planes
-__global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t in_plane, __half* out, int64_t out_plane,
-                                                      int n, int t_in, int w_in, int cg, int pt, int pf) {
+// split != 0: planes [0, cg) hold hi parts and [cg, 2cg) lo parts of the same values; the pooled element is the one
+// with the largest hi + lo, i.e. the lexicographic maximum of (hi, lo) since |lo| <= ulp(hi)/2.
+struct PoolOut { __half* p[3]; int toff[3]; int out_T; };     // out_T == 0: plain [n][t_out][wp_out] into p[0]
+__global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t in_plane, PoolOut po, int64_t out_plane,
+                                                      int n, int t_in, int w_in, int cg, int pt, int pf, int split) {
+    __half* const out = po.p[0];
     const int t_out = t_in / pt, w_out = w_in / pf;
     const int wp_in = w_in + 1, wp_out = w_out + 1;
     const int64_t per_out = (int64_t)t_out * wp_out;
@@ -287,28 +331,49 @@ __global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t 
         const int64_t r = p / wp_out;
         const int t = (int)(r % t_out);
         const int64_t s = r / t_out;
-        uint4 res = make_uint4(0, 0, 0, 0);
+        uint4 res = make_uint4(0, 0, 0, 0), res_lo = make_uint4(0, 0, 0, 0);
         if (f < w_out) {
-            __half2 m[4];
+            __half mh[8], ml[8];
             bool first = true;
             for (int da = 0; da < pt; ++da)
                 for (int db = 0; db < pf; ++db) {
                     const int64_t pi = s * (int64_t)t_in * wp_in + (int64_t)(t * pt + da) * wp_in + (f * pf + db);
                     const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + (int64_t)g * in_plane + kGuard + pi);
-                    const __half2* hv = reinterpret_cast<const __half2*>(&v);
+                    uint4 vl = make_uint4(0, 0, 0, 0);
+                    if (split) vl = __ldg(reinterpret_cast<const uint4*>(in) + (int64_t)(cg + g) * in_plane + kGuard + pi);
+                    const __half* hv = reinterpret_cast<const __half*>(&v);
+                    const __half* lv = reinterpret_cast<const __half*>(&vl);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) m[u] = first ? hv[u] : __hmax2(m[u], hv[u]);
+                    for (int u = 0; u < 8; ++u) {
+                        const bool take = first || __hgt(hv[u], mh[u]) || (__heq(hv[u], mh[u]) && __hgt(lv[u], ml[u]));
+                        if (take) { mh[u] = hv[u]; ml[u] = lv[u]; }
+                    }
                     first = false;
                 }
-            res = *reinterpret_cast<uint4*>(m);
+            res = *reinterpret_cast<uint4*>(mh);
+            res_lo = *reinterpret_cast<uint4*>(ml);
         }
-        reinterpret_cast<uint4*>(out)[(int64_t)g * out_plane + kGuard + p] = res;
-        if (p == 0) reinterpret_cast<uint4*>(out)[(int64_t)g * out_plane + kGuard - 1] = make_uint4(0, 0, 0, 0);
+        if (po.out_T == 0) {
+            reinterpret_cast<uint4*>(out)[(int64_t)g * out_plane + kGuard + p] = res;
+            if (p == 0) reinterpret_cast<uint4*>(out)[(int64_t)g * out_plane + kGuard - 1] = make_uint4(0, 0, 0, 0);
+            if (split) {
+                reinterpret_cast<uint4*>(out)[(int64_t)(cg + g) * out_plane + kGuard + p] = res_lo;
+                if (p == 0) reinterpret_cast<uint4*>(out)[(int64_t)(cg + g) * out_plane + kGuard - 1] = make_uint4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (po.p[k]) {
+                    const int64_t q = kGuard + (s * po.out_T + t + po.toff[k]) * wp_out + f;
+                    reinterpret_cast<uint4*>(po.p[k])[(int64_t)g * out_plane + q] = res;
+                    if (split) reinterpret_cast<uint4*>(po.p[k])[(int64_t)(cg + g) * out_plane + q] = res_lo;
+                }
+        }
     }
 }
 
 // planes -> NHWC fp32 (debug / parity only)
-__global__ void tc_unpack_kernel(const __half* in, int64_t plane, float* out, int n, int t, int w, int c) {
+__global__ void tc_unpack_kernel(const __half* in, int64_t plane, float* out, int n, int t, int w, int c, int split) {
     const int wp = w + 1;
     const int64_t total = (int64_t)n * t * w * c;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -318,7 +383,9 @@ __global__ void tc_unpack_kernel(const __half* in, int64_t plane, float* out, in
         const int tt = (int)(r % t);
         const int64_t s = r / t;
         const int64_t p = s * (int64_t)t * wp + (int64_t)tt * wp + f;
-        out[i] = __half2float(in[((int64_t)(ch >> 3) * plane + kGuard + p) * 8 + (ch & 7)]);
+        float v = __half2float(in[((int64_t)(ch >> 3) * plane + kGuard + p) * 8 + (ch & 7)]);
+        if (split) v += __half2float(in[((int64_t)(c / 8 + (ch >> 3)) * plane + kGuard + p) * 8 + (ch & 7)]);
+        out[i] = v;
     }
 }
 
@@ -326,36 +393,39 @@ struct TcLayerGeom { int T, W, cg, cgp, np, T_out, rows, lo, tap_off[3]; };
 
 inline int round8(int v) { return (v + 7) & ~7; }
 
-template <int CGP, int NP>
+template <int CGP, int NP, int TERMS>
 int launch_tc(oww_ctx* ctx, const TcConvArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)3 * CGP * NP * 16 + (size_t)kStages * CGP * a.rows * 16 + 8 * (2 * kStages + 2 * kAccStages + 1) + 16;
+    constexpr int split = TERMS == 3 ? 2 : 1, stages = TERMS == 3 ? 2 : 4;
+    const size_t smem = (size_t)split * 3 * CGP * NP * 16 + (size_t)stages * split * CGP * a.rows * 16 +
+                        8 * (2 * stages + 2 * kAccStages + 1) + 16;
+    if (smem > 227 * 1024) return oww_fail(ctx, OWW_EUNSUPPORTED, "tcgen05 conv tile does not fit shared memory (%zu bytes)", smem);
     // the attribute is per (function, device): tracked per handle (one bit per kernel instance), not per process
-    const uint32_t bit = 1u << ((CGP / 2 + NP / 16) & 31);       // distinct for the seven instances in use
+    const uint32_t bit = 1u << (((CGP / 2 + NP / 16) + (TERMS == 3 ? 16 : 0)) & 31);     // distinct for the instances in use
     if (!(ctx->tc_attr_mask & bit)) {
-        OWW_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<CGP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        OWW_CUDA(ctx, cudaFuncSetAttribute(tc_conv_kernel<CGP, NP, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_mask |= bit;
     }
     int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
-    tc_conv_kernel<CGP, NP><<<grid, kTcThreads, smem, s>>>(a);
+    tc_conv_kernel<CGP, NP, TERMS><<<grid, kTcThreads, smem, s>>>(a);
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }
 
 }  // namespace
 
-// Host-side packing: fp16 weights [3][CGP][NP][8] + padded scale/bias per layer 1..19.
+// Host-side packing per layer 1..19: fp16 weights [3][CGP][NP][8] + padded scale/bias (TERMS = 1), and for the split
+// variant the hi and lo blocks of W * 2^s (s per layer: max |W| * 2^s in [2^13, 2^14), so the lo parts are normal fp16
+// numbers) with 2^-s folded exactly into the scale.
 int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob) {
     size_t off = 0, total_h = 0, total_f = 0;
-    for (int li = 0; li < OWW_N_CONV; ++li) {
+    for (int li = 1; li < OWW_N_CONV; ++li) {
         const ConvLayer& L = ctx->conv[li];
-        if (li > 0) {
-            const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
-            total_h += (size_t)3 * cgp * np * 8;
-            total_f += 2 * (size_t)np;
-        }
+        const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
+        total_h += (size_t)3 * cgp * np * 8;
+        total_f += 2 * (size_t)np;
     }
-    std::vector<__half> hw(total_h);
-    std::vector<float> hf(total_f);
+    std::vector<__half> hw(total_h), hw3(2 * total_h);
+    std::vector<float> hf(total_f), hf3(total_f);
     size_t oh = 0, of = 0;
     for (int li = 0; li < OWW_N_CONV; ++li) {
         const ConvLayer& L = ctx->conv[li];
@@ -365,68 +435,114 @@ int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob) {
         if (li == 0) continue;
         const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
         ctx->tc_w_off[li] = oh; ctx->tc_sb_off[li] = of;
+        float amax = 0.f;
+        for (size_t i = 0; i < nw; ++i) amax = std::fmax(amax, std::fabs(w[i]));
+        int sexp = 0;
+        if (amax > 0.f && std::isfinite(amax)) { int e; std::frexp(amax, &e); sexp = 14 - e; if (sexp > 24) sexp = 24; if (sexp < -8) sexp = -8; }
+        const float up = std::ldexp(1.0f, sexp), down = std::ldexp(1.0f, -sexp);
+        const size_t term = (size_t)3 * cgp * np * 8;
         for (int j = 0; j < 3; ++j)
             for (int g = 0; g < cgp; ++g)
                 for (int n = 0; n < np; ++n)
                     for (int e = 0; e < 8; ++e) {
                         const int c = g * 8 + e;
                         const float v = (c < L.cin && n < L.cout) ? w[((size_t)j * L.cin + c) * L.cout + n] : 0.f;
-                        hw[oh + (((size_t)j * cgp + g) * np + n) * 8 + e] = __float2half_rn(v);
+                        const size_t at = (((size_t)j * cgp + g) * np + n) * 8 + e;
+                        hw[oh + at] = __float2half_rn(v);
+                        const __half hi = __float2half_rn(v * up);
+                        hw3[2 * oh + at] = hi;
+                        hw3[2 * oh + term + at] = __float2half_rn(v * up - __half2float(hi));
                     }
-        oh += (size_t)3 * cgp * np * 8;
-        for (int n = 0; n < np; ++n) { hf[of + n] = n < L.cout ? sc[n] : 0.f; hf[of + np + n] = n < L.cout ? bi[n] : 0.f; }
+        oh += term;
+        for (int n = 0; n < np; ++n) {
+            hf[of + n] = n < L.cout ? sc[n] : 0.f; hf[of + np + n] = n < L.cout ? bi[n] : 0.f;
+            hf3[of + n] = hf[of + n] * down; hf3[of + np + n] = hf[of + np + n];
+        }
         of += 2 * (size_t)np;
     }
     if (!ctx->d_tc_w) OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_w, total_h * sizeof(__half)));
     if (!ctx->d_tc_sb) OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_sb, total_f * sizeof(float)));
+    if (!ctx->d_tc_w3) OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_w3, 2 * total_h * sizeof(__half)));
+    if (!ctx->d_tc_sb3) OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_sb3, total_f * sizeof(float)));
     OWW_CUDA(ctx, cudaMemcpy(ctx->d_tc_w, hw.data(), total_h * sizeof(__half), cudaMemcpyHostToDevice));
     OWW_CUDA(ctx, cudaMemcpy(ctx->d_tc_sb, hf.data(), total_f * sizeof(float), cudaMemcpyHostToDevice));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_tc_w3, hw3.data(), 2 * total_h * sizeof(__half), cudaMemcpyHostToDevice));
+    OWW_CUDA(ctx, cudaMemcpy(ctx->d_tc_sb3, hf3.data(), total_f * sizeof(float), cudaMemcpyHostToDevice));
     return OWW_OK;
 }
 
-size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows) {
-    // largest footprint over all layer outputs: planes * plane pitch, in 16-byte units
+// Largest footprint over all layer outputs of a pass over n inputs of T0 mel rows: planes * plane pitch, in 16-byte
+// units (tensors feeding a split layer hold hi and lo planes).
+size_t oww_tc_act_units_T(const oww_ctx* ctx, int n, int T0) {
     size_t best = 0;
-    int T = 76, W = 32;
-    auto upd = [&](int t, int w, int c) {
-        const size_t plane = ((size_t)kGuard + (size_t)n_windows * t * (w + 1) + kGuardBack + 7) & ~(size_t)7;
-        const size_t tot = (size_t)(c / 8) * plane;
+    int T = T0, W = 32;
+    auto upd = [&](int t, int w, int c, int mult) {
+        const size_t plane = ((size_t)kGuard + (size_t)n * t * (w + 1) + kGuardBack + 7) & ~(size_t)7;
+        const size_t tot = (size_t)(c / 8) * mult * plane;
         if (tot > best) best = tot;
     };
     for (int li = 0; li < OWW_N_CONV; ++li) {
         const ConvLayer& L = ctx->conv[li];
+        const int mult = li + 1 >= ctx->split_from ? 2 : 1;
         T -= (L.kh - 1);
-        upd(T, W, L.cout);
-        if (L.pool_t) { T /= L.pool_t; W /= L.pool_f; upd(T, W, L.cout); }
+        upd(T, W, L.cout, mult);
+        if (L.pool_t) { T /= L.pool_t; W /= L.pool_f; upd(T, W, L.cout, mult); }
     }
     return best + 64;
 }
+size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows) { return oww_tc_act_units_T(ctx, n_windows, OWW_WINDOW_ROWS); }
 
-// Runs the pyramid in tensor-core mode on n windows (n <= ctx->window_batch); d_emb [n][96] fp32.
-// stop_layer >= 0: stop after that layer (and its pool) and unpack it to NHWC fp32 in d_dbg.
-int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg,
-                            const TailCapture* cap, cudaStream_t s);
+// Runs the pyramid in tensor-core mode on n inputs of T0 mel rows each (n windows of 76 rows, or n clips: the CNN is
+// fully convolutional in time) -> d_emb [n][(T0 - 76) / 8 + 1][96] fp32.  Layers >= split_from take split
+// (hi/lo) operands.  stop_layer >= 0: stop after that layer (and its pool) and unpack it to NHWC fp32 in d_dbg.
+int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, int T0, int split_from, float* d_emb, int stop_layer,
+                            float* d_dbg, const TailCapture* cap, cudaStream_t s);
 int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s) {
-    return oww_cnn_tc_pyramid_impl(ctx, src, n, d_emb, stop_layer, d_dbg, nullptr, s);
+    return oww_cnn_tc_pyramid_impl(ctx, src, n, OWW_WINDOW_ROWS, ctx->split_from, d_emb, stop_layer, d_dbg, nullptr, s);
 }
 int oww_cnn_tc_pyramid_cap(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, const TailCapture* cap, cudaStream_t s) {
-    return oww_cnn_tc_pyramid_impl(ctx, src, n, d_emb, -1, nullptr, cap, s);
+    // tails of the layers inside the fused kernel (all below split_from: plain fp16 there as here) go to the group
+    // layout through oww_inc_capture; tails of the incremental late layers (hi/lo) to the late template
+    return oww_cnn_tc_pyramid_impl(ctx, src, n, OWW_WINDOW_ROWS, ctx->split_from, d_emb, -1, nullptr, cap, s);
 }
-int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg,
-                            const TailCapture* cap, cudaStream_t s) {
+int oww_cnn_tc_clip(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s) {
+    WindowSrc src{d_mel, (int64_t)T * 32, nullptr, -1, 0, 0};
+    const int W = (T - OWW_WINDOW_ROWS) / 8 + 1;
+    return oww_cnn_tc_pyramid_impl(ctx, src, n, OWW_WINDOW_ROWS + 8 * (W - 1), ctx->split_from, d_emb, -1, nullptr, nullptr, s);
+}
+
+template <int TERMS>
+static int dispatch_tc(oww_ctx* ctx, int cgp, int np, const TcConvArgs& a, cudaStream_t s) {
+    if (cgp == 4 && np == 32) return launch_tc<4, 32, TERMS>(ctx, a, s);
+    if (cgp == 4 && np == 48) return launch_tc<4, 48, TERMS>(ctx, a, s);
+    if (cgp == 6 && np == 48) return launch_tc<6, 48, TERMS>(ctx, a, s);
+    if (cgp == 6 && np == 80) return launch_tc<6, 80, TERMS>(ctx, a, s);
+    if (cgp == 10 && np == 80) return launch_tc<10, 80, TERMS>(ctx, a, s);
+    if (cgp == 10 && np == 96) return launch_tc<10, 96, TERMS>(ctx, a, s);
+    if (cgp == 12 && np == 96) return launch_tc<12, 96, TERMS>(ctx, a, s);
+    return oww_fail(ctx, OWW_EUNSUPPORTED, "no tcgen05 conv instance for cgp=%d np=%d", cgp, np);
+}
+
+int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, int T0, int split_from, float* d_emb, int stop_layer,
+                            float* d_dbg, const TailCapture* cap, cudaStream_t s) {
+    if (oww_tc_act_units_T(ctx, n, T0) > ctx->tc_act_units)
+        return oww_fail(ctx, OWW_ENOMEM, "tensor-core activation scratch too small for %d x %d rows", n, T0);
     __half* bufs[2] = {reinterpret_cast<__half*>(ctx->d_tc_act[0]), reinterpret_cast<__half*>(ctx->d_tc_act[1])};
     int cur = 0;
-    int T = 76, W = 32;
+    int T = T0, W = 32;
     auto plane_units = [&](int t, int w) { return (int64_t)((kGuard + (int64_t)n * t * (w + 1) + kGuardBack + 7) & ~7LL); };
     int64_t in_plane = 0;
     for (int li = 0; li < OWW_N_CONV; ++li) {
         const ConvLayer& L = ctx->conv[li];
         const int T_out = T - (L.kh - 1);
         const bool last = li == OWW_N_CONV - 1;
+        const bool in_split = li >= split_from;              // this layer takes hi/lo operands
+        const bool out_split = li + 1 >= split_from && !last; // the tensor it leaves feeds a split layer
         const int64_t out_plane = plane_units(T_out, W);
         if (li == 0) {
-            Tc0Args a{src, n, L.d_w, L.d_scale, L.d_bias, bufs[cur], out_plane};
-            const int64_t total = (int64_t)n * 74 * 33;
+            if (out_split) return oww_fail(ctx, OWW_EUNSUPPORTED, "split_from must be >= 2");
+            Tc0Args a{src, n, T_out, L.d_w, L.d_scale, L.d_bias, bufs[cur], out_plane};
+            const int64_t total = (int64_t)n * T_out * 33;
             unsigned grid = (unsigned)((total + 255) / 256);
             if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
             tc_conv0_kernel<<<grid, 256, 0, s>>>(a);
@@ -435,26 +551,27 @@ int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_
             const int cg = L.cin / 8, cgp = (cg + 1) & ~1, np = (L.cout + 15) & ~15;
             const int Wp = W + 1;
             TcConvArgs a;
+            std::memset(&a, 0, sizeof(a));
             a.in = bufs[cur ^ 1]; a.in_plane = in_plane;
             a.out = bufs[cur]; a.out_plane = out_plane;
             a.out_f32 = last ? d_emb : nullptr;
-            a.w = reinterpret_cast<const __half*>(ctx->d_tc_w) + ctx->tc_w_off[li];
-            a.scale = ctx->d_tc_sb + ctx->tc_sb_off[li]; a.bias = a.scale + np;
+            if (in_split) {
+                a.w = reinterpret_cast<const __half*>(ctx->d_tc_w3) + 2 * ctx->tc_w_off[li];
+                a.scale = ctx->d_tc_sb3 + ctx->tc_sb_off[li];
+            } else {
+                a.w = reinterpret_cast<const __half*>(ctx->d_tc_w) + ctx->tc_w_off[li];
+                a.scale = ctx->d_tc_sb + ctx->tc_sb_off[li];
+            }
+            a.bias = a.scale + np;
             a.n = n; a.T = T; a.W = W; a.T_out = T_out;
             if (L.kw == 3) { a.lo = 1; a.tap_off[0] = 0; a.tap_off[1] = 1; a.tap_off[2] = 2; a.rows = round8(128 + 2); }
             else { a.lo = 0; a.tap_off[0] = 0; a.tap_off[1] = Wp; a.tap_off[2] = 2 * Wp; a.rows = round8(128 + 2 * Wp); }
             a.cg_in = cg; a.cg_out = L.cout / 8; a.apply_act = last ? 0 : 1;
             a.p_in = (int64_t)n * T * Wp;
             a.n_tiles = (int)((a.p_in + 127) / 128);
-            int rc;
-            if (cgp == 4 && np == 32) rc = launch_tc<4, 32>(ctx, a, s);
-            else if (cgp == 4 && np == 48) rc = launch_tc<4, 48>(ctx, a, s);
-            else if (cgp == 6 && np == 48) rc = launch_tc<6, 48>(ctx, a, s);
-            else if (cgp == 6 && np == 80) rc = launch_tc<6, 80>(ctx, a, s);
-            else if (cgp == 10 && np == 80) rc = launch_tc<10, 80>(ctx, a, s);
-            else if (cgp == 10 && np == 96) rc = launch_tc<10, 96>(ctx, a, s);
-            else if (cgp == 12 && np == 96) rc = launch_tc<12, 96>(ctx, a, s);
-            else rc = oww_fail(ctx, OWW_EUNSUPPORTED, "no tcgen05 conv instance for cgp=%d np=%d", cgp, np);
+            a.out_split = out_split ? 1 : 0;
+            a.rows_out = T_out;
+            int rc = in_split ? dispatch_tc<3>(ctx, cgp, np, a, s) : dispatch_tc<1>(ctx, cgp, np, a, s);
             if (rc) return rc;
         }
         T = T_out; in_plane = out_plane; cur ^= 1;
@@ -465,7 +582,8 @@ int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_
             const int64_t total = (int64_t)n * T2 * (W2 + 1) * cgo;
             unsigned grid = (unsigned)((total + 255) / 256);
             if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
-            tc_pool_kernel<<<grid, 256, 0, s>>>(bufs[cur ^ 1], in_plane, bufs[cur], op, n, T, W, cgo, L.pool_t, L.pool_f);
+            PoolOut pout{{bufs[cur], nullptr, nullptr}, {0, 0, 0}, 0};
+            tc_pool_kernel<<<grid, 256, 0, s>>>(bufs[cur ^ 1], in_plane, pout, op, n, T, W, cgo, L.pool_t, L.pool_f, out_split ? 1 : 0);
             OWW_LAUNCH_CHECK(ctx);
             T = T2; W = W2; in_plane = op; cur ^= 1;
         }
@@ -473,13 +591,165 @@ int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, float* d_
             // the tensor just produced feeds layer li+1; if that is a (3,1) conv its last two rows are the tails
             int rc = oww_inc_capture(ctx, li, bufs[cur ^ 1], in_plane, T, W, cap->win0, cap->n_win, cap->stream0, cap->ids, s);
             if (rc) return rc;
+            if (cap->late && (rc = oww_late_capture(ctx, li + 1, bufs[cur ^ 1], in_plane, T, W, s))) return rc;
         }
         if (li == stop_layer && !last) {
             const int64_t total = (int64_t)n * T * W * L.cout;
-            tc_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bufs[cur ^ 1], in_plane, d_dbg, n, T, W, L.cout);
+            tc_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(bufs[cur ^ 1], in_plane, d_dbg, n, T, W, L.cout, out_split ? 1 : 0);
             OWW_LAUNCH_CHECK(ctx);
             return OWW_OK;
         }
     }
+    return OWW_OK;
+}
+
+// ================================================================================================
+// Incremental late layers (cnn_mode 3 with split_from < 20).
+//
+// The fused step kernel (cnn_tc_inc.cu) runs the frontend and conv layers 0 .. L0-1 of the 8 new mel rows in shared
+// memory and leaves the pooled output of layer L0-1 (2 new rows per stream at L0 = 11) in HBM as fp16 hi/lo planes.
+// Layers L0 .. 19 - 1.3 of the 5.6 MMAC per frame, but the ones whose fp16 rounding dominates the embedding error -
+// then run here as the SAME tcgen05 conv / pool kernels as the window mode, with split (hi/lo) operands, on "windows"
+// that are the incremental rows of every stream: a (3,1) layer's input holds [2 tail rows | new rows] per stream, and
+// every layer mirrors its new rows into the buffer(s) where they are tails of the following step(s) (two buffers for
+// tensors that gain two rows per step, three for the one that gains a single row), so no copy or shift pass exists.
+// A reset writes the tails of the all-ones window (template) into the slots the stream's next step reads.
+// ================================================================================================
+namespace {
+
+__global__ void late_capture_kernel(const uint4* planes, int64_t plane_pitch, int T, int Wp, int n_planes, uint4* tmpl) {
+    // last two rows of window 0 of every plane -> tmpl[plane][row][f]
+    const int total = n_planes * 2 * Wp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int f = i % Wp, r = (i / Wp) % 2, pl = i / (2 * Wp);
+        tmpl[i] = planes[(int64_t)pl * plane_pitch + kGuard + (int64_t)(T - 2 + r) * Wp + f];
+    }
+}
+
+}  // namespace
+
+int oww_late_alloc(oww_ctx* ctx) {
+    // geometry of the incremental tensors X_l (input of conv layer l), l = L0 .. 19
+    for (auto& X : ctx->late_x) for (auto& b : X.buf) { cudaFree(b); b = nullptr; }
+    for (auto& b : ctx->d_late_tmp) { cudaFree(b); b = nullptr; }
+    cudaFree(ctx->d_late_template); ctx->d_late_template = nullptr;
+    ctx->late_active = false;
+    const int L0 = ctx->split_from;
+    if (ctx->cfg.cnn_mode != OWW_CNN_TC_INCREMENTAL || L0 >= OWW_N_CONV) return OWW_OK;
+    if (L0 < 2 || ctx->conv[L0].kh != 1 || !ctx->conv[L0 - 1].pool_t)
+        return oww_fail(ctx, OWW_EUNSUPPORTED, "split_from=%d: the incremental split must start at a (1,3) layer that follows a pool (3, 7, 11, 15)", L0);
+    const int n = ctx->n_streams;
+    int rows = 8, W = 32;
+    for (int l = 0; l < L0; ++l) if (ctx->conv[l].pool_t) { rows /= ctx->conv[l].pool_t; W /= ctx->conv[l].pool_f; }
+    size_t tmpl_units = 0, tmp_units = 0;
+    for (int l = L0; l < OWW_N_CONV; ++l) {
+        const ConvLayer& C = ctx->conv[l];
+        oww_ctx::LateTensor& X = ctx->late_x[l];
+        const bool kh3 = C.kh == 3;
+        X.rows_new = rows; X.W = W; X.cg = C.cin / 8;
+        X.T_buf = rows + (kh3 ? 2 : 0);
+        X.n_buf = kh3 ? (rows == 1 ? 3 : 2) : 1;
+        X.plane = (int64_t)((kGuard + (int64_t)n * X.T_buf * (W + 1) + kGuardBack + 7) & ~7LL);
+        X.tmpl_off = kh3 ? (int)tmpl_units : -1;
+        if (kh3) tmpl_units += (size_t)2 * X.cg * 2 * (W + 1);
+        for (int k = 0; k < X.n_buf; ++k) {
+            OWW_CUDA(ctx, cudaMalloc(&X.buf[k], (size_t)2 * X.cg * X.plane * 16));
+            OWW_CUDA(ctx, cudaMemset(X.buf[k], 0, (size_t)2 * X.cg * X.plane * 16));
+        }
+        if (C.pool_t) {
+            const size_t u = (size_t)2 * (C.cout / 8) * ((kGuard + (size_t)n * rows * (W + 1) + kGuardBack + 7) & ~(size_t)7);
+            if (u > tmp_units) tmp_units = u;
+            rows /= C.pool_t; W /= C.pool_f;
+        }
+    }
+    if (tmp_units) {
+        OWW_CUDA(ctx, cudaMalloc(&ctx->d_late_tmp[0], tmp_units * 16));
+        OWW_CUDA(ctx, cudaMemset(ctx->d_late_tmp[0], 0, tmp_units * 16));
+    }
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_late_template, std::max<size_t>(tmpl_units, 1) * 16));
+    OWW_CUDA(ctx, cudaMemset(ctx->d_late_template, 0, std::max<size_t>(tmpl_units, 1) * 16));
+    ctx->late_step = 0;
+    ctx->late_active = true;
+    return OWW_OK;
+}
+
+// Layers L0 .. 19 for every stream's new rows of this step; d_emb [n_streams][96].
+int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
+    const int L0 = ctx->split_from, n = ctx->n_streams;
+    const long k = ctx->late_step;
+    for (int l = L0; l < OWW_N_CONV; ++l) {
+        const ConvLayer& C = ctx->conv[l];
+        const oww_ctx::LateTensor& X = ctx->late_x[l];
+        const bool last = l == OWW_N_CONV - 1;
+        const int cg = C.cin / 8, cgp = (cg + 1) & ~1, np = (C.cout + 15) & ~15;
+        const int W = X.W, Wp = W + 1, T = X.T_buf, T_out = X.rows_new;
+        TcConvArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.in = reinterpret_cast<const __half*>(X.buf[X.n_buf == 1 ? 0 : (int)(k % X.n_buf)]);
+        a.in_plane = X.plane;
+        a.w = reinterpret_cast<const __half*>(ctx->d_tc_w3) + 2 * ctx->tc_w_off[l];
+        a.scale = ctx->d_tc_sb3 + ctx->tc_sb_off[l]; a.bias = a.scale + np;
+        a.n = n; a.T = T; a.W = W; a.T_out = T_out;
+        if (C.kw == 3) { a.lo = 1; a.tap_off[0] = 0; a.tap_off[1] = 1; a.tap_off[2] = 2; a.rows = round8(128 + 2); }
+        else { a.lo = 0; a.tap_off[0] = 0; a.tap_off[1] = Wp; a.tap_off[2] = 2 * Wp; a.rows = round8(128 + 2 * Wp); }
+        a.cg_in = cg; a.cg_out = C.cout / 8; a.apply_act = last ? 0 : 1;
+        a.p_in = (int64_t)n * T * Wp;
+        a.n_tiles = (int)((a.p_in + 127) / 128);
+        a.rows_out = T_out;
+        // where the output rows go: the next layer's input buffers (or the unpooled temp)
+        auto route = [&](const oww_ctx::LateTensor& Y, __half** p, int* toff, int& n_out) {
+            n_out = 0;
+            if (Y.n_buf == 1) { p[0] = reinterpret_cast<__half*>(Y.buf[0]); toff[0] = 0; n_out = 1; return; }
+            const int r = Y.rows_new;                       // 2 -> two buffers, 1 -> three
+            for (int m = 0; m < Y.n_buf; ++m) {
+                p[m] = reinterpret_cast<__half*>(Y.buf[(k + m) % Y.n_buf]);
+                toff[m] = 2 - m * r;                        // this step: behind the two tails; later steps: as their tails
+            }
+            n_out = Y.n_buf;
+        };
+        if (last) {
+            a.out_f32 = d_emb;
+        } else if (C.pool_t) {
+            a.out = reinterpret_cast<__half*>(ctx->d_late_tmp[0]);
+            a.out_plane = (int64_t)((kGuard + (int64_t)n * T_out * Wp + kGuardBack + 7) & ~7LL);
+            a.out_split = 1;
+        } else {
+            const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
+            __half* p[3] = {nullptr, nullptr, nullptr}; int toff[3] = {0, 0, 0}; int n_out = 0;
+            route(Y, p, toff, n_out);
+            a.out = p[0]; a.out_plane = Y.plane; a.out_split = 1;
+            a.out_T = Y.T_buf; a.out_toff = toff[0];
+            for (int m = 1; m < n_out; ++m) { a.out_b[m - 1] = p[m]; a.out_b_toff[m - 1] = toff[m]; }
+        }
+        int rc = dispatch_tc<3>(ctx, cgp, np, a, s);
+        if (rc) return rc;
+        if (C.pool_t && !last) {
+            const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
+            PoolOut po{{nullptr, nullptr, nullptr}, {0, 0, 0}, Y.T_buf};
+            int n_out = 0;
+            route(Y, po.p, po.toff, n_out);
+            const int cgo = C.cout / 8;
+            const int64_t total = (int64_t)n * Y.rows_new * (Y.W + 1) * cgo;
+            unsigned grid = (unsigned)((total + 255) / 256);
+            if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
+            tc_pool_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(ctx->d_late_tmp[0]), a.out_plane, po, Y.plane, n, T_out, W, cgo,
+                                               C.pool_t, C.pool_f, 1);
+            OWW_LAUNCH_CHECK(ctx);
+        }
+    }
+    ctx->late_step = k + 1;
+    return OWW_OK;
+}
+
+// Called by the full-window pyramid on the all-ones window (template pass): remember the last two rows of every
+// tensor that carries tails in the incremental chain.
+int oww_late_capture(oww_ctx* ctx, int next_layer, const void* planes, int64_t plane_pitch, int T, int W, cudaStream_t s) {
+    if (!ctx->late_active || next_layer < ctx->split_from || next_layer >= OWW_N_CONV) return OWW_OK;
+    const oww_ctx::LateTensor& X = ctx->late_x[next_layer];
+    if (X.tmpl_off < 0) return OWW_OK;
+    if (W != X.W) return oww_fail(ctx, OWW_EINVAL, "late capture: width mismatch at layer %d", next_layer);
+    late_capture_kernel<<<4, 256, 0, s>>>(reinterpret_cast<const uint4*>(planes), plane_pitch, T, W + 1, 2 * X.cg,
+                                         reinterpret_cast<uint4*>(ctx->d_late_template) + X.tmpl_off);
+    OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }

@@ -64,9 +64,10 @@ struct IncArgs {
     const HeadDev* heads; int n_heads; int max_n_in;
     float* scores; int score_stride;
     int hring_off, hslot_bytes, hns;                          // smem ring the producer streams the heads' first-layer weights through
-    const uint8_t* primed;                                    // optional [B]: 0 = stream is skipped entirely (its state is untouched:
-                                                              // it is being re-primed from a full window by other launches)
     const Gate* gates; int n_gates;                           // conditional verifier pairs, applied after the heads phase
+    // cut plan (plan.n_layers < 20): the pooled output of the last fused layer leaves the kernel as fp16 hi/lo planes in
+    // the window-mode layout [plane][stream][row][f + pad] - the input of the incremental late layers (cnn_tc.cu)
+    uint4* gx; int64_t gx_plane;
 };
 
 // Rows of a later head layer (K x D floats) per ring chunk: a multiple of 4 rows (16-byte chunk starts) that fits a slot.
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             uint32_t par[2] = {0, 0};
             uint32_t hs_par = 0, he_par = 0; int hchunk = 0;
             for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-                for (int l = 1; l < OWW_N_CONV; ++l) {
+                for (int l = 1; l < P.n_layers; ++l) {
                     const int i = l & 1;
                     mbar_wait(wempty(i), par[i] ^ 1);
                     mbar_expect_tx(wfull(i), (uint32_t)P.L[l].w_bytes);
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         bool have_prev = false; int prev_i = 0;
         uint32_t tails_par = 0;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-            for (int l = 1; l < OWW_N_CONV; ++l) {
+            for (int l = 1; l < P.n_layers; ++l) {
                 const IncLayer& L = P.L[l];
                 named_bar_sync(1, (kIncEpiWarps + 1) * 32);       // layer l-1 output complete and fenced
                 tc_fence_after();
@@ -245,13 +246,13 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
             int* s_cnt = reinterpret_cast<int*>(smem + 1536);      // [0..7] mel row count, [8..15] feature count, before this step
-            int* s_live = s_cnt + 16;                              // [0..7] stream exists and is primed: it takes part in this launch
+            int* s_live = s_cnt + 16;                              // [0..7] stream exists, [8..15] it is fresh (first chunk after a reset)
             float* s_mel = reinterpret_cast<float*>(smem + P.scratch_off + 6144);   // [G][8][32] this step's mel rows
             if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[101] = clock64();
             named_bar_sync(2, kIncEpiWarps * 32);                  // every warp is done with the previous group's s_live / s_cnt
             if (et < G) {
                 const int b = grp * G + et;
-                s_live[et] = b < a.B && (!a.primed || a.primed[b]);
+                s_live[et] = b < a.B;
             }
             named_bar_sync(2, kIncEpiWarps * 32);
             if (a.fused) {
@@ -266,6 +267,10 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     const int b = grp * G + et;
                     s_cnt[et] = s_live[et] ? a.mel_count_rw[b] : 0;
                     s_cnt[8 + et] = s_live[et] ? a.feat_count[b] : 0;
+                    // fresh stream (first chunk after a reset): only 5 mel frames exist.  Its history is
+                    // ones(76,32), which is invariant under a shift in time, so the step is the ordinary 8-row step on
+                    // the rows [1, 1, 1, m0..m4] with the tails of the all-ones window (written at reset)
+                    s_live[8 + et] = s_live[et] && a.seen[b] == 0;
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 const int my_start = a.mel_start[lane], my_len = a.mel_len[lane];
@@ -289,8 +294,9 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 named_bar_sync(2, kIncEpiWarps * 32);
                 if (warp < G) {                                    // per-call (= per stream, this step) maximum -> -80 dB floor
                     float m = -INFINITY;
+                    const int j0 = s_live[8 + warp] ? 3 : 0;       // a fresh stream's call holds frames 3..7 only
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) m = fmaxf(m, s_mel[warp * 256 + j * 32 + lane]);
+                    for (int j = 0; j < 8; ++j) if (j >= j0) m = fmaxf(m, s_mel[warp * 256 + j * 32 + lane]);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
                     if (lane == 0) s_floor[warp] = m - 80.0f;
@@ -300,9 +306,11 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     const int g = i >> 8, b = grp * G + g;
                     float v = fmaxf(s_mel[i], s_floor[g]);
                     v = v / 10.0f + 2.0f;
+                    const int fr = (i >> 5) & 7, skip = s_live[8 + g] ? 3 : 0;
+                    if (fr < skip) v = 1.0f;                       // the three rows a fresh stream does not have: ones, like its history
                     s_mel[i] = v;
-                    if (s_live[g])
-                        a.mel_rw[(int64_t)b * a.mel_stride + (int64_t)((s_cnt[g] + ((i >> 5) & 7)) & a.mel_mask) * 32 + (i & 31)] = v;
+                    if (s_live[g] && fr >= skip)
+                        a.mel_rw[(int64_t)b * a.mel_stride + (int64_t)((s_cnt[g] + fr - skip) & a.mel_mask) * 32 + (i & 31)] = v;
                 }
                 for (int i = et; i < G * OWW_TAIL; i += kIncEpiWarps * 32) {
                     const int g = i / OWW_TAIL, k = i - g * OWW_TAIL, b = grp * G + g;
@@ -310,14 +318,15 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 }
                 if (et < G && s_live[et]) {
                     const int b = grp * G + et;
-                    a.mel_count_rw[b] = oww_wrap_count(s_cnt[et] + 8);
+                    a.mel_count_rw[b] = oww_wrap_count(s_cnt[et] + (s_live[8 + et] ? 5 : 8));
                     const int sn = a.seen[b] + 1;
                     a.seen[b] = sn > (1 << 30) ? (1 << 30) : sn;
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
             }
-            for (int l = 0; l < OWW_N_CONV; ++l) {
+            for (int l = 0; l < P.n_layers; ++l) {
                 const IncLayer& L = P.L[l];
+                const bool to_global = l == P.n_layers - 1 && P.n_layers < OWW_N_CONV;   // cut plan: pooled output -> HBM (hi/lo)
                 if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[l] = clock64();
                 uint4* nx = act0 + L.nx_base;
                 // ---- (a) tails of the buffer this phase fills (rows 0..1) and front guards.  In a pool phase that
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         }
                         const float* base = a.mel + (int64_t)b * a.mel_stride;
                         // rows 0..9 of the input = two rows from before this step + the eight new ones
-                        const int row0 = (a.fused ? s_cnt[g] - 2 : a.mel_count[b] - a.back - 10) + t;
+                        const int row0 = (a.fused ? s_cnt[g] - 2 : a.mel_count[b] - a.back - 10) + t;     // fused: the two rows before this step's
                         float x[3][4];                               // mel rows t..t+2, columns f0-1..f0+2
 #pragma unroll
                         for (int dt = 0; dt < 3; ++dt) {
@@ -474,14 +483,23 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             const float4* sc4 = reinterpret_cast<const float4*>(sb + pl * 8);
                             const float4* bi4 = reinterpret_cast<const float4*>(sb + L.np + pl * 8);
                             const float4 s0 = sc4[0], s1 = sc4[1], b0 = bi4[0], b1 = bi4[1];
+                            const float y[8] = {act(fmaf(__uint_as_float(v[k][0]), s0.x, b0.x)), act(fmaf(__uint_as_float(v[k][1]), s0.y, b0.y)),
+                                                act(fmaf(__uint_as_float(v[k][2]), s0.z, b0.z)), act(fmaf(__uint_as_float(v[k][3]), s0.w, b0.w)),
+                                                act(fmaf(__uint_as_float(v[k][4]), s1.x, b1.x)), act(fmaf(__uint_as_float(v[k][5]), s1.y, b1.y)),
+                                                act(fmaf(__uint_as_float(v[k][6]), s1.z, b1.z)), act(fmaf(__uint_as_float(v[k][7]), s1.w, b1.w))};
                             __half2 h[4];
-                            h[0] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][0]), s0.x, b0.x)), act(fmaf(__uint_as_float(v[k][1]), s0.y, b0.y)));
-                            h[1] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][2]), s0.z, b0.z)), act(fmaf(__uint_as_float(v[k][3]), s0.w, b0.w)));
-                            h[2] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][4]), s1.x, b1.x)), act(fmaf(__uint_as_float(v[k][5]), s1.y, b1.y)));
-                            h[3] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][6]), s1.z, b1.z)), act(fmaf(__uint_as_float(v[k][7]), s1.w, b1.w)));
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(y[2 * u], y[2 * u + 1]);
                             const uint4 pk = pad ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<uint4*>(h);
                             d0[pl * dpitch] = pk;
                             if (keep_tail) t0[pl * (2 * G * L.Wp)] = pk;
+                            if (to_global) {                      // the unpooled temp also keeps the lo parts: y = hi + lo
+                                __half2 lo[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u)
+                                    lo[u] = __floats2half2_rn(y[2 * u] - __low2float(h[u]), y[2 * u + 1] - __high2float(h[u]));
+                                d0[(L.cg_out + pl) * dpitch] = pad ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<uint4*>(lo);
+                            }
                         }
                     }
                     acc_par = par0 ^ (uint32_t)(((acc0 + n_tiles) >> 2) & 1);
@@ -490,7 +508,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     if (L.pool_t) {
                         // ---- max-pool: tmp (unpooled conv output) -> nx ----
                         named_bar_sync(2, kIncEpiWarps * 32);          // every tile drained: the conv input buffer is free
-                        fill_tails_and_guards();
+                        if (!to_global) fill_tails_and_guards();
                         if (L.nx_tail_off >= 0 && L.nx_rows_new == 1) {
                             // single new row: next step's tails are (old tail row 1, new row); copy the old row once it landed
                             mbar_wait(tails_bar, epi_tails_par);
@@ -512,6 +530,35 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             const int tg = (int)__umulhi((uint32_t)p, nwp_magic), f = p - tg * L.nx_Wp;
                             const int t = G > 1 ? (int)__umulhi((uint32_t)tg, gp_magic) : tg, g = tg - t * G;
                             uint4 res = make_uint4(0, 0, 0, 0);
+                            if (to_global) {
+                                // pool on (hi, lo) pairs: the element with the largest hi + lo = lexicographic maximum
+                                uint4 res_lo = make_uint4(0, 0, 0, 0);
+                                if (f < L.nx_W) {
+                                    __half mh[8], ml[8];
+                                    bool first = true;
+                                    for (int da = 0; da < L.pool_t; ++da)
+                                        for (int db = 0; db < L.pool_f; ++db) {
+                                            const int at = 1 + ((t * L.pool_t + da) * G + g) * L.Wp + f * L.pool_f + db;
+                                            const uint4 q = src[pl * L.tmp_pitch + at], ql = src[(L.cg_out + pl) * L.tmp_pitch + at];
+                                            const __half* hv = reinterpret_cast<const __half*>(&q);
+                                            const __half* lv = reinterpret_cast<const __half*>(&ql);
+#pragma unroll
+                                            for (int u = 0; u < 8; ++u) {
+                                                const bool take = first || __hgt(hv[u], mh[u]) || (__heq(hv[u], mh[u]) && __hgt(lv[u], ml[u]));
+                                                if (take) { mh[u] = hv[u]; ml[u] = lv[u]; }
+                                            }
+                                            first = false;
+                                        }
+                                    res = *reinterpret_cast<uint4*>(mh);
+                                    res_lo = *reinterpret_cast<uint4*>(ml);
+                                }
+                                if (s_live[g]) {
+                                    const int64_t q = kGuard + ((int64_t)(grp * G + g) * T2 + t) * L.nx_Wp + f;
+                                    a.gx[(int64_t)pl * a.gx_plane + q] = res;
+                                    a.gx[(int64_t)(L.cg_out + pl) * a.gx_plane + q] = res_lo;
+                                }
+                                continue;
+                            }
                             if (f < L.nx_W) {
                                 __half2 mx[4];
                                 bool first = true;
@@ -538,13 +585,13 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 if (L.nx_tail_off >= 0) epi_tails_par ^= 1;
                 // ---- phase done: make generic-proxy smem writes visible to the tensor core ----
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (l < OWW_N_CONV - 1) {
+                if (l < P.n_layers - 1) {
                     tc_fence_before();
                     named_bar_sync(1, (kIncEpiWarps + 1) * 32);
                 }
             }
             if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[OWW_N_CONV] = clock64();
-            if (a.fused) {
+            if (a.fused && P.n_layers == OWW_N_CONV) {
                 // ===== K3 inside the step kernel: every head on this group's streams, straight from the feature ring =====
                 named_bar_sync(2, kIncEpiWarps * 32);              // the new embedding rows (written by this CTA) are visible
                 if (a.n_heads > 0) {                               // n_heads == 0: the heads run as their own launch after this one
@@ -761,14 +808,19 @@ __global__ void __launch_bounds__(256) tc_capture_kernel(const uint4* planes, in
 
 // ------------------------------------------------------------------------------------------------
 // Plan: per-layer geometry of the fused kernel for groups of G streams.
-int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
+int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, int n_layers, IncPlan* out) {
     if (G < 1 || G > kIncMaxG) return oww_fail(ctx, OWW_EINVAL, "group size must be 1..%d", kIncMaxG);
+    const int NL = n_layers;            // conv layers inside the kernel: 20, or a cut after a pooled layer (cut plan)
+    if (NL < 3 || NL > OWW_N_CONV || (NL < OWW_N_CONV && !ctx->conv[NL - 1].pool_t))
+        return oww_fail(ctx, OWW_EINVAL, "fused-CNN plan: cannot cut after layer %d", NL - 1);
     constexpr int kTop = 227 * 1024;     // usable dynamic shared memory per CTA on sm_100
     constexpr int kActBase = 2048;
     IncPlan P;
     std::memset(&P, 0, sizeof(P));
     P.G = G;
     P.n_groups = (n_streams + G - 1) / G;
+    P.n_layers = NL;
+    for (int l = 0; l < OWW_N_CONV; ++l) P.L[l].nx_tail_off = -1;
     int rows_new = 8, W = 32;            // geometry of the tensor produced by the previous phase
     int tail_units = 0;
     int x_units = 0, y_units = 0;
@@ -777,9 +829,10 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
     auto need = [&](int buf, int units) { if (buf) { if (units > y_units) y_units = units; } else { if (units > x_units) x_units = units; } };
     int cur_buf = 0;                      // buffer holding the input of the next layer
     int use_x[OWW_N_CONV] = {0}, use_y[OWW_N_CONV] = {0};   // units of X / Y alive during phase l
-    for (int l = 0; l < OWW_N_CONV; ++l) {
+    for (int l = 0; l < NL; ++l) {
         const ConvLayer& C = ctx->conv[l];
         IncLayer& L = P.L[l];
+        const bool cut = l == NL - 1 && NL < OWW_N_CONV;     // pooled output leaves the kernel (hi/lo planes in HBM)
         L.final = l == OWW_N_CONV - 1;
         L.kh3 = C.kh == 3 && l > 0;
         L.W = W; L.Wp = W + 1;
@@ -802,7 +855,7 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
             w_off += (size_t)((L.w_bytes + 127) & ~127);
         }
         // geometry of what this phase leaves for layer l+1
-        const bool next_kh3 = l + 1 < OWW_N_CONV && ctx->conv[l + 1].kh == 3;
+        const bool next_kh3 = !cut && l + 1 < OWW_N_CONV && ctx->conv[l + 1].kh == 3;
         int nrows = L.T_out, nW = W;
         if (L.pool_t) { nrows = L.T_out / L.pool_t; nW = W / L.pool_f; }
         L.nx_W = nW; L.nx_Wp = nW + 1; L.nx_rows_new = nrows;
@@ -810,8 +863,8 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
         L.out_buf = l == 0 ? 0 : (cur_buf ^ 1);
         L.nx_buf = (l == 0) ? 0 : (L.pool_t ? cur_buf : L.out_buf);
         L.nx_pitch = pitch_of(nrows + L.nx_t_off, L.nx_Wp);
-        if (L.pool_t) { L.tmp_pitch = pitch_of(L.T_out, L.Wp); use(L.out_buf, L.tmp_pitch * L.cg_out); }
-        if (!L.final) use(L.nx_buf, L.nx_pitch * L.cg_out);
+        if (L.pool_t) { L.tmp_pitch = pitch_of(L.T_out, L.Wp); use(L.out_buf, L.tmp_pitch * L.cg_out * (cut ? 2 : 1)); }
+        if (!L.final && !cut) use(L.nx_buf, L.nx_pitch * L.cg_out);
         L.nx_tail_off = -1;
         if (L.nx_t_off == 2) { L.nx_tail_off = tail_units; tail_units += L.cg_out * 2 * G * L.nx_Wp; }
         cur_buf = L.nx_buf;
@@ -821,14 +874,15 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
     P.x_units = (x_units + 7) & ~7; P.y_units = (y_units + 7) & ~7;
     // ---- placement: class-0 tensors sit at offset 0; a class-1 tensor sits just above the largest class-0 tensor
     //      that is alive at any time during its own lifetime (produced in phase p, consumed in phase p+1) ----
-    int size_nx[OWW_N_CONV], size_tmp[OWW_N_CONV], xlive[OWW_N_CONV + 1];
-    for (int l = 0; l < OWW_N_CONV; ++l) {
+    int size_nx[OWW_N_CONV] = {0}, size_tmp[OWW_N_CONV] = {0}, xlive[OWW_N_CONV + 1];
+    for (int l = 0; l < NL; ++l) {
         const IncLayer& L = P.L[l];
-        size_nx[l] = L.final ? 0 : L.nx_pitch * L.cg_out;
-        size_tmp[l] = L.pool_t ? L.tmp_pitch * L.cg_out : 0;
+        const bool cut = l == NL - 1 && NL < OWW_N_CONV;
+        size_nx[l] = (L.final || cut) ? 0 : L.nx_pitch * L.cg_out;
+        size_tmp[l] = L.pool_t ? L.tmp_pitch * L.cg_out * (cut ? 2 : 1) : 0;
     }
     for (int l = 0; l <= OWW_N_CONV; ++l) xlive[l] = 0;
-    for (int l = 0; l < OWW_N_CONV; ++l) {
+    for (int l = 0; l < NL; ++l) {
         const IncLayer& L = P.L[l];
         auto upd = [&](int cls, int sz) { if (cls == 0 && sz > xlive[l]) xlive[l] = sz; };
         if (l > 0) upd(L.in_buf, size_nx[l - 1]);
@@ -837,7 +891,7 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
     }
     auto r8 = [](int v) { return (v + 7) & ~7; };
     int act_high[OWW_N_CONV] = {0};
-    for (int l = 0; l < OWW_N_CONV; ++l) {
+    for (int l = 0; l < NL; ++l) {
         IncLayer& L = P.L[l];
         L.in_base = l > 0 ? P.L[l - 1].nx_base : 0;
         L.tmp_base = (L.pool_t && L.out_buf == 1) ? r8(xlive[l]) : 0;
@@ -850,14 +904,18 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
     }
     // weight slots, top-down: odd layers end at the top, an even layer sits just below its odd successor's
     // slot (sizes are non-decreasing with depth, so it also clears its odd predecessor).
-    auto wsz = [&](int l) { return l >= 1 && l < OWW_N_CONV ? (P.L[l].w_bytes + 127) & ~127 : 0; };
-    for (int l = 1; l < OWW_N_CONV; ++l)
-        P.L[l].w_smem = (l & 1) ? kTop - wsz(l) : kTop - wsz(l + 1) - wsz(l);
-    for (int l = 1; l < OWW_N_CONV; ++l) {
+    auto wsz = [&](int l) { return l >= 1 && l < NL ? (P.L[l].w_bytes + 127) & ~127 : 0; };
+    for (int l = 1; l < NL; ++l) {
+        // (in a cut plan the last layer can be even: it still sits below its odd predecessor, whose slot is live while
+        // this one is prefetched)
+        const int above = wsz(l + 1) > wsz(l - 1) ? wsz(l + 1) : wsz(l - 1);
+        P.L[l].w_smem = (l & 1) ? kTop - wsz(l) : kTop - above - wsz(l);
+    }
+    for (int l = 1; l < NL; ++l) {
         // while layer l runs, its own slot and the prefetch of layer l+1 are live next to the activations in use;
         // slot l itself was filled during phase l-1
         int w_low = P.L[l].w_smem;
-        if (l + 1 < OWW_N_CONV && P.L[l + 1].w_smem < w_low) w_low = P.L[l + 1].w_smem;
+        if (l + 1 < NL && P.L[l + 1].w_smem < w_low) w_low = P.L[l + 1].w_smem;
         if (act_high[l] > w_low || act_high[l - 1] > P.L[l].w_smem)
             return oww_fail(ctx, OWW_EUNSUPPORTED, "fused-CNN smem plan does not fit at layer %d (G=%d)", l, G);
         if (l >= 2 && wsz(l) < wsz(l - 1)) return oww_fail(ctx, OWW_EUNSUPPORTED, "weight sizes must not shrink with depth");
@@ -880,7 +938,7 @@ int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out) {
 int oww_inc_setup(oww_ctx* ctx, const float* h_blob) {
     // packed blob for the fused kernel: per layer fp16 [3][CGP][NP][8] | scale[NP] | bias[NP], 128-byte aligned
     IncPlan P;
-    int rc = oww_inc_build_plan(ctx, 1, 1, &P);
+    int rc = oww_inc_build_plan(ctx, 1, 1, OWW_N_CONV, &P);
     if (rc) return rc;
     std::vector<uint8_t> blob(P.w_total_bytes, 0);
     size_t off = 0;
@@ -908,20 +966,25 @@ int oww_inc_setup(oww_ctx* ctx, const float* h_blob) {
     return OWW_OK;
 }
 
+// conv layers inside the fused kernel: all 20, or - with the incremental late layers of cnn_tc.cu - those below split_from
+int oww_inc_n_layers(const oww_ctx* ctx) {
+    return (ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && ctx->split_from < OWW_N_CONV) ? ctx->split_from : OWW_N_CONV;
+}
+
 int oww_inc_alloc_streams(oww_ctx* ctx) {
     // Group size: a group's latency is mostly per-layer fixed cost (about 50 us + 6.5 us per stream on B200), so take
     // the feasible G that minimises rounds(G) * T(G) for this stream count.
     int best_g = 0; double best_cost = 0;
     for (int g = 1; g <= kIncMaxG; ++g) {
         IncPlan P;
-        if (oww_inc_build_plan(ctx, g, ctx->n_streams, &P) != OWW_OK) continue;
+        if (oww_inc_build_plan(ctx, g, ctx->n_streams, oww_inc_n_layers(ctx), &P) != OWW_OK) continue;
         const int rounds = (P.n_groups + ctx->sm_count - 1) / ctx->sm_count;
         const double cost = rounds * (50.0 + 6.5 * g);
         if (!best_g || cost < best_cost) { best_g = g; best_cost = cost; }
     }
     if (!best_g) return oww_fail(ctx, OWW_EUNSUPPORTED, "no feasible group size for the fused CNN kernel");
     ctx->err.clear();
-    int rc = oww_inc_build_plan(ctx, best_g, ctx->n_streams, &ctx->inc_plan);
+    int rc = oww_inc_build_plan(ctx, best_g, ctx->n_streams, oww_inc_n_layers(ctx), &ctx->inc_plan);
     if (rc) return rc;
     const size_t bytes = (size_t)ctx->inc_plan.n_groups * ctx->inc_plan.tail_units * 16;
     for (int i = 0; i < 2; ++i) {
@@ -930,6 +993,7 @@ int oww_inc_alloc_streams(oww_ctx* ctx) {
         OWW_CUDA(ctx, cudaMemset(ctx->d_inc_tails[i], 0, bytes));
     }
     ctx->inc_cur = 0;
+    ctx->tails_template_valid = false;                   // the scatter table depends on the group size
     OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
     return OWW_OK;
 }
@@ -956,8 +1020,7 @@ int oww_heads_sync_devs(oww_ctx* ctx) {
     return OWW_OK;
 }
 
-// Can the frontend + CNN + ring append of a one-chunk step run as the fused launch?  (mode 3, at least the streams
-// that are primed; the caller decides what happens to unprimed ones)
+// Can the frontend + CNN + ring append of a one-chunk step run as the fused launch?
 bool oww_fused_frontend_supported(const oww_ctx* ctx) {
     return ctx->fuse_step && ctx->cfg.cnn_mode == OWW_CNN_TC_INCREMENTAL && ctx->inc_plan.scratch_off != 0;
 }
@@ -966,6 +1029,7 @@ bool oww_fused_frontend_supported(const oww_ctx* ctx) {
 // first-layer matrices once per group of G streams is cheap)
 bool oww_fused_heads_supported(const oww_ctx* ctx) {
     if (!oww_fused_frontend_supported(ctx) || ctx->heads.empty() || ctx->heads.size() > 16) return false;
+    if (ctx->inc_plan.n_layers < OWW_N_CONV) return false;       // cut plan: the embedding is produced by the late layers' launches
     // In the fused kernel every group of G streams re-streams each head's first-layer matrix from L2; with many
     // groups x many/large heads that traffic (and the 7-row tiles) loses to the stand-alone heads kernel's 32-row tiles.
     {
@@ -994,16 +1058,19 @@ static void fill_inc_args(oww_ctx* ctx, IncArgs& a) {
     a.tails_out = reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur ^ 1]);
     a.B = ctx->n_streams;
     a.dbg_clock = reinterpret_cast<long long*>(ctx->d_inc_dbg);
+    if (ctx->late_active) {
+        a.gx = reinterpret_cast<uint4*>(ctx->late_x[ctx->split_from].buf[0]);
+        a.gx_plane = ctx->late_x[ctx->split_from].plane;
+    }
 }
 
-// One launch per step: frontend, 20-layer CNN and ring append for every primed stream (d_primed == nullptr: all of
-// them), plus - with_heads - every head and the verifier gates, i.e. PCM in -> scores out.
+// One launch per step: frontend, 20-layer CNN and ring append for every stream, plus - with_heads - every head and
+// the verifier gates, i.e. PCM in -> scores out.
 int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, bool with_heads,
-                   const uint8_t* d_primed, cudaStream_t s) {
+                   cudaStream_t s) {
     IncArgs a;
     fill_inc_args(ctx, a);
     a.fused = 1;
-    a.primed = d_primed;
     a.pcm = d_pcm; a.pcm_stride = pcm_stride;
     a.tail = ctx->d_tail; a.seen = ctx->d_seen; a.mel_rw = ctx->d_mel_ring; a.mel_count_rw = ctx->d_mel_count;
     a.mel_window = ctx->d_window; a.mel_twiddle = ctx->d_twiddle; a.mel_start = ctx->d_mel_start; a.mel_len = ctx->d_mel_len;
@@ -1042,6 +1109,7 @@ int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
     tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
     OWW_LAUNCH_CHECK(ctx);
     ctx->inc_cur ^= 1;
+    if (ctx->late_active) return oww_late_chain(ctx, d_emb, s);
     return OWW_OK;
 }
 
@@ -1050,7 +1118,7 @@ int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
 int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
                     int stream0, const int* d_ids, cudaStream_t s) {
     const IncLayer& L = ctx->inc_plan.L[layer];
-    if (L.nx_tail_off < 0) return OWW_OK;
+    if (layer >= ctx->inc_plan.n_layers - (ctx->inc_plan.n_layers < OWW_N_CONV ? 1 : 0) || L.nx_tail_off < 0) return OWW_OK;
     const int Wp = W + 1;
     const int64_t total = (int64_t)n_win * L.cg_out * 2 * Wp;
     unsigned grid = (unsigned)((total + 255) / 256);
@@ -1058,5 +1126,52 @@ int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_p
                                           stream0, d_ids, ctx->inc_plan.G, L.nx_tail_off, ctx->inc_plan.tail_units,
                                           reinterpret_cast<uint4*>(ctx->d_inc_tails[ctx->inc_cur]));
     OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+namespace {
+__global__ void fill_ones_kernel(float* p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 1.0f;
+}
+}  // namespace
+
+// Tails of the all-ones window in the compact single-stream (G = 1) layout + the table reset_kernel scatters them with.
+// Runs the full-window tcgen05 pyramid (cnn_tc.cu) once on ones(76,32) with the tail capture pointed at a G = 1 plan;
+// the incremental kernel is bit-identical to that pyramid, so a stream seeded with these tails continues exactly as if
+// its (constant) history had been streamed through it.  Synchronous; called lazily by the first reset after a weight load.
+int oww_inc_build_template(oww_ctx* ctx) {
+    if (!ctx->emb_loaded) return oww_fail(ctx, OWW_EINVAL, "embedding weights not loaded");
+    if (!ctx->d_tc_act[0] || !ctx->d_inc_tails[0]) return oww_fail(ctx, OWW_EINVAL, "oww_set_streams has not been called");
+    IncPlan P1;
+    int rc = oww_inc_build_plan(ctx, 1, 1, ctx->inc_plan.n_layers, &P1);
+    if (rc) return rc;
+    ctx->n_tail_tab = 0;
+    for (int l = 0; l < OWW_N_CONV; ++l)
+        if (P1.L[l].nx_tail_off >= 0)
+            ctx->tail_tab[ctx->n_tail_tab++] = make_int4(P1.L[l].nx_tail_off, ctx->inc_plan.L[l].nx_tail_off, P1.L[l].cg_out, P1.L[l].nx_Wp);
+    cudaFree(ctx->d_tails_template); ctx->d_tails_template = nullptr;
+    OWW_CUDA(ctx, cudaMalloc(&ctx->d_tails_template, (size_t)P1.tail_units * 16));
+    OWW_CUDA(ctx, cudaMemset(ctx->d_tails_template, 0, (size_t)P1.tail_units * 16));
+    float* d_ones = nullptr; float* d_emb = nullptr;
+    OWW_CUDA(ctx, cudaMalloc(&d_ones, OWW_WINDOW_ROWS * 32 * sizeof(float)));
+    OWW_CUDA(ctx, cudaMalloc(&d_emb, 96 * sizeof(float)));
+    fill_ones_kernel<<<(OWW_WINDOW_ROWS * 32 + 255) / 256, 256>>>(d_ones, OWW_WINDOW_ROWS * 32);
+    // point the capture hook at the G = 1 layout for this one pass
+    const IncPlan saved_plan = ctx->inc_plan;
+    void* const saved_tails = ctx->d_inc_tails[ctx->inc_cur];
+    ctx->inc_plan = P1;
+    ctx->d_inc_tails[ctx->inc_cur] = ctx->d_tails_template;
+    WindowSrc src{d_ones, (int64_t)OWW_WINDOW_ROWS * 32, nullptr, -1, 0, 0};
+    TailCapture cap{0, 1, 0};
+    cap.late = ctx->late_active;
+    rc = oww_cnn_tc_pyramid_cap(ctx, src, 1, d_emb, &cap, nullptr);
+    cudaError_t e = cudaDeviceSynchronize();
+    ctx->inc_plan = saved_plan;
+    ctx->d_inc_tails[ctx->inc_cur] = saved_tails;
+    cudaFree(d_ones); cudaFree(d_emb);
+    if (rc) return rc;
+    if (e != cudaSuccess) return oww_fail(ctx, OWW_ECUDA, "tails template: %s", cudaGetErrorString(e));
+    ctx->tails_template_valid = true;
     return OWW_OK;
 }

@@ -29,12 +29,21 @@ struct Head {
     int col0;            // first score column
     float* d_blob;       // packed weights (layout of pack_head_blob)
     std::vector<size_t> w_off, b_off, g_off, h_off;   // float offsets per layer
-    // tensor-core first layer (heads_tc.cu): fp16 hi/lo of W1 * 2^s in UMMA order, or tc_ok == false
+    // tensor-core path (heads_tc.cu): every Linear layer as fp16 hi/lo of W * 2^s in UMMA order, or tc_ok == false
+    struct TcLayer { int K, D, Kp, NP; uint32_t w_off, w_bytes; float unscale; };
     bool tc_ok = false;
-    void* d_w1_tc = nullptr;
-    int tc_np = 0;
-    float tc_unscale = 1.f;
+    void* d_w1_tc = nullptr;         // packed weights of all layers
+    std::vector<TcLayer> tc_layers;
 };
+
+// what reset_kernel needs to seed a stream's conv tails (mode 3)
+struct ResetLate {           // one tails-bearing tensor of the incremental late layers
+    uint4* now;              // buffer the stream's next step reads: rows 0, 1 <- template rows 0, 1
+    uint4* next;             // tensors that gain ONE row per step: the buffer of the step after, row 0 <- template row 1
+    const uint4* tmpl;       // [planes][2][Wp]
+    int64_t plane; int T_buf, Wp, n_planes;
+};
+struct ResetTails { uint4* tails; const uint4* tmpl; int G, tail_units, n_tab; int4 tab[OWW_N_CONV]; int n_late; ResetLate late[6]; };
 
 // conditional verifier pair (hey_jarvis, docs/models/hey_jarvis.md:38): score column `main_col` is replaced by column
 // `ver_col` wherever it exceeds `thr`
@@ -77,6 +86,7 @@ struct IncPlan {
     int G, n_groups, tail_units, x_units, y_units, w_total_bytes, smem_bytes;
     int scratch_off;         // byte offset of the frontend (mel) scratch used before phase 0; 0 = does not fit
     IncLayer L[OWW_N_CONV];
+    int n_layers;            // conv layers inside the kernel (20, or a cut after a pooled layer: the rest run in cnn_tc.cu)
 };
 
 struct oww_ctx {
@@ -129,6 +139,10 @@ struct oww_ctx {
     // tensor-core path (cnn_tc.cu)
     void* d_tc_w = nullptr;          // packed fp16 weights, all layers
     float* d_tc_sb = nullptr;        // padded scale/bias per layer
+    void* d_tc_w3 = nullptr;         // split variant: per layer [hi block | lo block] of W * 2^s (offsets = 2 x tc_w_off)
+    float* d_tc_sb3 = nullptr;       // scale * 2^-s | bias
+    int split_from = 11;             // window / clip passes: conv layers >= split_from take fp16 hi/lo split operands
+                                     // (fp32-grade products); OWW_N_CONV = plain fp16 everywhere
     size_t tc_w_off[OWW_N_CONV] = {0};
     size_t tc_sb_off[OWW_N_CONV] = {0};
     void* d_tc_act[2] = {nullptr, nullptr};   // fp16 channel-group planes, ping-pong
@@ -138,17 +152,25 @@ struct oww_ctx {
     void* d_inc_w = nullptr;         // packed per-layer {fp16 weights, scale, bias}
     void* d_inc_tails[2] = {nullptr, nullptr};   // [n_groups][tail_units] 16-byte units, double-buffered per step
     int inc_cur = 0;                 // tails buffer the next step reads
-    // Priming: a stream is primed when its tails describe its newest window, so the next chunk can take the incremental
-    // path.  A reset un-primes the stream (its next window shifts by 5 rows, not 8 - SURVEY.md F8); the next step
-    // re-primes exactly those streams from a full window while the primed ones go through the fused kernel.
-    std::vector<uint8_t> primed;     // host mirror, [n_streams]
-    int n_unprimed = 0;
-    uint8_t* d_primed = nullptr;     // [n_streams]
-    int* d_unprimed_ids = nullptr;   // [n_streams] compacted list, uploaded by the step that consumes it
+    // Incremental late layers (cnn_tc.cu, bottom): tensors X_l = input of conv layer l >= split_from, per stream
+    // [tails | new rows], fp16 hi/lo planes in the window-mode layout
+    struct LateTensor { void* buf[3] = {nullptr, nullptr, nullptr}; int n_buf = 0, T_buf = 0, rows_new = 0, W = 0, cg = 0, tmpl_off = -1; int64_t plane = 0; };
+    LateTensor late_x[OWW_N_CONV];
+    void* d_late_tmp[1] = {nullptr};             // unpooled output of a late layer that is followed by a pool
+    void* d_late_template = nullptr;             // tails of the all-ones window per tails-bearing late tensor: [plane][2][Wp]
+    bool late_active = false;
+    long late_step = 0;                          // chunks processed since the buffers were allocated (buffer rotation)
+
+    // Priming.  A reset stream's mel history is ones(76,32) (utils.py:165) and its first chunk yields 5 rows (F8).  A
+    // constant history is shift invariant, so that first step equals the ordinary 8-row step on the rows [1,1,1,m0..m4]
+    // starting from the tails of the all-ones window: those tails are computed once per weight set (template, compact
+    // G = 1 layout) and scattered into the stream's slots by the reset kernel.  No stream is ever "unprimed".
+    void* d_tails_template = nullptr;            // [tail units of one stream] x 16 B
+    bool tails_template_valid = false;
+    int4 tail_tab[OWW_N_CONV];                   // per tails-bearing tensor: {offset in the template, offset in a group, planes, Wp}
+    int n_tail_tab = 0;
     int* d_reset_ids = nullptr;      // [n_streams] staging for oww_reset / oww_reset_async
     float* d_reset_init = nullptr;   // [feat_rows][96]
-    cudaStream_t side_stream = nullptr;          // re-prime chain of a partially primed step
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     IncPlan inc_plan;
     void* d_inc_dbg = nullptr;
     HeadDev* d_head_devs = nullptr;  // device copy of the head descriptors (fused step kernel)
@@ -237,14 +259,23 @@ int oww_cnn_window(oww_ctx* ctx, const WindowSrc& src, int n_windows, float* d_e
 // ---- cnn_tc.cu ----
 int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob);
 size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows);
+size_t oww_tc_act_units_T(const oww_ctx* ctx, int n, int T0);
+// fully-convolutional pass over linear mel [n][T][32] -> [n][(T-76)/8+1][96] on the tensor cores
+int oww_cnn_tc_clip(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s);
+// incremental late layers of mode 3 (split operands)
+int oww_late_alloc(oww_ctx* ctx);
+int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s);
+int oww_late_capture(oww_ctx* ctx, int next_layer, const void* planes, int64_t plane_pitch, int T, int W, cudaStream_t s);
 int oww_cnn_tc_pyramid(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, int stop_layer, float* d_dbg, cudaStream_t s);
 // fp32 pyramid with an optional early stop that leaves NHWC fp32 [n][T][W][C] of `stop_layer` in d_dbg
 // capture descriptor: which local windows of a full-window pass are the newest window of which streams
-struct TailCapture { int win0, n_win, stream0; const int* ids = nullptr; };   // ids: local stream -> stream id
+struct TailCapture { int win0, n_win, stream0; const int* ids = nullptr; bool late = false; };   // ids: local stream -> stream id;
+                                                                  // late: window 0 is the template window of the incremental late layers
 int oww_cnn_tc_pyramid_cap(oww_ctx* ctx, const WindowSrc& src, int n, float* d_emb, const TailCapture* cap, cudaStream_t s);
 
 // ---- cnn_tc_inc.cu ----
-int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, IncPlan* out);
+int oww_inc_build_plan(oww_ctx* ctx, int G, int n_streams, int n_layers, IncPlan* out);
+int oww_inc_n_layers(const oww_ctx* ctx);
 int oww_inc_setup(oww_ctx* ctx, const float* h_blob);
 int oww_inc_alloc_streams(oww_ctx* ctx);
 int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s);
@@ -252,7 +283,7 @@ int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s);
 bool oww_fused_frontend_supported(const oww_ctx* ctx);
 bool oww_fused_heads_supported(const oww_ctx* ctx);
 int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float* d_scores, int out_stride, bool with_heads,
-                   const uint8_t* d_primed, cudaStream_t s);
+                   cudaStream_t s);
 int oww_heads_sync_devs(oww_ctx* ctx);
 int oww_inc_capture(oww_ctx* ctx, int layer, const void* planes, int64_t plane_pitch, int T, int W, int win0, int n_win,
                     int stream0, const int* d_ids, cudaStream_t s);

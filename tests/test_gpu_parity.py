@@ -105,6 +105,44 @@ def test_default_mode_is_tc_and_embedding_windows_within_fp16_budget(af_default)
     assert d < 8e-3
 
 
+def _gated_error(c, name, got, err):
+    from oracle import streaming
+    h = head(name)
+    om = streaming.OracleModel(emb_weights(int(c["emb_seed"])), {"m": h["main"], "v": h["verifier"]}, feature_init=c["feature_init"])
+    raw = om.predict_clip(c["pcm"], padding=int(c["padding"]), chunk_size=int(c["chunk"]))
+    if int(c["chunk"]) != 1280:
+        return _gated_multi(c, h, got, err)
+    out = err.copy()
+    for s, r in enumerate(raw):
+        if abs(r["m"] - h["threshold"]) < 2e-3 and s >= 5:
+            out[s] = min(abs(got[s] - r["m"]), abs(got[s] - r["v"]))
+    return out
+
+
+def _gated_multi(c, h, got, err):
+    """multi-chunk calls: the per-chunk main scores are not in the golden; accept a frame whose error is explained by a
+    gate flip of one chunk, i.e. the output equals the max over chunks with some chunk taking its other branch."""
+    from oracle import streaming, heads as oheads
+    af = streaming.OracleAudioFeatures(emb_weights(int(c["emb_seed"])), feature_init=c["feature_init"])
+    data = np.concatenate((np.zeros(16000 * int(c["padding"]), np.int16), c["pcm"], np.zeros(16000 * int(c["padding"]), np.int16)))
+    ch = int(c["chunk"])
+    out = err.copy()
+    for s, i in enumerate(range(0, data.shape[0] - ch, ch)):
+        n = af(data[i:i + ch])
+        if n < 1280 or s < 5:
+            continue
+        k = n // 1280
+        m = [oheads.forward(h["main"], af.get_features(16, -16 - j))[0, 0] for j in range(k - 1, -1, -1)]
+        v = [oheads.forward(h["verifier"], af.get_features(16, -16 - j))[0, 0] for j in range(k - 1, -1, -1)]
+        if any(abs(x - h["threshold"]) < 2e-3 for x in m):
+            cands = []
+            for flip in range(1 << k):
+                vals = [(v[j] if ((m[j] > h["threshold"]) != bool(flip >> j & 1)) else m[j]) for j in range(k)]
+                cands.append(max(vals))
+            out[s] = min(abs(got[s] - x) for x in cands)
+    return out
+
+
 def test_heads_vs_oracle(torch_cuda, built_library):
     import openwakeword_b200 as owb
     from oracle import heads
@@ -134,7 +172,14 @@ def test_predict_clip_golden(torch_cuda, built_library, tag, mode):
     res = m.predict_clip(c["pcm"], padding=int(c["padding"]), chunk_size=int(c["chunk"]), **c["kw"])
     assert list(res[0].keys()) == c["labels"]
     got = np.array([[r[l] for l in c["labels"]] for r in res], dtype=np.float32)
-    d = np.abs(got - c["scores"]).max()
+    err = np.abs(got - c["scores"])
+    for j, name in enumerate(c["labels"]):
+        if name in c["names"] and "verifier" in head(name):
+            # a verifier gate is a step function of the main score: where the reference's main score sits within 2e-3
+            # of the threshold no implementation that differs in the last bits can be held to 1e-3 - there the output
+            # must equal one of the two branches instead
+            err[:, j] = _gated_error(c, name, got[:, j], err[:, j])
+    d = err.max()
     print(tag, "mode", mode, "max |score - golden| =", d)
     assert d < SCORE_TOL
 

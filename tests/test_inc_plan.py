@@ -26,7 +26,8 @@ def get_plan(G, n_streams, built_library):
     assert n > 0
     a = np.array(buf[:n])
     hdr = dict(zip("G n_groups tail_units x_units y_units w_total_bytes smem_bytes pad".split(), a[:8]))
-    layers = [dict(zip(NAMES, map(int, row))) for row in a[8:].reshape(20, len(NAMES))]
+    layers = [dict(zip(NAMES, map(int, row))) for row in a[8:8 + 20 * len(NAMES)].reshape(20, len(NAMES))]
+    assert int(a[8 + 20 * len(NAMES)]) == 20                      # n_layers: the exported plan is the full 20-layer one
     return hdr, layers
 
 
