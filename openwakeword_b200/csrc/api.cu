@@ -147,6 +147,30 @@ int ensure_act(oww_ctx* ctx, size_t floats) {
     return OWW_OK;
 }
 
+// grow the fp16 plane scratch of the tensor-core window / clip passes to `units` 16-byte units per buffer
+int ensure_tc_units(oww_ctx* ctx, size_t units) {
+    if (ctx->tc_act_units >= units) return OWW_OK;
+    cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]);
+    ctx->d_tc_act[0] = ctx->d_tc_act[1] = nullptr; ctx->tc_act_units = 0;
+    for (int i = 0; i < 2; ++i) {
+        OWW_CUDA(ctx, cudaMalloc(&ctx->d_tc_act[i], units * 16));
+        OWW_CUDA(ctx, cudaMemset(ctx->d_tc_act[i], 0, units * 16));
+    }
+    ctx->tc_act_units = units;
+    return OWW_OK;
+}
+
+__global__ void fill_init_rows_kernel(float* feats, int64_t clip_stride, int n_clips, const float* init, int n_rows) {
+    const int64_t total = (int64_t)n_clips * n_rows * 24;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % 24);
+        const int r = (int)((i / 24) % n_rows);
+        const int64_t clip = i / ((int64_t)24 * n_rows);
+        reinterpret_cast<float4*>(feats + clip * clip_stride + (int64_t)r * 96)[c4] =
+            init ? __ldg(reinterpret_cast<const float4*>(init + (int64_t)r * 96) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 int ensure_emb_tmp(oww_ctx* ctx, size_t floats) {
     if (ctx->emb_tmp_floats >= floats) return OWW_OK;
     cudaFree(ctx->d_emb_tmp); ctx->d_emb_tmp = nullptr; ctx->emb_tmp_floats = 0;
@@ -644,6 +668,27 @@ int oww_embed_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sampl
         return oww_fail(ctx, OWW_EINVAL, "Embedding model requires the input melspectrograms to have at least 76 frames");
     const int W = (T - OWW_WINDOW_ROWS) / 8 + 1;
     cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->cfg.cnn_mode != OWW_CNN_FP32_WINDOW) {
+        // tensor-core modes: per-clip mel (one call per clip, as the reference's CPU path runs the graph), then ONE fully
+        // convolutional tcgen05 pass over the clip's [T x 32] mel - slabs bounded by a ~1 GB plane scratch
+        const int t_use = OWW_WINDOW_ROWS + 8 * (W - 1);
+        const size_t per1 = oww_tc_act_units_T(ctx, 1, t_use);
+        int slab = (int)std::max<size_t>(1, ((size_t)1 << 26) / per1);          // 2^26 units = 1 GiB per buffer
+        slab = std::min(slab, n_clips);
+        int rc = ensure_tc_units(ctx, oww_tc_act_units_T(ctx, slab, t_use));
+        if (rc) return rc;
+        float* d_mel = nullptr;
+        OWW_CUDA(ctx, cudaMallocAsync(&d_mel, (size_t)slab * T * 32 * sizeof(float), s));
+        for (int c0 = 0; c0 < n_clips; c0 += slab) {
+            const int m = std::min(slab, n_clips - c0);
+            MelLaunch ml{d_pcm + (size_t)c0 * n_samples, (int64_t)n_samples, n_samples, nullptr, nullptr, d_mel, (int64_t)T * 32,
+                         -1, nullptr, m, 1, 0};
+            if ((rc = oww_mel_launch(ctx, ml, s))) break;
+            if ((rc = oww_cnn_tc_clip(ctx, d_mel, m, T, d_emb + (size_t)c0 * W * 96, s))) break;
+        }
+        cudaFreeAsync(d_mel, s);
+        return rc;
+    }
     // slabs bounded by the activation scratch (~512 windows' worth of layer-1 output)
     const size_t per_clip = (size_t)(T - 2) * 32 * 24;
     int rc = ensure_act(ctx, std::max(ctx->act_floats, std::max(per_clip, (size_t)ctx->window_batch * 74 * 32 * 24)));
@@ -671,6 +716,49 @@ int oww_predict_clips(oww_ctx* ctx, const int16_t* d_pcm, int n_clips, int n_sam
     const int steps = L > OWW_SAMPLES_PER_CHUNK ? (int)((L - OWW_SAMPLES_PER_CHUNK + OWW_SAMPLES_PER_CHUNK - 1) / OWW_SAMPLES_PER_CHUNK) : 0;
     if (steps == 0) return OWW_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        // ---- bulk path: per slab of clips ONE mel launch over the padded clips (frames grouped and
+        //      clamped per streaming call, behind the 71 rows of ones a fresh stream's window starts with), ONE fully
+        //      convolutional tcgen05 pass per conv layer over [76 + 8 (steps-1)] x 32, then the heads over all sliding
+        //      windows of [feature_init rows | embeddings] in one launch.  Bit-identical to streaming the clips.
+        bool tc_all = ctx->cfg.cnn_mode != OWW_CNN_FP32_WINDOW && steps <= 8192 && !ctx->heads.empty();
+        for (size_t i = 0; i < ctx->heads.size(); ++i) tc_all = tc_all && oww_heads_tc_supported(ctx, (int)i);
+        if (tc_all) {
+            const int T_v = OWW_WINDOW_ROWS + 8 * (steps - 1);
+            const int init_rows = h_feature_init ? n_rows : OWW_INIT_FEATURE_ROWS;
+            const int64_t f_stride = (int64_t)(init_rows + steps) * 96;
+            const size_t per1 = oww_tc_act_units_T(ctx, 1, T_v);
+            int slab = (int)std::max<size_t>(1, ((size_t)1 << 26) / per1);      // 1 GiB of fp16 planes per buffer
+            slab = std::min(slab, n_clips);
+            int rc = ensure_tc_units(ctx, oww_tc_act_units_T(ctx, slab, T_v));
+            if (rc) return rc;
+            float *d_v = nullptr, *d_f = nullptr, *d_init = nullptr;
+            OWW_CUDA(ctx, cudaMallocAsync(&d_v, (size_t)slab * T_v * 32 * sizeof(float), s));
+            OWW_CUDA(ctx, cudaMallocAsync(&d_f, (size_t)slab * f_stride * sizeof(float), s));
+            if (h_feature_init && init_rows > 0) {
+                OWW_CUDA(ctx, cudaMallocAsync(&d_init, (size_t)init_rows * 96 * sizeof(float), s));
+                OWW_CUDA(ctx, cudaMemcpyAsync(d_init, h_feature_init, (size_t)init_rows * 96 * sizeof(float), cudaMemcpyHostToDevice, s));
+            }
+            for (int c0 = 0; c0 < n_clips && rc == OWW_OK; c0 += slab) {
+                const int m = std::min(slab, n_clips - c0);
+                if ((rc = oww_mel_clips_launch(ctx, d_pcm + (size_t)c0 * n_samples, n_samples, m, n_samples, pad_samples, steps, d_v,
+                                               (int64_t)T_v * 32, s))) break;
+                if (init_rows > 0) {
+                    fill_init_rows_kernel<<<std::min(1024, (m * init_rows * 24 + 255) / 256), 256, 0, s>>>(d_f, f_stride, m, d_init, init_rows);
+                    ctx->launches++;
+                }
+                // embeddings of step st land at row init_rows + st of the clip's feature array
+                WindowSrc src{d_v, (int64_t)T_v * 32, nullptr, -1, 0, 0};
+                if ((rc = oww_cnn_tc_clip_rows(ctx, src, m, T_v, d_f + (int64_t)init_rows * 96, init_rows + steps, s))) break;
+                FeatSrc fs{d_f, f_stride, nullptr, -1, 0};
+                fs.steps = steps; fs.row0 = init_rows;
+                rc = oww_heads_all(ctx, fs, m * steps, d_scores + (size_t)c0 * steps * ctx->n_out_total, ctx->n_out_total, 0, s);
+            }
+            cudaFreeAsync(d_v, s); cudaFreeAsync(d_f, s);
+            if (d_init) cudaFreeAsync(d_init, s);
+            return rc;
+        }
+    }
     const int slab_max = 16384;
     // the private stream set shares this handle's weights (shallow copy, non-owning)
     if (!ctx->clip_ctx) {

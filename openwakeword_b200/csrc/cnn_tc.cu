@@ -510,6 +510,13 @@ int oww_cnn_tc_clip(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb
     const int W = (T - OWW_WINDOW_ROWS) / 8 + 1;
     return oww_cnn_tc_pyramid_impl(ctx, src, n, OWW_WINDOW_ROWS + 8 * (W - 1), ctx->split_from, d_emb, -1, nullptr, nullptr, s);
 }
+// same, the embeddings of input i landing at d_emb + i * out_rows * 96 (rows of a larger per-input array)
+int oww_cnn_tc_clip_rows(oww_ctx* ctx, const WindowSrc& src, int n, int T, float* d_emb, int out_rows, cudaStream_t s) {
+    ctx->tc_rows_out_override = out_rows;
+    int rc = oww_cnn_tc_pyramid_impl(ctx, src, n, T, ctx->split_from, d_emb, -1, nullptr, nullptr, s);
+    ctx->tc_rows_out_override = 0;
+    return rc;
+}
 
 template <int TERMS>
 static int dispatch_tc(oww_ctx* ctx, int cgp, int np, const TcConvArgs& a, cudaStream_t s) {
@@ -570,7 +577,7 @@ int oww_cnn_tc_pyramid_impl(oww_ctx* ctx, const WindowSrc& src, int n, int T0, i
             a.p_in = (int64_t)n * T * Wp;
             a.n_tiles = (int)((a.p_in + 127) / 128);
             a.out_split = out_split ? 1 : 0;
-            a.rows_out = T_out;
+            a.rows_out = (last && ctx->tc_rows_out_override) ? ctx->tc_rows_out_override : T_out;
             int rc = in_split ? dispatch_tc<3>(ctx, cgp, np, a, s) : dispatch_tc<1>(ctx, cgp, np, a, s);
             if (rc) return rc;
         }

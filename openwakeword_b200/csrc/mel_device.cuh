@@ -16,6 +16,7 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 // window, 256-point complex radix-4 Stockham FFT of the even/odd-packed frame in the two 256-entry buffers a/b,
 // real-spectrum unpack of the bins the filterbank reads (into pw), sparse mel projection (lane = mel bin) and
 // 10*log10(max(.,1e-10)).  Returns this lane's dB value (before the per-call clamp and the x/10+2 affine).
+template <bool kBodyGlobal = true>     // false: `body` points into shared memory (plain loads instead of ld.global.nc)
 __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, const int16_t* body, int f, float2* a, float2* b,
                                               float* pw_buf, const float2* s_tw, const float* s_win, int kmax, int my_start,
                                               int my_len, const float* my_w, int lane) {
@@ -26,8 +27,11 @@ __device__ __forceinline__ float mel_frame_db(const int16_t* tail, int prefix, c
             const int s0 = f * OWW_HOP + 2 * n;
             float x0, x1;
             if (s0 + 1 < prefix) { x0 = (float)tail[s0]; x1 = (float)tail[s0 + 1]; }
-            else if (s0 >= prefix) { x0 = (float)__ldg(body + (s0 - prefix)); x1 = (float)__ldg(body + (s0 + 1 - prefix)); }
-            else { x0 = (float)tail[s0]; x1 = (float)__ldg(body); }
+            else if (s0 >= prefix) {
+                if (kBodyGlobal) { x0 = (float)__ldg(body + (s0 - prefix)); x1 = (float)__ldg(body + (s0 + 1 - prefix)); }
+                else { x0 = (float)body[s0 - prefix]; x1 = (float)body[s0 + 1 - prefix]; }
+            }
+            else { x0 = (float)tail[s0]; x1 = kBodyGlobal ? (float)__ldg(body) : (float)body[0]; }
             a[n] = make_float2(__fmul_rn(x0, s_win[2 * n]), __fmul_rn(x1, s_win[2 * n + 1]));
         }
         __syncwarp();

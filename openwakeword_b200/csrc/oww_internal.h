@@ -141,6 +141,7 @@ struct oww_ctx {
     float* d_tc_sb = nullptr;        // padded scale/bias per layer
     void* d_tc_w3 = nullptr;         // split variant: per layer [hi block | lo block] of W * 2^s (offsets = 2 x tc_w_off)
     float* d_tc_sb3 = nullptr;       // scale * 2^-s | bias
+    int tc_rows_out_override = 0;    // clip pass: embedding rows per input in the caller's array (0 = tightly packed)
     int split_from = 11;             // window / clip passes: conv layers >= split_from take fp16 hi/lo split operands
                                      // (fp32-grade products); OWW_N_CONV = plain fp16 everywhere
     size_t tc_w_off[OWW_N_CONV] = {0};
@@ -198,6 +199,7 @@ struct oww_ctx {
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remembered per handle
     bool heads_attr_set = false;
     bool heads_tc_attr_set = false;
+    bool mel_clip_attr_set = false;
     uint32_t tc_attr_mask = 0;
     bool tc_heads = true;            // modes 2/3: first head layer on tensor cores when the head allows it (reserved[0] bit 1 disables)
     int tc_heads_terms = 3;          // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = plain fp16 operands
@@ -237,6 +239,10 @@ struct MelLaunch {
     const int* ids = nullptr;      // streaming only: clip j is stream ids[j] (body / tail / seen / ring rows of that stream)
 };
 int oww_mel_launch(oww_ctx* ctx, const MelLaunch& p, cudaStream_t s);
+// bulk path: mel rows of whole padded clips, grouped and clamped per streaming call, behind 71 rows of ones:
+// d_out [n_clips][76 + 8 (steps - 1)][32] (the virtual history a fully convolutional CNN pass reproduces predict_clip from)
+int oww_mel_clips_launch(oww_ctx* ctx, const int16_t* d_pcm, int64_t clip_stride, int n_clips, int n_samples, int pad, int steps,
+                         float* d_out, int64_t out_stride, cudaStream_t s);
 
 // ---- cnn_fp32.cu ----
 // Window-mode embedding CNN on n windows.  Source of window j:
@@ -262,6 +268,7 @@ size_t oww_tc_act_units(const oww_ctx* ctx, int n_windows);
 size_t oww_tc_act_units_T(const oww_ctx* ctx, int n, int T0);
 // fully-convolutional pass over linear mel [n][T][32] -> [n][(T-76)/8+1][96] on the tensor cores
 int oww_cnn_tc_clip(oww_ctx* ctx, const float* d_mel, int n, int T, float* d_emb, cudaStream_t s);
+int oww_cnn_tc_clip_rows(oww_ctx* ctx, const WindowSrc& src, int n, int T, float* d_emb, int out_rows, cudaStream_t s);
 // incremental late layers of mode 3 (split operands)
 int oww_late_alloc(oww_ctx* ctx);
 int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s);

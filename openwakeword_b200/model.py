@@ -335,9 +335,14 @@ class Model:
     def predict_clips_array(self, clips, padding=1, feature_init=None):
         """-> (float32 [N, steps, n_labels], labels) with the first-5-steps zeroing of model.py:330-333 applied."""
         torch = _torch()
-        clips = np.ascontiguousarray(np.asarray(clips))
-        if clips.dtype != np.int16:
-            clips = clips.astype(np.int16)
+        if isinstance(clips, torch.Tensor):            # CPU (ideally pinned) or CUDA int16 tensor: no host copy
+            if clips.dtype != torch.int16:
+                clips = clips.to(torch.int16)
+            clips = clips.contiguous()
+        else:
+            clips = np.ascontiguousarray(np.asarray(clips))
+            if clips.dtype != np.int16:
+                clips = clips.astype(np.int16)
         N, S = clips.shape
         L = S + 2 * 16000 * padding
         steps = len(range(0, L - CHUNK, CHUNK))
@@ -345,7 +350,7 @@ class Model:
         if fi is None:
             fi = self.preprocessor._get_embeddings(np.random.randint(-1000, 1000, 16000 * 4).astype(np.int16))
         dev = f"cuda:{self.preprocessor.device_index}"
-        d = torch.from_numpy(clips).to(dev)
+        d = clips.to(dev, non_blocking=True) if isinstance(clips, torch.Tensor) else torch.from_numpy(clips).to(dev)
         raw = torch.zeros((N, steps, max(self._n_cols, 1)), dtype=torch.float32, device=dev)
         self.preprocessor.ctx.predict_clips(d, N, S, 16000 * padding, fi, raw, torch.cuda.current_stream(d.device).cuda_stream)
         raw = raw.cpu().numpy()

@@ -73,13 +73,13 @@ class AudioFeatures:
 
     def __init__(self, melspec_model_path="", embedding_model_path="", sr=16000, ncpu=1,
                  inference_framework="b200", device="gpu", n_streams=1, feature_init=None,
-                 max_chunks=8, cnn_mode=_native.CNN_TC_INCREMENTAL, window_batch=0, device_index=0):
+                 max_chunks=8, cnn_mode=_native.CNN_TC_INCREMENTAL, window_batch=0, device_index=0, split_from=11):
         if inference_framework != "b200":
             raise ValueError(f"openwakeword_b200 only provides inference_framework='b200' (got '{inference_framework}')")
         if sr != 16000:
             raise ValueError("only 16 kHz audio is supported")
         self.ctx = _native.Context(device=device_index, max_chunks=max_chunks, cnn_mode=cnn_mode,
-                                   window_batch=window_batch)
+                                   window_batch=window_batch, split_from=split_from)
         if melspec_model_path.endswith(".npz"):
             z = np.load(melspec_model_path)
             self.ctx.load_mel(z["window"], z["mel_fb"])
@@ -357,14 +357,21 @@ def bulk_predict(file_paths, wakeword_models, prediction_function="predict_clip"
     init_kw = {k: v for k, v in kwargs.items() if k in init_names}
     clip_kw = {k: v for k, v in kwargs.items() if k not in init_names}
     mdl = Model(wakeword_models=wakeword_models, inference_framework=inference_framework, **init_kw)
-    clips = _read_wavs(file_paths, ncpu)
+    clips = _read_wavs(file_paths, ncpu)                       # RIFF parsing on ncpu host threads, order kept
     out = {}
     by_len = {}
     for p, c in zip(file_paths, clips):
         by_len.setdefault(c.shape[0], []).append(p)
     lookup = dict(zip(file_paths, clips))
-    for _, paths in by_len.items():
-        res = mdl.predict_clips(np.stack([lookup[p] for p in paths]), **clip_kw)
+    torch = _torch()
+    for length, paths in by_len.items():
+        # equal-length clips form one device batch; they are gathered in page-locked memory so the H2D copy is a single
+        # asynchronous DMA (the reference forks one process per ncpu instead, utils.py:505-536)
+        stage = torch.empty((len(paths), length), dtype=torch.int16, pin_memory=True)
+        view = stage.numpy()
+        for i, p in enumerate(paths):
+            view[i] = lookup[p]
+        res = mdl.predict_clips(stage, **clip_kw)
         for p, r in zip(paths, res):
             out[p] = r
     return out

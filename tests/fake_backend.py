@@ -40,7 +40,7 @@ def unpack_head_blob(n_in, dims, layernorm, final_act, blob):
 class FakeContext:
     instances = []
 
-    def __init__(self, device=0, max_chunks=4, cnn_mode=0, window_batch=0, fuse_step=True, **kw):
+    def __init__(self, device=0, max_chunks=4, cnn_mode=0, window_batch=0, fuse_step=True, split_from=11, **kw):
         self.max_chunks = max_chunks
         self.heads = []
         self.gates = []

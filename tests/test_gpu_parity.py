@@ -350,3 +350,77 @@ def test_model_from_onnx_files(torch_cuda, built_library, tmp_path):
     assert list(res[0].keys()) == c["labels"]
     got = np.array([[r[l] for l in c["labels"]] for r in res], dtype=np.float32)
     assert np.abs(got - c["scores"]).max() < SCORE_TOL
+
+
+def _write_wav(path, pcm):
+    import wave
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+        f.writeframes(np.asarray(pcm, np.int16).tobytes())
+
+
+def test_bulk_predict_file_paths_on_reference_wavs(torch_cuda, built_library, tmp_path):
+    """utils.bulk_predict(file_paths=...) end to end (reference signature, utils.py:467-539) on WAV files holding the
+    audio of the reference's three test clips (tests/data/{alexa_test,hey_mycroft_test,hey_jane}.wav; their samples
+    travel inside the golden fixtures) plus two synthetic clips of a shared length (one batched group): threaded RIFF
+    ingest -> pinned staging -> the bulk device path (one mel launch per slab, fully convolutional tcgen05 CNN, heads
+    over all sliding windows).  Every clip's result must equal the golden scores the UNMODIFIED reference plumbing
+    produced for predict_clip on a fresh model (1e-3), and the bulk path must be bit-identical to streaming the clip."""
+    import openwakeword_b200 as owb
+    from openwakeword_b200 import utils as U
+    cases = {"alexa_test": load_case("alexa_c1280"), "hey_mycroft_test": load_case("mycroft_all4_c1280"),
+             "hey_jane": load_case("jane_all4_c1280")}
+    names = ["alexa_v0.1", "hey_mycroft_v0.1", "timer_v0.1", "big_v0.1"]
+    paths = []
+    for nm, c in cases.items():
+        p = tmp_path / f"{nm}.wav"
+        _write_wav(p, c["pcm"])
+        paths.append(str(p))
+    rng = np.random.default_rng(8)
+    for i in range(2):
+        p = tmp_path / f"synthetic_{i}.wav"
+        _write_wav(p, np.clip(rng.normal(0, 3000, 20000), -32768, 32767).astype(np.int16))
+        paths.append(str(p))
+    fi = cases["hey_jane"]["feature_init"]
+    specs = [{"name": n, "head": head(n), "class_mapping": class_mapping([n]).get(n)} for n in names]
+    res = U.bulk_predict(paths, wakeword_models=specs, ncpu=3, embedding_model_path=emb_weights(), feature_init=fi)
+    assert set(res) == set(paths)
+    labels = cases["hey_jane"]["labels"]
+    # jane_all4_c1280 was generated with exactly these four heads and this feature_init: golden comparison
+    got = np.array([[r[l] for l in labels] for r in res[paths[2]]], np.float32)
+    assert got.shape == cases["hey_jane"]["scores"].shape
+    d = np.abs(got - cases["hey_jane"]["scores"]).max()
+    print("bulk_predict(hey_jane.wav) vs reference-plumbing golden: max |delta| =", d)
+    assert d < SCORE_TOL
+    # every file: bulk == streaming predict_clip on a fresh model (same kernels, same arithmetic -> bit-identical)
+    m = owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(), feature_init=fi)
+    for p in paths:
+        m.reset()
+        ref = m.predict_clip(p)
+        assert len(ref) == len(res[p])
+        a = np.array([[r[l] for l in labels] for r in ref], np.float32)
+        b = np.array([[r[l] for l in labels] for r in res[p]], np.float32)
+        assert np.array_equal(a, b), (p, np.abs(a - b).max())
+
+
+def test_embed_clips_and_feature_generator_on_gpu(torch_cuda, built_library, tmp_path):
+    """AudioFeatures.embed_clips on the default (tensor-core, fully convolutional) path against the reference-plumbing
+    golden, and utils.compute_features_from_generator writing the same features through its memmap (utils.py:542-601)."""
+    from openwakeword_b200 import AudioFeatures, utils as U
+    c = load_case("embed_clips")
+    af = AudioFeatures(embedding_model_path=emb_weights())
+    got = af.embed_clips(c["pcm"])
+    d = np.abs(got - c["embeddings"]).max()
+    print("embed_clips (tcgen05 clip pass) vs golden: max |delta| =", d)
+    assert got.shape == (3, 16, 96) and d < 2e-3
+    rng = np.random.default_rng(5)
+    clips = np.clip(rng.normal(0, 4000, (10, 32000)), -32768, 32767).astype(np.int16)
+
+    def gen():
+        for i in range(0, 10, 4):
+            yield clips[i:i + 4]
+    out = str(tmp_path / "feats.npy")
+    U.compute_features_from_generator(gen(), n_total=16, clip_duration=32000, output_file=out, audio_features=af)
+    feats = np.load(out)
+    assert feats.shape == (10, 16, 96)
+    assert np.array_equal(feats, af.embed_clips(clips))
