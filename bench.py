@@ -159,14 +159,36 @@ def _cpu_worker(conn, stream_id, seed, workload):
     except Exception:
         pass
     from openwakeword_b200 import weights as W
-    from oracle import streaming
-    emb = W.synthetic_embedding(0)
-    heads = bench_heads(workload)
-    cm = {"timer": dict(TIMER_MAP)} if "timer" in heads else None
-    om = streaming.OracleModel(emb, heads, cm, feature_init=np.zeros((41, 96), np.float32))
+    from oracle import streaming, probe
+    om = None
+    ok, where = probe.ort_reference_available()
+    if ok:
+        # the genuine reference: unmodified openwakeword.Model on onnxruntime CPU with the released models (never the case
+        # in this image - SURVEY.md F2 - but the arm upgrades itself when the assets exist)
+        try:
+            import glob
+            for extra in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+                if os.path.isdir(extra) and extra not in sys.path:
+                    sys.path.insert(0, extra)
+            import openwakeword
+            hp = sorted(p for p in glob.glob(os.path.join(where, "*.onnx"))
+                        if os.path.basename(p) not in ("melspectrogram.onnx", "embedding_model.onnx", "silero_vad.onnx"))
+            if workload == "c2":
+                hp = [p for p in hp if "alexa" in os.path.basename(p)][:1] or hp[:1]
+            om = openwakeword.Model(wakeword_models=hp, inference_framework="onnx",
+                                    melspec_model_path=os.path.join(where, "melspectrogram.onnx"),
+                                    embedding_model_path=os.path.join(where, "embedding_model.onnx"))
+        except Exception:          # noqa: BLE001
+            om = None
+    kind = "reference" if om is not None else "port"
+    if om is None:
+        emb = W.synthetic_embedding(0)
+        heads = bench_heads(workload)
+        cm = {"timer": dict(TIMER_MAP)} if "timer" in heads else None
+        om = streaming.OracleModel(emb, heads, cm, feature_init=np.zeros((41, 96), np.float32))
     pcm = synth_pcm(stream_id % 4 + 1, 64, seed + stream_id // 4)[stream_id % 4]
     pos = 0
-    conn.send("ready")
+    conn.send("ready:" + kind)
     while True:
         n = conn.recv()
         if n <= 0:
@@ -217,8 +239,12 @@ class CpuArm:
             p = ctx.Process(target=_cpu_worker, args=(b, i, 1234, workload), daemon=True)
             p.start()
             self.workers.append((p, a))
+        kinds = set()
         for _, a in self.workers:
-            assert a.recv() == "ready"
+            msg = a.recv()
+            assert msg.startswith("ready:")
+            kinds.add(msg.split(":")[1])
+        self.kind = "reference" if kinds == {"reference"} else "port"
 
     def step(self, frames_each):
         t0 = time.perf_counter()
@@ -263,7 +289,7 @@ def run_reference_arm(args):
         "config": {"workload": WORKLOADS[wl]["label"] + " - sampled: one single-stream model per host core (the reference's "
                                "own deployment shape); onnxruntime + .onnx files are absent in this image, so the NumPy oracle port is timed",
                    "streams": arm.P, "heads": n_heads},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.P, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": arm.P, "kind": arm.kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -467,7 +493,7 @@ def run_own_arm(args):
             tt += arm.step(4)
             fr += arm.P * 4
         arm.close()
-        cpu = {"value": fr / tt, "unit": UNIT, "cores": arm.P, "kind": "port",
+        cpu = {"value": fr / tt, "unit": UNIT, "cores": arm.P, "kind": arm.kind,
                "sample": f"{arm.P} single-stream NumPy-oracle models (1 BLAS thread each, one per usable core; "
                          f"os.cpu_count()={os.cpu_count()}), {main['heads']} heads, x {fr // arm.P} frames, {tt:.1f} s; "
                          "onnxruntime CPU unavailable in this image"}
