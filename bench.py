@@ -339,7 +339,7 @@ def measure(args, wl, rank, world, local, dev, sampler_windows, do_model=True):
     def factory(n_local, lo, hi):
         return StreamEngine(list(heads.values()), n_local, embedding="synthetic:0", device_index=local, max_chunks=1,
                             cnn_mode=args.cnn_mode, fuse_step=not args.no_fuse, tc_heads=not args.no_tc_heads,
-                            tc_heads_terms=args.tc_heads_terms)
+                            tc_heads_terms=args.tc_heads_terms, split_from=args.split_from)
     sh = owd.ShardedStreams(n_total, factory, rank=rank, world=world, gather=args.gather)
     eng = sh.engine
     host_pcm = synth_pcm_fast(B, POOL, 1234 + rank)
@@ -401,7 +401,7 @@ def measure(args, wl, rank, world, local, dev, sampler_windows, do_model=True):
         from openwakeword_b200 import Model
         specs = [{"name": n, "head": h, "class_mapping": (dict(TIMER_MAP) if n == "timer" else None)} for n, h in heads.items()]
         m = Model(wakeword_models=specs, embedding_model_path="synthetic:0", n_streams=B, feature_init=np.zeros((41, 96), np.float32),
-                  max_chunks=1, device_index=local, cnn_mode=args.cnn_mode)
+                  max_chunks=1, device_index=local, cnn_mode=args.cnn_mode, split_from=args.split_from)
         for k in range(max(Wm, 6)):
             m.predict(host_steps[k % POOL])
         torch.cuda.synchronize()
@@ -512,6 +512,7 @@ def run_own_arm(args):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload]["label"],
                    "streams_per_gpu": B, "heads": main["heads"], "score_columns": main["n_cols"], "cnn_mode": args.cnn_mode,
+                   "split_from": args.split_from,
                    "fused_step": bool(fused),
                    "l2": "inputs larger than L2: distinct PCM batches totalling >= 168 MB cycled",
                    "weights": "synthetic seed 0 (reference shapes); released .onnx weights absent",
@@ -572,6 +573,9 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="mode 3: keep mel / CNN / append / heads as separate launches (stage breakdown)")
     ap.add_argument("--no-tc-heads", action="store_true", help="heads on CUDA cores (heads.cu)")
     ap.add_argument("--tc-heads-terms", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--split-from", type=int, default=11,
+                    help="first conv layer on fp16 hi/lo split operands (11 = default, scores within ~2e-4 of the fp32 graph; "
+                         "20 = plain fp16 everywhere and the whole step as one fused launch, ~9e-4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -2,6 +2,7 @@
 // orchestration of one streaming step  PCM -> K1 mel -> K2 embedding CNN -> ring append -> K3 heads.
 #include "oww_internal.h"
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 

@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + kStages * stage_bytes);
     // bars: [0..S) full, [S..2S) empty, [2S..2S+A) tmem_full, [..+A) tmem_empty, then w_full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kAccStages + 1);
+    float* s_sb = reinterpret_cast<float*>(tmem_slot + 4);                 // folded BN scale[NP] | bias[NP], read by every epilogue thread
+    for (int i = threadIdx.x; i < NP; i += kTcThreads) { s_sb[i] = a.scale[i]; s_sb[NP + i] = a.bias[i]; }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }   // 8 epilogue warps
         mbar_init(wfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -228,8 +230,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
             }
         }
     } else {
-        // ===================== epilogue: 4 warps, one TMEM lane quarter each =====================
-        const int quarter = warp & 3;
+        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 halves of the channel-group planes ============
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        constexpr int NP8 = NP / 8, PH = NP8 / 2;              // planes per half (NP8 is even for every instance)
+        const int pl0 = half * PH;
         const int row = quarter * 32 + lane;
         const int Wp = a.W + 1;
         const int per_in = a.T * Wp;
@@ -238,10 +242,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            uint32_t v[NP];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u;
+            uint32_t v[PH * 8];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u + (uint32_t)pl0 * 8u;
 #pragma unroll
-            for (int c = 0; c < NP; c += 16) tmem_ld16(taddr + c, v + c);
+            for (int k = 0; k < PH; ++k) tc_tmem_ld8(taddr + k * 8, v + k * 8);
             tmem_wait_ld();
             tc_fence_before();
             __syncwarp();
@@ -258,13 +262,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 if (f != 0) continue;
                 float* o = a.out_f32 + ((int64_t)n * a.rows_out + t) * 96;
 #pragma unroll
-                for (int c = 0; c < 96 && c < NP; c += 4) {
-                    float4 r4;
-                    r4.x = fmaf(__uint_as_float(v[c + 0]), __ldg(a.scale + c + 0), __ldg(a.bias + c + 0));
-                    r4.y = fmaf(__uint_as_float(v[c + 1]), __ldg(a.scale + c + 1), __ldg(a.bias + c + 1));
-                    r4.z = fmaf(__uint_as_float(v[c + 2]), __ldg(a.scale + c + 2), __ldg(a.bias + c + 2));
-                    r4.w = fmaf(__uint_as_float(v[c + 3]), __ldg(a.scale + c + 3), __ldg(a.bias + c + 3));
-                    reinterpret_cast<float4*>(o)[c >> 2] = r4;
+                for (int k = 0; k < PH; ++k) {
+                    const int c = (pl0 + k) * 8;
+                    if (c >= 96) continue;
+                    float4 r0, r1;
+                    r0.x = fmaf(__uint_as_float(v[k * 8 + 0]), s_sb[c + 0], s_sb[NP + c + 0]);
+                    r0.y = fmaf(__uint_as_float(v[k * 8 + 1]), s_sb[c + 1], s_sb[NP + c + 1]);
+                    r0.z = fmaf(__uint_as_float(v[k * 8 + 2]), s_sb[c + 2], s_sb[NP + c + 2]);
+                    r0.w = fmaf(__uint_as_float(v[k * 8 + 3]), s_sb[c + 3], s_sb[NP + c + 3]);
+                    r1.x = fmaf(__uint_as_float(v[k * 8 + 4]), s_sb[c + 4], s_sb[NP + c + 4]);
+                    r1.y = fmaf(__uint_as_float(v[k * 8 + 5]), s_sb[c + 5], s_sb[NP + c + 5]);
+                    r1.z = fmaf(__uint_as_float(v[k * 8 + 6]), s_sb[c + 6], s_sb[NP + c + 6]);
+                    r1.w = fmaf(__uint_as_float(v[k * 8 + 7]), s_sb[c + 7], s_sb[NP + c + 7]);
+                    reinterpret_cast<float4*>(o + c)[0] = r0;
+                    reinterpret_cast<float4*>(o + c)[1] = r1;
                 }
                 continue;
             }
@@ -273,13 +284,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
             uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + po;
             const bool pad = f == a.W;
 #pragma unroll
-            for (int g = 0; g < NP / 8; ++g) {
+            for (int k = 0; k < PH; ++k) {
+                const int g = pl0 + k;
                 __half2 h[4], l[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int c = g * 8 + u * 2;
-                    float y0 = fmaf(__uint_as_float(v[c]), __ldg(a.scale + c), __ldg(a.bias + c));
-                    float y1 = fmaf(__uint_as_float(v[c + 1]), __ldg(a.scale + c + 1), __ldg(a.bias + c + 1));
+                    float y0 = fmaf(__uint_as_float(v[k * 8 + u * 2]), s_sb[c], s_sb[NP + c]);
+                    float y1 = fmaf(__uint_as_float(v[k * 8 + u * 2 + 1]), s_sb[c + 1], s_sb[NP + c + 1]);
                     if (a.apply_act) { y0 = act(y0); y1 = act(y1); }
                     if (pad) { y0 = 0.f; y1 = 0.f; }
                     const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
@@ -294,10 +306,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                         if (po == 0) o[(int64_t)(a.cg_out + g) * a.out_plane - 1] = make_uint4(0, 0, 0, 0);
                     }
 #pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        if (a.out_b[k]) {
-                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[k]) + kGuard + (int64_t)n * a.out_T * Wp +
-                                        (int64_t)(t + a.out_b_toff[k]) * Wp + f;
+                    for (int kk = 0; kk < 2; ++kk)
+                        if (a.out_b[kk]) {
+                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[kk]) + kGuard + (int64_t)n * a.out_T * Wp +
+                                        (int64_t)(t + a.out_b_toff[kk]) * Wp + f;
                             ob[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
                             if (a.out_split) ob[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
                         }
@@ -397,7 +409,7 @@ template <int CGP, int NP, int TERMS>
 int launch_tc(oww_ctx* ctx, const TcConvArgs& a, cudaStream_t s) {
     constexpr int split = TERMS == 3 ? 2 : 1, stages = TERMS == 3 ? 2 : 4;
     const size_t smem = (size_t)split * 3 * CGP * NP * 16 + (size_t)stages * split * CGP * a.rows * 16 +
-                        8 * (2 * stages + 2 * kAccStages + 1) + 16;
+                        8 * (2 * stages + 2 * kAccStages + 1) + 16 + 2 * NP * sizeof(float);
     if (smem > 227 * 1024) return oww_fail(ctx, OWW_EUNSUPPORTED, "tcgen05 conv tile does not fit shared memory (%zu bytes)", smem);
     // the attribute is per (function, device): tracked per handle (one bit per kernel instance), not per process
     const uint32_t bit = 1u << (((CGP / 2 + NP / 16) + (TERMS == 3 ? 16 : 0)) & 31);     // distinct for the instances in use

@@ -77,15 +77,20 @@ __device__ __forceinline__ int head_rows(int slot_bytes, int K, int D) {
 }
 
 // 96 registers is the ceiling for 18 warps: registers are allocated for warps in fours (20 x 32 x 96 = 61 440 of 65 536)
+// kNL: number of conv layers the kernel runs, fixed at compile time (20 = whole CNN, 11 = the default cut before the
+// split-operand layers) or 0 = read from the plan (any other cut).  With the count known the full-depth instance
+// carries none of the cut layer's code.
+template <int kNL>
 __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_constant__ IncArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     const IncPlan& P = a.plan;
+    const int NL = kNL ? kNL : P.n_layers;
     const int G = P.G;
     // [0, 2048): barriers, TMEM slot, layer-0 weights.  Activations grow from 2048 up; the per-layer weight
     // slots sit at the top of the arena (offsets in the plan, checked against the activation extents).
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * kIncAcc);
-    float* s_l0 = reinterpret_cast<float*>(smem + 256);              // 9*24 + 24 + 24 floats
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * kIncAcc);      // 22 barriers: [0, 176)
+    float* s_l0 = reinterpret_cast<float*>(smem + 704);              // 9*24 + 24 + 24 floats: [704, 1760)
     uint4* act0 = reinterpret_cast<uint4*>(smem + 2048);            // activation arena; tensors at plan offsets
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
             uint32_t par[2] = {0, 0};
             uint32_t hs_par = 0, he_par = 0; int hchunk = 0;
             for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-                for (int l = 1; l < P.n_layers; ++l) {
+                for (int l = 1; l < NL; ++l) {
                     const int i = l & 1;
                     mbar_wait(wempty(i), par[i] ^ 1);
                     mbar_expect_tx(wfull(i), (uint32_t)P.L[l].w_bytes);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         bool have_prev = false; int prev_i = 0;
         uint32_t tails_par = 0;
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
-            for (int l = 1; l < P.n_layers; ++l) {
+            for (int l = 1; l < NL; ++l) {
                 const IncLayer& L = P.L[l];
                 named_bar_sync(1, (kIncEpiWarps + 1) * 32);       // layer l-1 output complete and fenced
                 tc_fence_after();
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
         for (int grp = blockIdx.x; grp < P.n_groups; grp += gridDim.x) {
             const uint4* tin = a.tails_in + (int64_t)grp * P.tail_units;
             uint4* tout = a.tails_out + (int64_t)grp * P.tail_units;
-            int* s_cnt = reinterpret_cast<int*>(smem + 1536);      // [0..7] mel row count, [8..15] feature count, before this step
+            int* s_cnt = reinterpret_cast<int*>(smem + 512);       // [0..7] mel row count, [8..15] feature count, before this step
             int* s_live = s_cnt + 16;                              // [0..7] stream exists, [8..15] it is fresh (first chunk after a reset)
             float* s_mel = reinterpret_cast<float*>(smem + P.scratch_off + 6144);   // [G][8][32] this step's mel rows
             if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[101] = clock64();
@@ -324,9 +329,9 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
             }
-            for (int l = 0; l < P.n_layers; ++l) {
+            for (int l = 0; l < NL; ++l) {
                 const IncLayer& L = P.L[l];
-                const bool to_global = l == P.n_layers - 1 && P.n_layers < OWW_N_CONV;   // cut plan: pooled output -> HBM (hi/lo)
+                const bool to_global = kNL != OWW_N_CONV && l == NL - 1 && NL < OWW_N_CONV;   // cut plan: pooled output -> HBM (hi/lo)
                 if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[l] = clock64();
                 uint4* nx = act0 + L.nx_base;
                 // ---- (a) tails of the buffer this phase fills (rows 0..1) and front guards.  In a pool phase that
@@ -483,21 +488,26 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             const float4* sc4 = reinterpret_cast<const float4*>(sb + pl * 8);
                             const float4* bi4 = reinterpret_cast<const float4*>(sb + L.np + pl * 8);
                             const float4 s0 = sc4[0], s1 = sc4[1], b0 = bi4[0], b1 = bi4[1];
-                            const float y[8] = {act(fmaf(__uint_as_float(v[k][0]), s0.x, b0.x)), act(fmaf(__uint_as_float(v[k][1]), s0.y, b0.y)),
-                                                act(fmaf(__uint_as_float(v[k][2]), s0.z, b0.z)), act(fmaf(__uint_as_float(v[k][3]), s0.w, b0.w)),
-                                                act(fmaf(__uint_as_float(v[k][4]), s1.x, b1.x)), act(fmaf(__uint_as_float(v[k][5]), s1.y, b1.y)),
-                                                act(fmaf(__uint_as_float(v[k][6]), s1.z, b1.z)), act(fmaf(__uint_as_float(v[k][7]), s1.w, b1.w))};
                             __half2 h[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) h[u] = __floats2half2_rn(y[2 * u], y[2 * u + 1]);
+                            h[0] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][0]), s0.x, b0.x)), act(fmaf(__uint_as_float(v[k][1]), s0.y, b0.y)));
+                            h[1] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][2]), s0.z, b0.z)), act(fmaf(__uint_as_float(v[k][3]), s0.w, b0.w)));
+                            h[2] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][4]), s1.x, b1.x)), act(fmaf(__uint_as_float(v[k][5]), s1.y, b1.y)));
+                            h[3] = __floats2half2_rn(act(fmaf(__uint_as_float(v[k][6]), s1.z, b1.z)), act(fmaf(__uint_as_float(v[k][7]), s1.w, b1.w)));
                             const uint4 pk = pad ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<uint4*>(h);
                             d0[pl * dpitch] = pk;
                             if (keep_tail) t0[pl * (2 * G * L.Wp)] = pk;
-                            if (to_global) {                      // the unpooled temp also keeps the lo parts: y = hi + lo
+                            if (to_global) {
+                                // cut layer only (warp-uniform, one layer per step): the unpooled temp also keeps the lo parts
+                                // (y = hi + lo).  The values are recomputed here so the common path above carries no extra registers.
+                                const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                                 __half2 lo[4];
 #pragma unroll
-                                for (int u = 0; u < 4; ++u)
-                                    lo[u] = __floats2half2_rn(y[2 * u] - __low2float(h[u]), y[2 * u + 1] - __high2float(h[u]));
+                                for (int u = 0; u < 4; ++u) {
+                                    const float y0 = act(fmaf(__uint_as_float(v[k][2 * u]), sv[2 * u], bv[2 * u]));
+                                    const float y1 = act(fmaf(__uint_as_float(v[k][2 * u + 1]), sv[2 * u + 1], bv[2 * u + 1]));
+                                    lo[u] = __floats2half2_rn(y0 - __low2float(h[u]), y1 - __high2float(h[u]));
+                                }
                                 d0[(L.cg_out + pl) * dpitch] = pad ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<uint4*>(lo);
                             }
                         }
@@ -585,13 +595,13 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 if (L.nx_tail_off >= 0) epi_tails_par ^= 1;
                 // ---- phase done: make generic-proxy smem writes visible to the tensor core ----
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (l < P.n_layers - 1) {
+                if (l < NL - 1) {
                     tc_fence_before();
                     named_bar_sync(1, (kIncEpiWarps + 1) * 32);
                 }
             }
             if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[OWW_N_CONV] = clock64();
-            if (a.fused && P.n_layers == OWW_N_CONV) {
+            if (a.fused && NL == OWW_N_CONV) {
                 // ===== K3 inside the step kernel: every head on this group's streams, straight from the feature ring =====
                 named_bar_sync(2, kIncEpiWarps * 32);              // the new embedding rows (written by this CTA) are visible
                 if (a.n_heads > 0) {                               // n_heads == 0: the heads run as their own launch after this one
@@ -994,7 +1004,9 @@ int oww_inc_alloc_streams(oww_ctx* ctx) {
     }
     ctx->inc_cur = 0;
     ctx->tails_template_valid = false;                   // the scatter table depends on the group size
-    OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
+    OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<OWW_N_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
+    OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
+    OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
     return OWW_OK;
 }
 
@@ -1047,6 +1059,12 @@ bool oww_fused_heads_supported(const oww_ctx* ctx) {
     return 2048 + floats * 4 + 128 + (size_t)96 * d1max * 4 <= (size_t)ctx->inc_plan.L[2].w_smem;
 }
 
+static void launch_inc(const IncArgs& a, int grid, cudaStream_t s) {
+    if (a.plan.n_layers == OWW_N_CONV) tc_inc_kernel<OWW_N_CONV><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    else if (a.plan.n_layers == 11) tc_inc_kernel<11><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    else tc_inc_kernel<0><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+}
+
 static void fill_inc_args(oww_ctx* ctx, IncArgs& a) {
     std::memset(&a, 0, sizeof(a));
     a.plan = ctx->inc_plan;
@@ -1093,7 +1111,7 @@ int oww_fused_step(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, float
         if (a.hns < 1 && !ctx->heads.empty()) return oww_fail(ctx, OWW_EUNSUPPORTED, "no room for the fused heads weight ring");
     }
     const int grid = a.plan.n_groups < ctx->sm_count ? a.plan.n_groups : ctx->sm_count;
-    tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    launch_inc(a, grid, s);
     OWW_LAUNCH_CHECK(ctx);
     ctx->inc_cur ^= 1;
     return OWW_OK;
@@ -1106,7 +1124,7 @@ int oww_cnn_inc_step(oww_ctx* ctx, int back, float* d_emb, cudaStream_t s) {
     a.back = back;
     a.emb = d_emb;
     const int grid = a.plan.n_groups < ctx->sm_count ? a.plan.n_groups : ctx->sm_count;
-    tc_inc_kernel<<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    launch_inc(a, grid, s);
     OWW_LAUNCH_CHECK(ctx);
     ctx->inc_cur ^= 1;
     if (ctx->late_active) return oww_late_chain(ctx, d_emb, s);

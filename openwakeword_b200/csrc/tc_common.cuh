@@ -12,7 +12,7 @@ constexpr int kGuard = 8;          // 16-byte units of zero guard in front of ev
 constexpr int kGuardBack = 384;    // readable units behind the last position
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;    // producer, MMA issuer, 8 epilogue warps
 
 // -DOWW_ACT_MAX3=1: one 3-input max (FMNMX3 on sm_100) instead of two FMNMX - same result for every non-NaN input.
 // Off until it has been A/B-timed on hardware (scripts/gpu_variants.sh).
@@ -81,6 +81,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
