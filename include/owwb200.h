@@ -69,7 +69,12 @@ typedef struct oww_config {
                               (mel, CNN, append, heads) instead of the single fused step kernel;
                               bit 1: 1 = heads on CUDA cores (heads.cu) even in the tensor-core modes;
                               bit 2: 1 = tensor-core heads with plain fp16 operands (1 MMA term instead of the
-                              fp32-grade 3-term hi/lo split)                                          */
+                              fp32-grade 3-term hi/lo split);
+                              bit 3: 1 = one tensor-core heads CTA per (128 streams, head) reading the fp32 rings
+                              (heads_tc.cu) instead of one CTA per 128 streams for all heads that share a window,
+                              fed from the fp16 mirror of the rings (heads_grp.cu).
+                              reserved[1]: first conv layer that takes fp16 hi/lo split operands in the
+                              tensor-core modes, 2..20 (0 = default 11; 20 = plain fp16 everywhere)           */
 } oww_config;
 
 typedef struct oww_head_desc {
@@ -190,6 +195,10 @@ int oww_debug_inc_plan(oww_ctx* ctx, int group, int n_streams, int32_t* out, int
  * [101] group start (before the fused frontend), [102] end of the fused heads phase (0 when the step was not fused). */
 int oww_debug_inc_clocks(oww_ctx* ctx, int64_t* h_unused);
 int oww_debug_inc_clocks_read(oww_ctx* ctx, int64_t* h_out104);
+/* Instrumentation of the grouped heads kernel (heads_grp.cu): the first call arms the stamps, later calls synchronise and
+ * return 8 clock64() values per head group (tile 0's CTA): start, producer done, last first-layer MMA issued,
+ * first-layer accumulators complete, team 0 done, CTA end, 0, 0. */
+int oww_debug_heads_clocks(oww_ctx* ctx, int64_t* h_out64);
 
 /* ---- multi-GPU gather over peer memory (one process per GPU) ---------------------------------
  * The reference has no multi-device path; SURVEY.md section 8e defines the only exchange of the sharded hot path: the

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "oww_debug_inc_plan": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
     "oww_debug_inc_clocks": (C.c_int, [_P, _P]),
     "oww_debug_inc_clocks_read": (C.c_int, [_P, _P]),
+    "oww_debug_heads_clocks": (C.c_int, [_P, _P]),
     "oww_peer_alloc": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "oww_peer_free": (C.c_int, [_P, _P]),
     "oww_peer_open": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_void_p)]),
@@ -117,13 +118,14 @@ class Context:
     """One handle = one GPU's weights + stream state (include/owwb200.h conventions)."""
 
     def __init__(self, device=0, max_chunks=4, cnn_mode=CNN_TC_INCREMENTAL, window_batch=0, fuse_step=True,
-                 tc_heads=True, tc_heads_terms=3, split_from=11):
+                 tc_heads=True, tc_heads_terms=3, split_from=11, group_heads=True):
         """split_from: first conv layer that takes fp16 hi/lo split operands in the tensor-core modes (fp32-grade products;
         11 = default: scores within ~2e-4 of the fp32 graph; 20 = plain fp16 everywhere: the whole step as ONE fused
         launch, ~9e-4)."""
         self.lib = load_library()
         cfg = Config(device=device, max_chunks=max_chunks, cnn_mode=cnn_mode, window_batch=window_batch)
-        cfg.reserved[0] = (0 if fuse_step else 1) | (0 if tc_heads else 2) | (4 if tc_heads_terms == 1 else 0)
+        cfg.reserved[0] = ((0 if fuse_step else 1) | (0 if tc_heads else 2) | (4 if tc_heads_terms == 1 else 0)
+                           | (0 if group_heads else 8))
         cfg.reserved[1] = int(split_from)
         h = _P()
         rc = self.lib.oww_create(C.byref(cfg), C.byref(h))
@@ -265,6 +267,12 @@ class Context:
     def debug_inc_clocks_read(self):
         out = np.zeros(104, np.int64)
         self._check(self.lib.oww_debug_inc_clocks_read(self.h, _ptr(out)))
+        return out
+
+    def debug_heads_clocks(self):
+        """First call arms; later calls -> int64[8, 8] clock stamps per head group (include/owwb200.h)."""
+        out = np.zeros(256, np.int64)
+        self._check(self.lib.oww_debug_heads_clocks(self.h, _ptr(out)))
         return out
 
     # ---- peer memory (multi-GPU gather without a collective; include/owwb200.h) ----

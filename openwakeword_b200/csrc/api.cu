@@ -109,6 +109,7 @@ void free_streams(oww_ctx* c) {
     cudaFree(c->d_emb_tmp); cudaFree(c->d_inc_tails[0]); cudaFree(c->d_inc_tails[1]);
     cudaFree(c->d_reset_ids); cudaFree(c->d_reset_init);
     cudaFree(c->d_scores_tmp);
+    oww_heads_grp_drop_mirror(c);
     for (auto& X : c->late_x) for (auto& b : X.buf) { cudaFree(b); b = nullptr; }
     cudaFree(c->d_late_tmp[0]); c->d_late_tmp[0] = nullptr;
     cudaFree(c->d_late_template); c->d_late_template = nullptr;
@@ -205,6 +206,8 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
             if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, 1, s))) return rc;
         }
         if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
+        if (heads_inside) oww_feat16_invalidate(ctx);
+        else if ((rc = oww_feat16_advance(ctx, 1, s))) return rc;
         if (!heads_inside && (rc = oww_heads_all(ctx, fs0, B, d_scores, out_stride, 0, s))) return rc;
         if (ev) {
             if (heads_inside) ctx->ev_fused[slot] = 1;
@@ -231,6 +234,7 @@ int step_core(oww_ctx* ctx, const int16_t* d_pcm, int64_t pcm_stride, int n_chun
     }
     if ((rc = oww_feat_append(ctx, ctx->d_emb_tmp, n_chunks, s))) return rc;
     if (ev) OWW_CUDA(ctx, cudaEventRecord(ev[2], s));
+    if ((rc = oww_feat16_advance(ctx, n_chunks, s))) return rc;
     for (int i = n_chunks - 1; i >= 0; --i) {
         FeatSrc fs = fs0; fs.back = i;
         if ((rc = oww_heads_all(ctx, fs, B, d_scores, out_stride, i != n_chunks - 1, s))) return rc;
@@ -281,7 +285,7 @@ int reset_enqueue(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float*
                                    ctx->d_mel_count, ctx->d_feat_count, ctx->d_mel_ring, ctx->mel_rows, ctx->d_feat_ring,
                                    ctx->feat_rows, have_init ? ctx->d_reset_init : nullptr, n_rows, rt);
     OWW_LAUNCH_CHECK(ctx);
-    return OWW_OK;
+    return oww_feat16_resync(ctx, h_stream_ids ? ctx->d_reset_ids : nullptr, n, s);     // fp16 mirror of the rings (heads_grp.cu)
 }
 
 }  // namespace
@@ -323,6 +327,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     ctx->tc_heads = (cfg->reserved[0] & 2) == 0;
     ctx->split_from = (cfg->reserved[1] >= 2 && cfg->reserved[1] <= OWW_N_CONV) ? cfg->reserved[1] : 11;
     ctx->tc_heads_terms = (cfg->reserved[0] & 4) ? 1 : 3;
+    ctx->grp_heads = (cfg->reserved[0] & 8) == 0;
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     fill_layer_table(ctx);
@@ -337,8 +342,9 @@ void oww_destroy(oww_ctx* ctx) {
         cudaStreamDestroy(c->own_stream);
         cudaFree(c->d_tails_template);
         cudaFree(c->d_tc_act[0]); cudaFree(c->d_tc_act[1]);
-        cudaFree(c->slot[0].d_pcm); delete c; }
+        cudaFree(c->slot[0].d_pcm); oww_heads_grp_free(c); delete c; }
     free_streams(ctx);
+    oww_heads_grp_free(ctx);
     cudaFree(ctx->d_window); cudaFree(ctx->d_twiddle); cudaFree(ctx->d_mel_start); cudaFree(ctx->d_mel_len);
     cudaFree(ctx->d_mel_w); cudaFree(ctx->d_emb_blob); cudaFree(ctx->d_tc_w); cudaFree(ctx->d_tc_sb);
     cudaFree(ctx->d_tc_w3); cudaFree(ctx->d_tc_sb3);

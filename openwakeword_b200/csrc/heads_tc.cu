@@ -407,6 +407,7 @@ int oww_heads_tc_pack(oww_ctx* ctx, Head& h, const float* blob /* staging in dev
     cudaFree(h.d_w1_tc); h.d_w1_tc = nullptr;
     OWW_CUDA(ctx, cudaMalloc(&h.d_w1_tc, packed.size() * sizeof(__half)));
     OWW_CUDA(ctx, cudaMemcpy(h.d_w1_tc, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    h.tc_w0_host.assign(blob + h.w_off[0], blob + h.w_off[0] + (size_t)h.desc.dims[0] * h.desc.dims[1]);
     h.tc_ok = true;
     return OWW_OK;
 }
@@ -455,6 +456,19 @@ int oww_heads_all(oww_ctx* ctx, const FeatSrc& src, int n, float* d_out, int out
         out = ctx->d_scores_tmp; stride = ctx->n_out_total; comb = 0;
     }
     int rc;
+    // streaming ring of the handle: the heads the groups cover run in one CTA per 128 streams (heads_grp.cu)
+    if (src.count && src.base == ctx->d_feat_ring && n == ctx->n_streams) {
+        const uint32_t grp_mask = oww_heads_grp_covered(ctx) & tc_mask;
+        if (grp_mask) {
+            if ((rc = oww_heads_grp_launch(ctx, src.back, n, out, stride, comb, s))) return rc;
+            tc_mask &= ~grp_mask;
+        }
+    }
+    if (!src.count && src.steps > 0 && !combine_max) {     // bulk clips: every sliding window of every clip, same kernel
+        const uint32_t grp_mask = oww_heads_grp_bulk(ctx, src, n, out, stride, s, &rc) & tc_mask;
+        if (rc) return rc;
+        tc_mask &= ~grp_mask;
+    }
     if (tc_mask && (rc = oww_heads_tc_launch(ctx, -1, src, n, out, stride, 0, comb, s, tc_mask))) return rc;
     if (cc_mask && (rc = oww_heads_launch(ctx, -1, src, n, out, stride, 0, comb, s, cc_mask))) return rc;
     if (!ctx->gates.empty()) {

@@ -34,6 +34,7 @@ struct Head {
     bool tc_ok = false;
     void* d_w1_tc = nullptr;         // packed weights of all layers
     std::vector<TcLayer> tc_layers;
+    std::vector<float> tc_w0_host;   // first-layer matrix [n_in*96][D1] (host copy: the grouped kernel packs it per group)
 };
 
 // what reset_kernel needs to seed a stream's conv tails (mode 3)
@@ -202,6 +203,8 @@ struct oww_ctx {
     bool mel_clip_attr_set = false;
     uint32_t tc_attr_mask = 0;
     bool tc_heads = true;            // modes 2/3: first head layer on tensor cores when the head allows it (reserved[0] bit 1 disables)
+    bool grp_heads = true;           // streaming: heads that share a window run in one CTA per 128 streams (heads_grp.cu; reserved[0] bit 3 disables)
+    struct oww_heads_grp* heads_grp = nullptr;
     int tc_heads_terms = 3;          // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = plain fp16 operands
 
     // private stream set for oww_predict_clips
@@ -314,5 +317,14 @@ int oww_heads_tc_pack(oww_ctx* ctx, Head& h, const float* w1);
 bool oww_heads_tc_supported(const oww_ctx* ctx, int head_id);
 int oww_heads_tc_launch(oww_ctx* ctx, int head_id, const FeatSrc& src, int n, float* d_out, int out_stride,
                         int out_col0, int combine_max, cudaStream_t s, uint32_t head_mask = 0xFFFFFFFFu);
+// ---- heads_grp.cu: streaming heads grouped by window, A operand from the fp16 mirror of the feature rings ----
+void oww_heads_grp_free(oww_ctx* ctx);
+void oww_heads_grp_drop_mirror(oww_ctx* ctx);
+void oww_feat16_invalidate(oww_ctx* ctx);        // rows were appended without oww_feat16_advance: rebuild at the next advance
+int oww_feat16_advance(oww_ctx* ctx, int n_chunks, cudaStream_t s);
+int oww_feat16_resync(oww_ctx* ctx, const int* d_ids, int n, cudaStream_t s);
+uint32_t oww_heads_grp_covered(oww_ctx* ctx);
+uint32_t oww_heads_grp_bulk(oww_ctx* ctx, const FeatSrc& src, int n, float* d_out, int out_stride, cudaStream_t s, int* rc_out);
+int oww_heads_grp_launch(oww_ctx* ctx, int back, int n, float* d_out, int out_stride, int combine_max, cudaStream_t s);
 // every head (tensor-core kernel where a head allows it, heads.cu otherwise) + the verifier gates
 int oww_heads_all(oww_ctx* ctx, const FeatSrc& src, int n, float* d_out, int out_stride, int combine_max, cudaStream_t s);

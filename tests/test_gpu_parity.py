@@ -392,7 +392,9 @@ def test_bulk_predict_file_paths_on_reference_wavs(torch_cuda, built_library, tm
     d = np.abs(got - cases["hey_jane"]["scores"]).max()
     print("bulk_predict(hey_jane.wav) vs reference-plumbing golden: max |delta| =", d)
     assert d < SCORE_TOL
-    # every file: bulk == streaming predict_clip on a fresh model (same kernels, same arithmetic -> bit-identical)
+    # every file: bulk == streaming predict_clip on a fresh model.  Mel, CNN and ring contents are bit-identical; the
+    # heads accumulate their first layer in a different order in the two paths (streaming: all heads of a window in one
+    # CTA, K chunks of 32; bulk: one CTA per head, K chunks of 96), so the scores agree to fp32 rounding
     m = owb.Model(wakeword_models=specs, embedding_model_path=emb_weights(), feature_init=fi)
     for p in paths:
         m.reset()
@@ -400,7 +402,7 @@ def test_bulk_predict_file_paths_on_reference_wavs(torch_cuda, built_library, tm
         assert len(ref) == len(res[p])
         a = np.array([[r[l] for l in labels] for r in ref], np.float32)
         b = np.array([[r[l] for l in labels] for r in res[p]], np.float32)
-        assert np.array_equal(a, b), (p, np.abs(a - b).max())
+        assert np.abs(a - b).max() < 2e-6, (p, np.abs(a - b).max())
 
 
 def test_embed_clips_and_feature_generator_on_gpu(torch_cuda, built_library, tmp_path):

@@ -415,3 +415,58 @@ def test_partial_reset_keeps_the_fused_kernel_and_matches_oracle(torch_cuda, bui
     for b in (reset_of_step[-1], B - 1, 0):
         assert np.abs(eng.ctx.get_mel(b, 76) - orc[b].melspectrogram_buffer[-76:]).max() < 5e-3
         assert np.abs(eng.ctx.get_features(b, 30) - orc[b].feature_buffer[-30:]).max() < 8e-3
+
+
+@pytest.mark.gpu
+def test_grouped_heads_match_per_head_kernels(torch_cuda, built_library):
+    """heads_grp.cu (all heads that share a window in one CTA per 128 streams, A operand from the fp16 mirror of the
+    feature rings) against heads_tc.cu (one CTA per head, fp32 rings) and heads.cu (CUDA cores) on identical stream
+    state: 300 streams (ragged third tile), head groups with n_in 16 / 34 / 3, widths 30..128, 1-4 Linear layers,
+    LayerNorm on and off, sigmoid / softmax / relu-softmax / relu finals, a gated verifier pair; distinct feature
+    histories per stream block (resets with different init rows), single-chunk steps, 3-chunk calls (windows ending
+    0, 1, 2 rows back + max over chunks) and a partial reset between steps."""
+    from openwakeword_b200.engine import StreamEngine
+    from openwakeword_b200 import weights as W
+    rng = np.random.default_rng(77)
+    relu_head = W.synthetic_head(n_in=16, hidden=64, n_blocks=1, n_out=4, layernorm=True, final="relu_softmax", seed=13)
+    relu_head["final"] = "relu"
+    single = {"n_in": 16, "final": "softmax",                    # a head that is ONE Linear layer
+              "layers": [{"W": (rng.standard_normal((1536, 5)) / 40).astype(np.float32),
+                          "b": rng.normal(0, 0.1, 5).astype(np.float32), "ln": None}]}
+    hs = [head("alexa_v0.1"), head("timer_v0.1"),
+          W.synthetic_gated_head(seed_main=21, seed_verifier=22, threshold=0.5),
+          W.synthetic_head(n_in=16, hidden=30, n_blocks=1, n_out=1, seed=3),
+          W.synthetic_head(n_in=16, hidden=128, n_blocks=2, n_out=3, layernorm=True, final="softmax", seed=8),
+          W.synthetic_head(n_in=3, hidden=7, n_blocks=2, n_out=3, layernorm=False, final="softmax", seed=4),
+          relu_head, single]
+    B, steps = 300, 6
+    pcm = _mixes(rng, B, (steps + 3 * 2) * 1280)
+    inits = [rng.normal(0.2, 1.0, (41, 96)).astype(np.float32) for _ in range(5)]
+    outs = {}
+    for key, kw in (("grp", {}), ("tc", {"group_heads": False}), ("cc", {"tc_heads": False})):
+        eng = StreamEngine(hs, B, embedding=emb_weights(), max_chunks=3, **kw)
+        for i, fi in enumerate(inits):                          # five blocks of streams with different histories
+            eng.reset(fi[: 41 - 7 * i], stream_ids=list(range(i, B, 5)))
+        got = []
+        at = 0
+        for k in range(steps):
+            if k == 3:
+                eng.reset(inits[1][:20], stream_ids=[0, 7, 129, 299])
+            got.append(eng.step_host(np.ascontiguousarray(pcm[:, at:at + 1280]), 1).copy()); at += 1280
+        for _ in range(2):
+            got.append(eng.step_host(np.ascontiguousarray(pcm[:, at:at + 3 * 1280]), 3).copy()); at += 3 * 1280
+        outs[key] = np.stack(got)
+        eng.ctx.close()
+    cols = outs["cc"].shape[-1]
+    scale = np.maximum(1.0, np.abs(outs["cc"]))
+    # the gated column switches between two networks at the threshold: skip entries where either side shows a main
+    # score within 1e-3 of it (the two kernels may then legitimately decide differently)
+    gate_col = 1 + 7
+    def err(x, y):
+        e = np.abs(x - y) / scale
+        near = (np.abs(x[..., gate_col] - 0.5) < 1e-3) | (np.abs(y[..., gate_col] - 0.5) < 1e-3)
+        e[..., gate_col] = np.where(near, 0.0, e[..., gate_col])
+        return float(e.max())
+    e_grp_tc, e_grp_cc, e_tc_cc = err(outs["grp"], outs["tc"]), err(outs["grp"], outs["cc"]), err(outs["tc"], outs["cc"])
+    print(f"grouped vs per-head TC {e_grp_tc:.3e}; grouped vs CUDA cores {e_grp_cc:.3e}; per-head TC vs CUDA cores {e_tc_cc:.3e} ({cols} columns)")
+    assert e_grp_tc < 5e-5 and e_grp_cc < 2e-4
