@@ -203,23 +203,31 @@ int oww_debug_heads_clocks(oww_ctx* ctx, int64_t* h_out64);
 /* ---- multi-GPU gather over peer memory (one process per GPU) ---------------------------------
  * The reference has no multi-device path; SURVEY.md section 8e defines the only exchange of the sharded hot path: the
  * per-step scores float32[B/G][n_labels] of every rank gathered on one rank.  Instead of a collective call after the
- * step, the step's last kernel can write its scores straight into the gathering rank's memory: pass oww_step a
- * d_scores that points into a buffer opened with oww_peer_open (stores go over NVLink), then publish a step counter
- * with oww_peer_signal; the gathering rank orders its consumer behind oww_peer_wait.  openwakeword_b200.distributed
- * .PeerGather drives the protocol (double-buffered slots, acknowledgement counters).
+ * step, a rank moves its finished score block into the gathering rank's memory (a buffer opened with oww_peer_open)
+ * with oww_peer_copy - one DMA over NVLink; d_scores of oww_step may also point into the mapping directly, at the
+ * price of scattered 4-byte remote stores - then publishes a step counter with oww_peer_signal; the gathering rank
+ * orders its consumer behind oww_peer_wait.  openwakeword_b200.distributed.PeerGather drives the protocol
+ * (double-buffered slots, acknowledgement counters); validated on 2 x B200 by tests/test_gpu_multi.py.
  *   oww_peer_alloc  - cudaMalloc'd, zero-filled buffer on this handle's device + its 64-byte CUDA IPC handle
  *   oww_peer_open   - map another process's buffer (peer access is enabled lazily); oww_peer_close unmaps it
  *   oww_peer_signal - stream-ordered: after all earlier work of `stream`, *d_flag = value (system-scope release;
  *                     d_flag may be local or peer-mapped)
  *   oww_peer_wait   - stream-ordered: later work of `stream` starts once d_flags[i*stride] >= value for all i < n
- *                     (n <= 1024).  If that takes longer than timeout_s (<= 0: 10 s) the kernel traps and the next
- *                     CUDA call on the handle fails - a dead peer cannot hang the GPU.                              */
+ *                     (n <= 1024).  If that takes longer than timeout_s (<= 0: 10 s) the kernel gives up, the stream
+ *                     goes on and oww_peer_status reports the timeout - a dead peer can neither hang the GPU nor
+ *                     poison the CUDA context.                                                                    */
 int oww_peer_alloc(oww_ctx* ctx, size_t bytes, void** d_ptr, unsigned char handle_out[64]);
 int oww_peer_free(oww_ctx* ctx, void* d_ptr);
 int oww_peer_open(oww_ctx* ctx, const unsigned char handle[64], void** d_ptr);
 int oww_peer_close(oww_ctx* ctx, void* d_ptr);
+/* stream-ordered block copy into (or out of) a peer mapping: one DMA over NVLink instead of the kernels' scattered
+ * 4-byte stores - the way openwakeword_b200.distributed moves a rank's [rows x columns] score block */
+int oww_peer_copy(oww_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, void* stream);
 int oww_peer_signal(oww_ctx* ctx, uint64_t* d_flag, uint64_t value, void* stream);
 int oww_peer_wait(oww_ctx* ctx, const uint64_t* d_flags, int n, int stride, uint64_t value, double timeout_s, void* stream);
+/* a wait that ran into its timeout lets the stream continue and raises a flag on the handle: *timed_out = 1 (the flag is
+ * cleared by the read).  Synchronises the device. */
+int oww_peer_status(oww_ctx* ctx, int* timed_out);
 
 /* ---- introspection ------------------------------------------------------------------------- */
 uint64_t oww_launch_count(const oww_ctx* ctx);       /* kernels launched by this handle so far   */

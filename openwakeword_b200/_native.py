@@ -67,8 +67,10 @@ _SIGNATURES = {
     "oww_peer_free": (C.c_int, [_P, _P]),
     "oww_peer_open": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_void_p)]),
     "oww_peer_close": (C.c_int, [_P, _P]),
+    "oww_peer_copy": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "oww_peer_signal": (C.c_int, [_P, _P, C.c_uint64, _P]),
     "oww_peer_wait": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint64, C.c_double, _P]),
+    "oww_peer_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "oww_metrics_false_positives": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "oww_metrics_count_ge": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P]),
     "oww_launch_count": (C.c_uint64, [_P]),
@@ -294,11 +296,22 @@ class Context:
     def peer_close(self, addr):
         self._check(self.lib.oww_peer_close(self.h, int(addr)))
 
+    def peer_copy(self, dst_addr, src, n_bytes, stream=None):
+        """Stream-ordered block copy; src / dst: device addresses (int) or tensors."""
+        self._check(self.lib.oww_peer_copy(self.h, dst_addr if isinstance(dst_addr, int) else _ptr(dst_addr),
+                                           src if isinstance(src, int) else _ptr(src), int(n_bytes), stream))
+
     def peer_signal(self, flag_addr, value, stream=None):
         self._check(self.lib.oww_peer_signal(self.h, int(flag_addr), int(value), stream))
 
     def peer_wait(self, flags_addr, n, stride, value, timeout_s=10.0, stream=None):
         self._check(self.lib.oww_peer_wait(self.h, int(flags_addr), int(n), int(stride), int(value), float(timeout_s), stream))
+
+    def peer_timed_out(self):
+        """True if a peer_wait since the last call ran into its timeout (synchronises the device; clears the flag)."""
+        v = C.c_int(0)
+        self._check(self.lib.oww_peer_status(self.h, C.byref(v)))
+        return bool(v.value)
 
     # ---- metrics (device-resident scores) ----
     def metrics_false_positives(self, d_scores, series_stride, n_series, n_frames, thresholds, grouping_window=50, stream=None):

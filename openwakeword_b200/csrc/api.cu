@@ -350,7 +350,7 @@ void oww_destroy(oww_ctx* ctx) {
     cudaFree(ctx->d_tc_w3); cudaFree(ctx->d_tc_sb3);
     cudaFree(ctx->d_tc_act[0]); cudaFree(ctx->d_tc_act[1]); cudaFree(ctx->d_inc_w); cudaFree(ctx->d_head_devs);
     for (auto& h : ctx->heads) { cudaFree(h.d_blob); cudaFree(h.d_w1_tc); }
-    cudaFree(ctx->d_gates); cudaFree(ctx->d_tails_template);
+    cudaFree(ctx->d_gates); cudaFree(ctx->d_tails_template); cudaFree(ctx->d_peer_err);
     for (auto& S : ctx->slot) {
         cudaFreeHost(S.h_pcm); cudaFreeHost(S.h_scores); cudaFree(S.d_pcm); cudaFree(S.d_scores);
         if (S.done) cudaEventDestroy(S.done);

@@ -203,6 +203,7 @@ struct oww_ctx {
     bool mel_clip_attr_set = false;
     uint32_t tc_attr_mask = 0;
     bool tc_heads = true;            // modes 2/3: first head layer on tensor cores when the head allows it (reserved[0] bit 1 disables)
+    int* d_peer_err = nullptr;       // raised by oww_peer_wait's kernel on a timeout (oww_peer_status reads and clears it)
     bool grp_heads = true;           // streaming: heads that share a window run in one CTA per 128 streams (heads_grp.cu; reserved[0] bit 3 disables)
     struct oww_heads_grp* heads_grp = nullptr;
     int tc_heads_terms = 3;          // 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = plain fp16 operands

@@ -16,7 +16,7 @@ __global__ void peer_signal_kernel(unsigned long long* flag, unsigned long long 
 }
 
 __global__ void peer_wait_kernel(const unsigned long long* flags, int n, int stride, unsigned long long value,
-                                 long long timeout_cycles) {
+                                 long long timeout_cycles, int* timed_out) {
     // one lane per flag; every lane spins until its counter reaches `value`
     const int i = threadIdx.x;
     if (i >= n) return;
@@ -26,7 +26,9 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int n, int str
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         if (v >= value) break;
-        if (clock64() - t0 > timeout_cycles) __trap();      // a dead peer must surface as a launch error, not a hang
+        // a dead peer must not hang the stream - and must not poison the context either: raise the handle's flag
+        // (oww_peer_status) and let the stream go on; the consumer's data for this step is then stale
+        if (clock64() - t0 > timeout_cycles) { atomicExch(timed_out, 1); break; }
         __nanosleep(200);
     }
 }
@@ -79,6 +81,14 @@ int oww_peer_close(oww_ctx* ctx, void* d_ptr) {
     return OWW_OK;
 }
 
+int oww_peer_copy(oww_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, void* stream) {
+    if (!ctx || !d_dst || !d_src) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    // unified addressing: the copy engine moves the block over NVLink when d_dst is a peer mapping
+    OWW_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return OWW_OK;
+}
+
 int oww_peer_signal(oww_ctx* ctx, uint64_t* d_flag, uint64_t value, void* stream) {
     if (!ctx || !d_flag) return oww_fail(ctx, OWW_EINVAL, "null argument");
     OWW_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -96,9 +106,23 @@ int oww_peer_wait(oww_ctx* ctx, const uint64_t* d_flags, int n, int stride, uint
     if (khz <= 0) khz = 1900000;
     if (!(timeout_s > 0)) timeout_s = 10.0;
     const long long cycles = (long long)(timeout_s * 1e3 * khz);
+    if (!ctx->d_peer_err) {
+        OWW_CUDA(ctx, cudaMalloc(&ctx->d_peer_err, sizeof(int)));
+        OWW_CUDA(ctx, cudaMemset(ctx->d_peer_err, 0, sizeof(int)));
+    }
     peer_wait_kernel<<<1, ((n + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(d_flags),
-                                                                            n, stride, value, cycles);
+                                                                            n, stride, value, cycles, ctx->d_peer_err);
     OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+int oww_peer_status(oww_ctx* ctx, int* timed_out) {
+    if (!ctx || !timed_out) return oww_fail(ctx, OWW_EINVAL, "null argument");
+    *timed_out = 0;
+    if (!ctx->d_peer_err) return OWW_OK;
+    OWW_CUDA(ctx, cudaSetDevice(ctx->device));
+    OWW_CUDA(ctx, cudaMemcpy(timed_out, ctx->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost));   // synchronises
+    if (*timed_out) OWW_CUDA(ctx, cudaMemset(ctx->d_peer_err, 0, sizeof(int)));
     return OWW_OK;
 }
 

@@ -166,7 +166,8 @@ class ShardedStreams:
     ``gather``: ``"nccl"`` - all-gather on the compute stream after every step (every rank gets the scores);
     ``"nccl-overlap"`` - the all-gather of step k runs on a side stream while the compute stream already works on
     step k+1 (two score buffers; ``step`` returns a ``GatheredScores`` whose ``wait()`` yields the tensor);
-    ``"peer"`` - peer-memory stores into rank 0's buffer, no collective (experimental until run on hardware)."""
+    ``"peer"`` - every rank copies its score block into rank 0's buffer over NVLink, counters follow; no collective
+    (tests/test_gpu_multi.py, 2 x B200)."""
 
     def __init__(self, n_total, engine_factory, rank=None, world=None, gather="nccl"):
         r, w, _ = env_rank_world()
@@ -178,6 +179,7 @@ class ShardedStreams:
         if gather not in ("nccl", "nccl-overlap", "peer"):
             raise ValueError("gather is 'nccl', 'nccl-overlap' (side-stream all-gather) or 'peer' (peer-memory gather on rank 0)")
         self.peer = None
+        self._peer_loc = None
         self._k = 0
         self._ov = None
         self.gather_kind = "none (single rank)" if self.world == 1 else gather
@@ -232,7 +234,12 @@ class ShardedStreams:
         if self.rank == pg.root and k > 1:
             pg.release(k - 1, stream)             # whatever the caller enqueued on the previous result is ordered before this
         pg.begin(k, stream)
-        self.engine.step(local_pcm, n_chunks, out=pg.dest(k))
+        # the step writes its scores locally (the heads and the verifier gates read-modify-write them); the finished
+        # [rows x columns] block then crosses NVLink as ONE copy into this rank's rows of the root's buffer
+        if self._peer_loc is None:
+            self._peer_loc = torch.empty((self.hi - self.lo, self.engine.n_cols), dtype=torch.float32, device=local_pcm.device)
+        self.engine.step(local_pcm, n_chunks, out=self._peer_loc)
+        self.engine.ctx.peer_copy(pg.dest(k), self._peer_loc, self._peer_loc.numel() * 4, stream)
         pg.publish(k, stream)
         if self.rank != pg.root:
             return None
