@@ -72,7 +72,10 @@ typedef struct oww_config {
                               fp32-grade 3-term hi/lo split);
                               bit 3: 1 = one tensor-core heads CTA per (128 streams, head) reading the fp32 rings
                               (heads_tc.cu) instead of one CTA per 128 streams for all heads that share a window,
-                              fed from the fp16 mirror of the rings (heads_grp.cu).
+                              fed from the fp16 mirror of the rings (heads_grp.cu);
+                              bit 4: 1 = the incremental late (3,1) layers keep the window-mode tensor layout
+                              (per-stream [tails | new rows] x (W+1): most accumulator rows of a tile are not outputs)
+                              instead of the blocked time-major layout of tc_conv_blk_kernel.
                               reserved[1]: first conv layer that takes fp16 hi/lo split operands in the
                               tensor-core modes, 2..20 (0 = default 11; 20 = plain fp16 everywhere)           */
 } oww_config;

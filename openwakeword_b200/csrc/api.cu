@@ -69,6 +69,13 @@ __global__ void reset_kernel(const int* ids, int n_ids, int n_streams, int16_t* 
             for (int i = threadIdx.x; i < T.n_planes * 2 * T.Wp; i += blockDim.x) {
                 const int pl = i / (2 * T.Wp), u = i - pl * 2 * T.Wp, r = u / T.Wp, f = u - r * T.Wp;
                 const uint4 v = T.tmpl[i];
+                if (T.S) {                                  // blocked dense layout [block][T_buf][S][W] (cnn_tc.cu, tc_conv_blk_kernel)
+                    if (f >= T.W) continue;
+                    const int64_t at = (int64_t)pl * T.plane + 8 + ((int64_t)(b / T.S) * T.T_buf + r) * T.S * T.W + (int64_t)(b % T.S) * T.W + f;
+                    T.now[at] = v;
+                    if (T.next && r == 1) T.next[at - (int64_t)T.S * T.W] = v;           // same place, row 0
+                    continue;
+                }
                 T.now[(int64_t)pl * T.plane + 8 + ((int64_t)b * T.T_buf + r) * T.Wp + f] = v;
                 if (T.next && r == 1) T.next[(int64_t)pl * T.plane + 8 + ((int64_t)b * T.T_buf + 0) * T.Wp + f] = v;
             }
@@ -278,6 +285,7 @@ int reset_enqueue(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float*
                 T.next = X.n_buf == 3 ? reinterpret_cast<uint4*>(X.buf[(k + 1) % 3]) : nullptr;
                 T.tmpl = reinterpret_cast<const uint4*>(ctx->d_late_template) + X.tmpl_off;
                 T.plane = X.plane; T.T_buf = X.T_buf; T.Wp = X.W + 1; T.n_planes = 2 * X.cg;
+                T.S = X.S; T.W = X.W;
             }
         }
     }
@@ -328,6 +336,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     ctx->split_from = (cfg->reserved[1] >= 2 && cfg->reserved[1] <= OWW_N_CONV) ? cfg->reserved[1] : 11;
     ctx->tc_heads_terms = (cfg->reserved[0] & 4) ? 1 : 3;
     ctx->grp_heads = (cfg->reserved[0] & 8) == 0;
+    ctx->late_blocked_ok = (cfg->reserved[0] & 16) == 0;
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     fill_layer_table(ctx);

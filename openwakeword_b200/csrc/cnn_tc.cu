@@ -121,6 +121,7 @@ struct TcConvArgs {
     // tails of later steps.  out_T == 0: plain layout (out_T = T_out, no offset, no mirrors).
     int out_T, out_toff;
     __half* out_b[2]; int out_b_toff[2];    // mirrors (nullptr = unused); same plane pitch as `out`
+    int out_S, out_Wq;                      // out_S > 0: the destination is blocked dense [block][out_T][out_S][out_Wq] (no pad column)
 };
 
 // TERMS = 1: fp16 operands.  TERMS = 3: split operands - the input holds hi planes [0, cg_in) and lo planes
@@ -194,37 +195,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (one elected lane; the warp stays converged) =====================
+        {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            mbar_wait(wfull_bar, 0);
+            tc_warp_wait(wfull_bar, 0, lane);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             const uint32_t w_addr = smem_u32(w_smem);
             const uint32_t lbo_a = (uint32_t)a.rows * 16u;
+            const uint32_t rows16 = (uint32_t)a.rows * 16u;
+            const uint32_t tap16[3] = {(uint32_t)a.tap_off[0] * 16u, (uint32_t)a.tap_off[1] * 16u, (uint32_t)a.tap_off[2] * 16u};
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-                mbar_wait(full_bar(stage), phase);
+                tc_warp_wait(tempty_bar(acc), acc_phase ^ 1, lane);
+                tc_warp_wait(full_bar(stage), phase, lane);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(a_smem + stage * stage_bytes);
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
-                uint32_t accumulate = 0;
+                if (tc_elect_one()) {
+                    uint32_t accumulate = 0;
+                    // term order: every K step with the hi activations ((hi,hi), (hi,lo)), then every K step with the lo
+                    // activations ((lo,hi)) - the order tc_conv_blk_kernel is bound to (it holds one half at a time), so the
+                    // window / clip passes and the incremental late layers accumulate identically (bulk == streaming, bit for bit)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
+                    for (int ph = 0; ph < (TERMS == 3 ? 2 : 1); ++ph) {
 #pragma unroll
-                    for (int q = 0; q < CGP / 2; ++q) {
+                        for (int j = 0; j < 3; ++j) {
 #pragma unroll
-                        for (int t = 0; t < TERMS; ++t) {        // (hi,hi) (lo,hi) (hi,lo)
-                            const uint32_t a_t = a_addr + (t == 1 ? (uint32_t)term_bytes : 0u);
-                            const uint32_t w_t = w_addr + (t == 2 ? (uint32_t)W_TERM : 0u);
-                            const uint64_t ad = make_desc(a_t + (uint32_t)(2 * q * a.rows + a.tap_off[j]) * 16u, lbo_a, 128u);
-                            const uint64_t bd = make_desc(w_t + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
-                            tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
-                            accumulate = 1;
+                            for (int q = 0; q < CGP / 2; ++q) {
+#pragma unroll
+                                for (int wt = 0; wt < (TERMS == 3 && ph == 0 ? 2 : 1); ++wt) {
+                                    const uint32_t a_t = a_addr + (ph == 1 ? (uint32_t)term_bytes : 0u);
+                                    const uint32_t w_t = w_addr + (wt == 1 ? (uint32_t)W_TERM : 0u);
+                                    const uint64_t ad = make_desc(a_t + (uint32_t)(2 * q) * rows16 + tap16[j], lbo_a, 128u);
+                                    const uint64_t bd = make_desc(w_t + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
+                                    tc_mma_f16(d_tmem, ad, bd, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
                         }
                     }
+                    tc_commit(empty_bar(stage));
+                    tc_commit(tfull_bar(acc));
                 }
-                tc_commit(empty_bar(stage));
-                tc_commit(tfull_bar(acc));
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
@@ -279,10 +291,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 }
                 continue;
             }
-            const int64_t po = a.out_T ? (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_toff) * Wp + f
-                                       : (int64_t)n * per_out + (int64_t)t * Wp + f;
-            uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + po;
             const bool pad = f == a.W;
+            if (a.out_S && pad) continue;                                   // dense destination: it has no pad column
+            const int64_t po = a.out_S ? ((int64_t)(n / a.out_S) * a.out_T + t + a.out_toff) * a.out_S * a.out_Wq + (int64_t)(n % a.out_S) * a.out_Wq + f
+                               : a.out_T ? (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_toff) * Wp + f
+                                         : (int64_t)n * per_out + (int64_t)t * Wp + f;
+            uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + po;
 #pragma unroll
             for (int k = 0; k < PH; ++k) {
                 const int g = pl0 + k;
@@ -300,16 +314,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 }
                 if (g < a.cg_out) {
                     o[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
-                    if (po == 0) o[(int64_t)g * a.out_plane - 1] = make_uint4(0, 0, 0, 0);   // front guard (position -1)
+                    if (po == 0 && !a.out_S) o[(int64_t)g * a.out_plane - 1] = make_uint4(0, 0, 0, 0);   // front guard (position -1)
                     if (a.out_split) {
                         o[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
-                        if (po == 0) o[(int64_t)(a.cg_out + g) * a.out_plane - 1] = make_uint4(0, 0, 0, 0);
+                        if (po == 0 && !a.out_S) o[(int64_t)(a.cg_out + g) * a.out_plane - 1] = make_uint4(0, 0, 0, 0);
                     }
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk)
                         if (a.out_b[kk]) {
-                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[kk]) + kGuard + (int64_t)n * a.out_T * Wp +
-                                        (int64_t)(t + a.out_b_toff[kk]) * Wp + f;
+                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[kk]) + kGuard +
+                                        (a.out_S ? ((int64_t)(n / a.out_S) * a.out_T + t + a.out_b_toff[kk]) * a.out_S * a.out_Wq + (int64_t)(n % a.out_S) * a.out_Wq + f
+                                                 : (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_b_toff[kk]) * Wp + f);
                             ob[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
                             if (a.out_split) ob[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
                         }
@@ -325,10 +340,220 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- incremental late (3,1) layers: blocked input
+// The window-mode kernel above runs a (3,1) layer of the incremental chain on per-stream "windows" [2 tails | new rows]
+// x (W + 1): of the 128 accumulator rows of a tile only rows_new / T carry outputs, and one column in W + 1 is padding
+// (layer 16: 4 of 12 positions, layer 19: 1 of 6) - the MMAs cost the same.  Here the input tensor is stored in blocks
+// of S streams, time-major inside a block and without the pad column: [block][T rows][S streams][W] units.  One tile =
+// one block: tap k reads rows k .. k + rows_new - 1 = ONE contiguous run of rows_new*S*W = 128 units at offset k*S*W,
+// and every accumulator row is a real output.  The hi and the lo half of a block (98 KB together at 96 channels) do not
+// fit twice beside the 110 KB of split weights, so the two shared-memory slots hold one HALF each: the MMAs of the hi
+// half ((hi,hi), (hi,lo)) run while the lo half lands, the lo MMAs ((lo,hi)) while the next block's hi half lands.
+struct TcBlkArgs {
+    const __half* in; int64_t in_plane;     // hi planes [0, cg_in), lo planes [cg_in, 2 cg_in); block b at kGuard + b*T*S*W
+    const __half* w; const float* scale; const float* bias;
+    int n, T, W, S, rows_new;
+    int rows;                               // smem rows per plane: T*S*W rounded up to 8
+    int cg_in, cg_out, apply_act, n_tiles;
+    float* out_f32;                         // final layer: [n][96]
+    // destination tensor: plain [n][out_T][out_Wq] (out_S == 0; pad column zeroed) or blocked dense [block][out_T][out_S][out_Wq]
+    __half* out[3]; int out_toff[3]; int64_t out_plane; int out_S, out_Wq, out_T;
+};
+
+__device__ __forceinline__ int64_t late_pos(int S, int Wq, int T, int stream, int row, int f) {
+    return S ? ((int64_t)(stream / S) * T + row) * S * Wq + (int64_t)(stream % S) * Wq + f
+             : ((int64_t)stream * T + row) * Wq + f;
+}
+
+template <int CGP, int NP>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int W_TERM = 3 * CGP * NP * 16;
+    constexpr int W_BYTES = 2 * W_TERM;
+    uint8_t* w_smem = smem;
+    const int half_bytes = CGP * a.rows * 16;
+    uint8_t* a_smem = smem + W_BYTES;                                      // slot 0: hi half, slot 1: lo half
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + 2 * half_bytes);
+    // bars: full[2], empty[2], tmem_full[A], tmem_empty[A], w_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * kAccStages + 1);
+    float* s_sb = reinterpret_cast<float*>(tmem_slot + 4);
+    for (int i = threadIdx.x; i < NP; i += kTcThreads) { s_sb[i] = a.scale[i]; s_sb[NP + i] = a.bias[i]; }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int h) { return bar0 + 8u * h; };
+    auto empty_bar = [&](int h) { return bar0 + 8u * (2 + h); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (4 + kAccStages + s); };
+    const uint32_t wfull_bar = bar0 + 8u * (4 + 2 * kAccStages);
+
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < 2; ++h) { mbar_init(full_bar(h), 1); mbar_init(empty_bar(h), 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+        mbar_init(wfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // pad planes (cg_in odd) and the rows behind the block are never written by the bulk copies: zero them once
+    for (int h = 0; h < 2; ++h) {
+        uint4* base = reinterpret_cast<uint4*>(a_smem + h * half_bytes);
+        const int used = a.T * a.S * a.W;
+        for (int i = threadIdx.x; i < CGP * a.rows; i += kTcThreads) {
+            const int g = i / a.rows, r = i - g * a.rows;
+            if (g >= a.cg_in || r >= used) base[i] = make_uint4(0, 0, 0, 0);
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int blk_units = a.T * a.S * a.W;
+
+    if (warp == 0) {
+        // ===================== producer: weights once, then hi half / lo half of one block per tile =====================
+        if (lane == 0) {
+            mbar_expect_tx(wfull_bar, W_BYTES);
+            bulk_g2s(smem_u32(w_smem), a.w, W_BYTES, wfull_bar);
+            uint32_t phase = 0;
+            const uint32_t plane_bytes = (uint32_t)blk_units * 16u, pitch = (uint32_t)a.rows * 16u;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                const int64_t u0 = kGuard + (int64_t)tile * blk_units;
+                for (int h = 0; h < 2; ++h) {
+                    mbar_wait(empty_bar(h), phase ^ 1);
+                    mbar_expect_tx(full_bar(h), plane_bytes * a.cg_in);
+                    for (int g = 0; g < a.cg_in; ++g)
+                        bulk_g2s(smem_u32(a_smem + h * half_bytes + g * pitch),
+                                 reinterpret_cast<const uint4*>(a.in) + (int64_t)(h * a.cg_in + g) * a.in_plane + u0, plane_bytes, full_bar(h));
+                }
+                phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane; the warp stays converged) =====================
+        {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            tc_warp_wait(wfull_bar, 0, lane);
+            uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t w_addr = smem_u32(w_smem), a_addr = smem_u32(a_smem);
+            const uint32_t lbo_a = (uint32_t)a.rows * 16u, rows16 = (uint32_t)a.rows * 16u;
+            const uint32_t tap16 = (uint32_t)(a.S * a.W) * 16u;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                tc_warp_wait(tempty_bar(acc), acc_phase ^ 1, lane);
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tc_warp_wait(full_bar(h), phase, lane);
+                    tc_fence_after();
+                    if (tc_elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                            for (int q = 0; q < CGP / 2; ++q) {
+#pragma unroll
+                                for (int wt = 0; wt < (h == 0 ? 2 : 1); ++wt) {      // hi half: (hi,hi), (hi,lo); lo half: (lo,hi)
+                                    const uint32_t w_t = w_addr + (wt == 1 ? (uint32_t)W_TERM : 0u);
+                                    const uint64_t ad = make_desc(a_addr + (uint32_t)h * (uint32_t)half_bytes + (uint32_t)(2 * q) * rows16 + (uint32_t)j * tap16,
+                                                                  lbo_a, 128u);
+                                    const uint64_t bd = make_desc(w_t + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
+                                    tc_mma_f16(d_tmem, ad, bd, idesc, (h | j | q | wt) != 0);
+                                }
+                            }
+                        }
+                        tc_commit(empty_bar(h));
+                        if (h == 1) tc_commit(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                }
+                phase ^= 1;
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 halves of the channel-group planes ============
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        constexpr int NP8 = NP / 8, PH = NP8 / 2;
+        const int pl0 = half * PH;
+        const int row = quarter * 32 + lane;
+        const int SW = a.S * a.W;
+        const int t = row / SW, sl = (row - t * SW) / a.W, f = row - t * SW - sl * a.W;
+        const bool row_ok = row < a.rows_new * SW;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            uint32_t v[PH * 8];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 128u + (uint32_t)pl0 * 8u;
+#pragma unroll
+            for (int k = 0; k < PH; ++k) tc_tmem_ld8(taddr + k * 8, v + k * 8);
+            tmem_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+
+            const int n = tile * a.S + sl;
+            if (!row_ok || n >= a.n) continue;
+            if (a.out_f32) {
+                float* o = a.out_f32 + ((int64_t)n * a.rows_new + t) * 96;
+#pragma unroll
+                for (int k = 0; k < PH; ++k) {
+                    const int c = (pl0 + k) * 8;
+                    if (c >= 96) continue;
+                    float4 r0, r1;
+                    r0.x = fmaf(__uint_as_float(v[k * 8 + 0]), s_sb[c + 0], s_sb[NP + c + 0]);
+                    r0.y = fmaf(__uint_as_float(v[k * 8 + 1]), s_sb[c + 1], s_sb[NP + c + 1]);
+                    r0.z = fmaf(__uint_as_float(v[k * 8 + 2]), s_sb[c + 2], s_sb[NP + c + 2]);
+                    r0.w = fmaf(__uint_as_float(v[k * 8 + 3]), s_sb[c + 3], s_sb[NP + c + 3]);
+                    r1.x = fmaf(__uint_as_float(v[k * 8 + 4]), s_sb[c + 4], s_sb[NP + c + 4]);
+                    r1.y = fmaf(__uint_as_float(v[k * 8 + 5]), s_sb[c + 5], s_sb[NP + c + 5]);
+                    r1.z = fmaf(__uint_as_float(v[k * 8 + 6]), s_sb[c + 6], s_sb[NP + c + 6]);
+                    r1.w = fmaf(__uint_as_float(v[k * 8 + 7]), s_sb[c + 7], s_sb[NP + c + 7]);
+                    reinterpret_cast<float4*>(o + c)[0] = r0;
+                    reinterpret_cast<float4*>(o + c)[1] = r1;
+                }
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < PH; ++k) {
+                const int g = pl0 + k;
+                if (g >= a.cg_out) continue;
+                __half2 h[4], l[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = g * 8 + u * 2;
+                    float y0 = fmaf(__uint_as_float(v[k * 8 + u * 2]), s_sb[c], s_sb[NP + c]);
+                    float y1 = fmaf(__uint_as_float(v[k * 8 + u * 2 + 1]), s_sb[c + 1], s_sb[NP + c + 1]);
+                    if (a.apply_act) { y0 = act(y0); y1 = act(y1); }
+                    const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+                    h[u] = __halves2half2(h0, h1);
+                    l[u] = __floats2half2_rn(y0 - __half2float(h0), y1 - __half2float(h1));
+                }
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk)
+                    if (a.out[kk]) {
+                        uint4* o = reinterpret_cast<uint4*>(a.out[kk]) + kGuard + late_pos(a.out_S, a.out_Wq, a.out_T, n, t + a.out_toff[kk], f);
+                        o[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
+                        o[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
+                    }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    }
+}
+
 // ---------------------------------------------------------------- max-pool on fp16 planes
 // split != 0: planes [0, cg) hold hi parts and [cg, 2cg) lo parts of the same values; the pooled element is the one
 // with the largest hi + lo, i.e. the lexicographic maximum of (hi, lo) since |lo| <= ulp(hi)/2.
-struct PoolOut { __half* p[3]; int toff[3]; int out_T; };     // out_T == 0: plain [n][t_out][wp_out] into p[0]
+struct PoolOut { __half* p[3]; int toff[3]; int out_T; int S = 0; };     // out_T == 0: plain [n][t_out][wp_out] into p[0]; S > 0: blocked dense destination [block][out_T][S][w_out]
 __global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t in_plane, PoolOut po, int64_t out_plane,
                                                       int n, int t_in, int w_in, int cg, int pt, int pf, int split) {
     __half* const out = po.p[0];
@@ -376,7 +601,9 @@ __global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t 
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (po.p[k]) {
-                    const int64_t q = kGuard + (s * po.out_T + t + po.toff[k]) * wp_out + f;
+                    if (po.S && f >= w_out) continue;                   // dense destination: no pad column
+                    const int64_t q = po.S ? kGuard + ((s / po.S) * po.out_T + t + po.toff[k]) * po.S * w_out + (s % po.S) * w_out + f
+                                           : kGuard + (s * po.out_T + t + po.toff[k]) * wp_out + f;
                     reinterpret_cast<uint4*>(po.p[k])[(int64_t)g * out_plane + q] = res;
                     if (split) reinterpret_cast<uint4*>(po.p[k])[(int64_t)(cg + g) * out_plane + q] = res_lo;
                 }
@@ -419,6 +646,20 @@ int launch_tc(oww_ctx* ctx, const TcConvArgs& a, cudaStream_t s) {
     }
     int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
     tc_conv_kernel<CGP, NP, TERMS><<<grid, kTcThreads, smem, s>>>(a);
+    OWW_LAUNCH_CHECK(ctx);
+    return OWW_OK;
+}
+
+template <int CGP, int NP>
+int launch_tc_blk(oww_ctx* ctx, const TcBlkArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)2 * 3 * CGP * NP * 16 + (size_t)2 * CGP * a.rows * 16 + 8 * (4 + 2 * kAccStages + 1) + 16 + 2 * NP * sizeof(float);
+    if (smem > 227 * 1024) return oww_fail(ctx, OWW_EUNSUPPORTED, "blocked late conv tile does not fit shared memory (%zu bytes)", smem);
+    if (!ctx->tc_blk_attr_set) {
+        OWW_CUDA(ctx, cudaFuncSetAttribute(tc_conv_blk_kernel<CGP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ctx->tc_blk_attr_set = true;
+    }
+    const int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
+    tc_conv_blk_kernel<CGP, NP><<<grid, kTcThreads, smem, s>>>(a);
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }
@@ -661,6 +902,9 @@ int oww_late_alloc(oww_ctx* ctx) {
     int rows = 8, W = 32;
     for (int l = 0; l < L0; ++l) if (ctx->conv[l].pool_t) { rows /= ctx->conv[l].pool_t; W /= ctx->conv[l].pool_f; }
     size_t tmpl_units = 0, tmp_units = 0;
+    // the blocked kernel is instantiated for 96 -> 96 channels (every (3,1) layer from 11 on)
+    bool blocked = ctx->late_blocked_ok;
+    for (int l = L0; l < OWW_N_CONV; ++l) if (ctx->conv[l].kh == 3 && (ctx->conv[l].cin != 96 || ctx->conv[l].cout != 96)) blocked = false;
     for (int l = L0; l < OWW_N_CONV; ++l) {
         const ConvLayer& C = ctx->conv[l];
         oww_ctx::LateTensor& X = ctx->late_x[l];
@@ -668,7 +912,17 @@ int oww_late_alloc(oww_ctx* ctx) {
         X.rows_new = rows; X.W = W; X.cg = C.cin / 8;
         X.T_buf = rows + (kh3 ? 2 : 0);
         X.n_buf = kh3 ? (rows == 1 ? 3 : 2) : 1;
-        X.plane = (int64_t)((kGuard + (int64_t)n * X.T_buf * (W + 1) + kGuardBack + 7) & ~7LL);
+        // inputs of (3,1) layers: blocks of S streams, time-major, no pad column (tc_conv_blk_kernel): S*rows*W = 128
+        // accumulator rows where that fits shared memory (one half-block of <= 256 units per plane)
+        X.S = 0; X.Wq = W + 1;
+        if (kh3 && blocked) {
+            X.S = std::max(1, 128 / (rows * W));
+            while (X.S > 1 && X.T_buf * X.S * W > 256) X.S /= 2;
+            X.Wq = W;
+        }
+        const int64_t per_stream = (int64_t)X.T_buf * X.Wq;
+        const int64_t n_pad = X.S ? (int64_t)((n + X.S - 1) / X.S) * X.S : n;
+        X.plane = (int64_t)((kGuard + n_pad * per_stream + kGuardBack + 7) & ~7LL);
         X.tmpl_off = kh3 ? (int)tmpl_units : -1;
         if (kh3) tmpl_units += (size_t)2 * X.cg * 2 * (W + 1);
         for (int k = 0; k < X.n_buf; ++k) {
@@ -702,6 +956,46 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
         const bool last = l == OWW_N_CONV - 1;
         const int cg = C.cin / 8, cgp = (cg + 1) & ~1, np = (C.cout + 15) & ~15;
         const int W = X.W, Wp = W + 1, T = X.T_buf, T_out = X.rows_new;
+        // where the output rows go: the next layer's input buffers (or the unpooled temp)
+        auto route = [&](const oww_ctx::LateTensor& Y, __half** p, int* toff, int& n_out) {
+            n_out = 0;
+            if (Y.n_buf == 1) { p[0] = reinterpret_cast<__half*>(Y.buf[0]); toff[0] = 0; n_out = 1; return; }
+            const int r = Y.rows_new;                       // 2 -> two buffers, 1 -> three
+            for (int m = 0; m < Y.n_buf; ++m) {
+                p[m] = reinterpret_cast<__half*>(Y.buf[(k + m) % Y.n_buf]);
+                toff[m] = 2 - m * r;                        // this step: behind the two tails; later steps: as their tails
+            }
+            n_out = Y.n_buf;
+        };
+        const int64_t tmp_plane = (int64_t)((kGuard + (int64_t)n * T_out * Wp + kGuardBack + 7) & ~7LL);
+        int rc;
+        if (X.S) {
+            // (3,1) layer on the blocked dense input: one tile per block of S streams, every accumulator row an output
+            TcBlkArgs b;
+            std::memset(&b, 0, sizeof(b));
+            b.in = reinterpret_cast<const __half*>(X.buf[(int)(k % X.n_buf)]);
+            b.in_plane = X.plane;
+            b.w = reinterpret_cast<const __half*>(ctx->d_tc_w3) + 2 * ctx->tc_w_off[l];
+            b.scale = ctx->d_tc_sb3 + ctx->tc_sb_off[l]; b.bias = b.scale + np;
+            b.n = n; b.T = T; b.W = W; b.S = X.S; b.rows_new = T_out;
+            b.rows = round8(std::max(T * X.S * W, 2 * X.S * W + 128));
+            b.cg_in = cg; b.cg_out = C.cout / 8; b.apply_act = last ? 0 : 1;
+            b.n_tiles = (n + X.S - 1) / X.S;
+            if (last) {
+                b.out_f32 = d_emb;
+            } else if (C.pool_t) {
+                b.out[0] = reinterpret_cast<__half*>(ctx->d_late_tmp[0]);
+                b.out_plane = tmp_plane; b.out_S = 0; b.out_Wq = Wp; b.out_T = T_out;
+            } else {
+                const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
+                int n_out = 0;
+                route(Y, b.out, b.out_toff, n_out);
+                b.out_plane = Y.plane; b.out_S = Y.S; b.out_Wq = Y.Wq; b.out_T = Y.T_buf;
+            }
+            if (cgp == 12 && np == 96) rc = launch_tc_blk<12, 96>(ctx, b, s);
+            else rc = oww_fail(ctx, OWW_EUNSUPPORTED, "no blocked late conv instance for cgp=%d np=%d", cgp, np);
+            if (rc) return rc;
+        } else {
         TcConvArgs a;
         std::memset(&a, 0, sizeof(a));
         a.in = reinterpret_cast<const __half*>(X.buf[X.n_buf == 1 ? 0 : (int)(k % X.n_buf)]);
@@ -715,22 +1009,11 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
         a.p_in = (int64_t)n * T * Wp;
         a.n_tiles = (int)((a.p_in + 127) / 128);
         a.rows_out = T_out;
-        // where the output rows go: the next layer's input buffers (or the unpooled temp)
-        auto route = [&](const oww_ctx::LateTensor& Y, __half** p, int* toff, int& n_out) {
-            n_out = 0;
-            if (Y.n_buf == 1) { p[0] = reinterpret_cast<__half*>(Y.buf[0]); toff[0] = 0; n_out = 1; return; }
-            const int r = Y.rows_new;                       // 2 -> two buffers, 1 -> three
-            for (int m = 0; m < Y.n_buf; ++m) {
-                p[m] = reinterpret_cast<__half*>(Y.buf[(k + m) % Y.n_buf]);
-                toff[m] = 2 - m * r;                        // this step: behind the two tails; later steps: as their tails
-            }
-            n_out = Y.n_buf;
-        };
         if (last) {
             a.out_f32 = d_emb;
         } else if (C.pool_t) {
             a.out = reinterpret_cast<__half*>(ctx->d_late_tmp[0]);
-            a.out_plane = (int64_t)((kGuard + (int64_t)n * T_out * Wp + kGuardBack + 7) & ~7LL);
+            a.out_plane = tmp_plane;
             a.out_split = 1;
         } else {
             const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
@@ -738,20 +1021,23 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
             route(Y, p, toff, n_out);
             a.out = p[0]; a.out_plane = Y.plane; a.out_split = 1;
             a.out_T = Y.T_buf; a.out_toff = toff[0];
+            a.out_S = Y.S; a.out_Wq = Y.Wq;
             for (int m = 1; m < n_out; ++m) { a.out_b[m - 1] = p[m]; a.out_b_toff[m - 1] = toff[m]; }
         }
-        int rc = dispatch_tc<3>(ctx, cgp, np, a, s);
+        rc = dispatch_tc<3>(ctx, cgp, np, a, s);
         if (rc) return rc;
+        }
         if (C.pool_t && !last) {
             const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
             PoolOut po{{nullptr, nullptr, nullptr}, {0, 0, 0}, Y.T_buf};
+            po.S = Y.S;
             int n_out = 0;
             route(Y, po.p, po.toff, n_out);
             const int cgo = C.cout / 8;
             const int64_t total = (int64_t)n * Y.rows_new * (Y.W + 1) * cgo;
             unsigned grid = (unsigned)((total + 255) / 256);
             if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
-            tc_pool_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(ctx->d_late_tmp[0]), a.out_plane, po, Y.plane, n, T_out, W, cgo,
+            tc_pool_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(ctx->d_late_tmp[0]), tmp_plane, po, Y.plane, n, T_out, W, cgo,
                                                C.pool_t, C.pool_f, 1);
             OWW_LAUNCH_CHECK(ctx);
         }

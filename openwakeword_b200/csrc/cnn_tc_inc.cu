@@ -77,7 +77,7 @@ __device__ __forceinline__ int head_rows(int slot_bytes, int K, int D) {
 }
 
 // 96 registers is the ceiling for 18 warps: registers are allocated for warps in fours (20 x 32 x 96 = 61 440 of 65 536)
-// kNL: number of conv layers the kernel runs, fixed at compile time (20 = whole CNN, 11 = the default cut before the
+// kNL: number of conv layers the kernel runs, fixed at compile time (20 = whole CNN, 11 / 15 = cuts before the
 // split-operand layers) or 0 = read from the plan (any other cut).  With the count known the full-depth instance
 // carries none of the cut layer's code.
 template <int kNL>
@@ -1006,6 +1006,7 @@ int oww_inc_alloc_streams(oww_ctx* ctx) {
     ctx->tails_template_valid = false;                   // the scatter table depends on the group size
     OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<OWW_N_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
     OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
+    OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
     OWW_CUDA(ctx, cudaFuncSetAttribute(tc_inc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->inc_plan.smem_bytes));
     return OWW_OK;
 }
@@ -1062,6 +1063,7 @@ bool oww_fused_heads_supported(const oww_ctx* ctx) {
 static void launch_inc(const IncArgs& a, int grid, cudaStream_t s) {
     if (a.plan.n_layers == OWW_N_CONV) tc_inc_kernel<OWW_N_CONV><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
     else if (a.plan.n_layers == 11) tc_inc_kernel<11><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
+    else if (a.plan.n_layers == 15) tc_inc_kernel<15><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
     else tc_inc_kernel<0><<<grid, kIncThreads, a.plan.smem_bytes, s>>>(a);
 }
 

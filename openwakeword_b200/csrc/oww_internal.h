@@ -43,6 +43,7 @@ struct ResetLate {           // one tails-bearing tensor of the incremental late
     uint4* next;             // tensors that gain ONE row per step: the buffer of the step after, row 0 <- template row 1
     const uint4* tmpl;       // [planes][2][Wp]
     int64_t plane; int T_buf, Wp, n_planes;
+    int S, W;                // S > 0: blocked dense destination [block][T_buf][S][W]
 };
 struct ResetTails { uint4* tails; const uint4* tmpl; int G, tail_units, n_tab; int4 tab[OWW_N_CONV]; int n_late; ResetLate late[6]; };
 
@@ -156,11 +157,13 @@ struct oww_ctx {
     int inc_cur = 0;                 // tails buffer the next step reads
     // Incremental late layers (cnn_tc.cu, bottom): tensors X_l = input of conv layer l >= split_from, per stream
     // [tails | new rows], fp16 hi/lo planes in the window-mode layout
-    struct LateTensor { void* buf[3] = {nullptr, nullptr, nullptr}; int n_buf = 0, T_buf = 0, rows_new = 0, W = 0, cg = 0, tmpl_off = -1; int64_t plane = 0; };
+    struct LateTensor { void* buf[3] = {nullptr, nullptr, nullptr}; int n_buf = 0, T_buf = 0, rows_new = 0, W = 0, cg = 0, tmpl_off = -1; int64_t plane = 0;
+                        int S = 0, Wq = 0; };      // S > 0: blocked dense layout [block][T_buf][S][W] (input of a (3,1) layer); else [n][T_buf][W + 1]
     LateTensor late_x[OWW_N_CONV];
     void* d_late_tmp[1] = {nullptr};             // unpooled output of a late layer that is followed by a pool
     void* d_late_template = nullptr;             // tails of the all-ones window per tails-bearing late tensor: [plane][2][Wp]
     bool late_active = false;
+    bool late_blocked_ok = true;                 // OWW_LATE_PLAIN=1 keeps the window-mode layout for every late tensor (A/B)
     long late_step = 0;                          // chunks processed since the buffers were allocated (buffer rotation)
 
     // Priming.  A reset stream's mel history is ones(76,32) (utils.py:165) and its first chunk yields 5 rows (F8).  A
@@ -200,6 +203,7 @@ struct oww_ctx {
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remembered per handle
     bool heads_attr_set = false;
     bool heads_tc_attr_set = false;
+    bool tc_blk_attr_set = false;
     bool mel_clip_attr_set = false;
     uint32_t tc_attr_mask = 0;
     bool tc_heads = true;            // modes 2/3: first head layer on tensor cores when the head allows it (reserved[0] bit 1 disables)

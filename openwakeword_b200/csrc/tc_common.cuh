@@ -61,10 +61,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 27)) __trap();
     }
 }
+__device__ __forceinline__ void tc_warp_wait(uint32_t bar, uint32_t parity, int lane) {
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a converged warp: code under `if (tc_elect_one())` runs on the uniform datapath (UTCHMMA takes uniform
+// registers; from a plain `if (lane == 0)` region every MMA pays register -> uniform moves: ~160 instead of ~60 cycles).
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// one lane polls, the warp follows
+__device__ __forceinline__ void tc_warp_wait(uint32_t bar, uint32_t parity, int lane);
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {

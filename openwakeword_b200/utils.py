@@ -73,7 +73,7 @@ class AudioFeatures:
 
     def __init__(self, melspec_model_path="", embedding_model_path="", sr=16000, ncpu=1,
                  inference_framework="b200", device="gpu", n_streams=1, feature_init=None,
-                 max_chunks=8, cnn_mode=_native.CNN_TC_INCREMENTAL, window_batch=0, device_index=0, split_from=11):
+                 max_chunks=8, cnn_mode=_native.CNN_TC_INCREMENTAL, window_batch=0, device_index=0, split_from=None):
         if inference_framework != "b200":
             raise ValueError(f"openwakeword_b200 only provides inference_framework='b200' (got '{inference_framework}')")
         if sr != 16000:
