@@ -69,11 +69,10 @@ __global__ void reset_kernel(const int* ids, int n_ids, int n_streams, int16_t* 
             for (int i = threadIdx.x; i < T.n_planes * 2 * T.Wp; i += blockDim.x) {
                 const int pl = i / (2 * T.Wp), u = i - pl * 2 * T.Wp, r = u / T.Wp, f = u - r * T.Wp;
                 const uint4 v = T.tmpl[i];
-                if (T.S) {                                  // blocked dense layout [block][T_buf][S][W] (cnn_tc.cu, tc_conv_blk_kernel)
-                    if (f >= T.W) continue;
-                    const int64_t at = (int64_t)pl * T.plane + 8 + ((int64_t)(b / T.S) * T.T_buf + r) * T.S * T.W + (int64_t)(b % T.S) * T.W + f;
-                    T.now[at] = v;
-                    if (T.next && r == 1) T.next[at - (int64_t)T.S * T.W] = v;           // same place, row 0
+                if (T.lay.S) {                              // block-major layout (cnn_tc.cu, tc_conv_blk_kernel): no pad column
+                    if (f >= T.lay.Wq) continue;
+                    T.now[late_unit(T.lay, pl, b, r, f)] = v;
+                    if (T.next && r == 1) T.next[late_unit(T.lay, pl, b, 0, f)] = v;
                     continue;
                 }
                 T.now[(int64_t)pl * T.plane + 8 + ((int64_t)b * T.T_buf + r) * T.Wp + f] = v;
@@ -285,7 +284,7 @@ int reset_enqueue(oww_ctx* ctx, const int32_t* h_stream_ids, int n, const float*
                 T.next = X.n_buf == 3 ? reinterpret_cast<uint4*>(X.buf[(k + 1) % 3]) : nullptr;
                 T.tmpl = reinterpret_cast<const uint4*>(ctx->d_late_template) + X.tmpl_off;
                 T.plane = X.plane; T.T_buf = X.T_buf; T.Wp = X.W + 1; T.n_planes = 2 * X.cg;
-                T.S = X.S; T.W = X.W;
+                T.lay = X.lay;
             }
         }
     }

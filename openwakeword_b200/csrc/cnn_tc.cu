@@ -121,7 +121,6 @@ struct TcConvArgs {
     // tails of later steps.  out_T == 0: plain layout (out_T = T_out, no offset, no mirrors).
     int out_T, out_toff;
     __half* out_b[2]; int out_b_toff[2];    // mirrors (nullptr = unused); same plane pitch as `out`
-    int out_S, out_Wq;                      // out_S > 0: the destination is blocked dense [block][out_T][out_S][out_Wq] (no pad column)
 };
 
 // TERMS = 1: fp16 operands.  TERMS = 3: split operands - the input holds hi planes [0, cg_in) and lo planes
@@ -291,12 +290,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 }
                 continue;
             }
-            const bool pad = f == a.W;
-            if (a.out_S && pad) continue;                                   // dense destination: it has no pad column
-            const int64_t po = a.out_S ? ((int64_t)(n / a.out_S) * a.out_T + t + a.out_toff) * a.out_S * a.out_Wq + (int64_t)(n % a.out_S) * a.out_Wq + f
-                               : a.out_T ? (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_toff) * Wp + f
-                                         : (int64_t)n * per_out + (int64_t)t * Wp + f;
+            const int64_t po = a.out_T ? (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_toff) * Wp + f
+                                       : (int64_t)n * per_out + (int64_t)t * Wp + f;
             uint4* o = reinterpret_cast<uint4*>(a.out) + kGuard + po;
+            const bool pad = f == a.W;
 #pragma unroll
             for (int k = 0; k < PH; ++k) {
                 const int g = pl0 + k;
@@ -314,17 +311,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 }
                 if (g < a.cg_out) {
                     o[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
-                    if (po == 0 && !a.out_S) o[(int64_t)g * a.out_plane - 1] = make_uint4(0, 0, 0, 0);   // front guard (position -1)
+                    if (po == 0) o[(int64_t)g * a.out_plane - 1] = make_uint4(0, 0, 0, 0);   // front guard (position -1)
                     if (a.out_split) {
                         o[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
-                        if (po == 0 && !a.out_S) o[(int64_t)(a.cg_out + g) * a.out_plane - 1] = make_uint4(0, 0, 0, 0);
+                        if (po == 0) o[(int64_t)(a.cg_out + g) * a.out_plane - 1] = make_uint4(0, 0, 0, 0);
                     }
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk)
                         if (a.out_b[kk]) {
-                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[kk]) + kGuard +
-                                        (a.out_S ? ((int64_t)(n / a.out_S) * a.out_T + t + a.out_b_toff[kk]) * a.out_S * a.out_Wq + (int64_t)(n % a.out_S) * a.out_Wq + f
-                                                 : (int64_t)n * a.out_T * Wp + (int64_t)(t + a.out_b_toff[kk]) * Wp + f);
+                            uint4* ob = reinterpret_cast<uint4*>(a.out_b[kk]) + kGuard + (int64_t)n * a.out_T * Wp +
+                                        (int64_t)(t + a.out_b_toff[kk]) * Wp + f;
                             ob[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
                             if (a.out_split) ob[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
                         }
@@ -340,30 +336,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
     }
 }
 
-// ---------------------------------------------------------------- incremental late (3,1) layers: blocked input
-// The window-mode kernel above runs a (3,1) layer of the incremental chain on per-stream "windows" [2 tails | new rows]
-// x (W + 1): of the 128 accumulator rows of a tile only rows_new / T carry outputs, and one column in W + 1 is padding
-// (layer 16: 4 of 12 positions, layer 19: 1 of 6) - the MMAs cost the same.  Here the input tensor is stored in blocks
-// of S streams, time-major inside a block and without the pad column: [block][T rows][S streams][W] units.  One tile =
-// one block: tap k reads rows k .. k + rows_new - 1 = ONE contiguous run of rows_new*S*W = 128 units at offset k*S*W,
-// and every accumulator row is a real output.  The hi and the lo half of a block (98 KB together at 96 channels) do not
-// fit twice beside the 110 KB of split weights, so the two shared-memory slots hold one HALF each: the MMAs of the hi
-// half ((hi,hi), (hi,lo)) run while the lo half lands, the lo MMAs ((lo,hi)) while the next block's hi half lands.
+// ---------------------------------------------------------------- incremental late layers: block-major tensors
+// The window-mode kernel above can run a layer of the incremental chain on per-stream "windows" [2 tails | new rows] x
+// (W + 1) in plane-major HBM tensors.  Two things make that slow there: of the 128 accumulator rows of a (3,1) tile only
+// rows_new / T carry outputs and one column in W + 1 is padding (layer 16: 4 of 12 positions, layer 19: 1 of 6) while an
+// MMA costs the same; and a tile's channel-group planes are far apart in HBM, i.e. 24 bulk copies of 2-4 KB per tile.
+// Here a late tensor is stored in blocks of S streams, a block being [2*cg planes][units] CONTIGUOUS in HBM (LateLay):
+//   input of a (3,1) layer: time-major inside the block, no pad column: unit (row*S + s)*W + f.  Tap k of the conv reads
+//     rows k .. k + rows_new - 1 = one contiguous run of rows_new*S*W = 128 units at offset k*S*W: every accumulator row
+//     is an output;
+//   input of a (1,3) layer: stream-major with the pad column behind a zero guard unit: unit 1 + (s*T + row)*(W+1) + f,
+//     taps at unit offsets 0, 1, 2.
+// One tile = one block; its hi half and its lo half arrive by ONE bulk copy each.  The two halves of a 96-channel (3,1)
+// block (98 KB) do not fit twice beside the 110 KB of split weights, so the two shared-memory slots hold one half each:
+// the MMAs of the hi half ((hi,hi), (hi,lo)) run while the lo half lands, the lo MMAs ((lo,hi)) while the next block's
+// hi half lands.  The epilogue writes straight into the next layer's block-major tensor(s) (or the plain unpooled temp).
 struct TcBlkArgs {
-    const __half* in; int64_t in_plane;     // hi planes [0, cg_in), lo planes [cg_in, 2 cg_in); block b at kGuard + b*T*S*W
+    const __half* in; LateLay lay;          // input tensor
     const __half* w; const float* scale; const float* bias;
-    int n, T, W, S, rows_new;
-    int rows;                               // smem rows per plane: T*S*W rounded up to 8
+    int n, W, rows_new;                     // streams, real width, output rows per stream
+    int m_valid, tap;                       // accumulator rows that are positions of the block; unit distance of the taps
     int cg_in, cg_out, apply_act, n_tiles;
-    float* out_f32;                         // final layer: [n][96]
-    // destination tensor: plain [n][out_T][out_Wq] (out_S == 0; pad column zeroed) or blocked dense [block][out_T][out_S][out_Wq]
-    __half* out[3]; int out_toff[3]; int64_t out_plane; int out_S, out_Wq, out_T;
+    float* out_f32;                         // final layer: [n][rows_new][96]
+    __half* out[3]; int out_toff[3];        // destination buffers (this step / later steps' tails) and their row offsets
+    LateLay out_lay;                        // out_lay.S > 0: block-major destination; else the plain temp [n][rows_new][W+1]
+    int64_t out_plane;                      //   (plane pitch of the plain temp)
 };
-
-__device__ __forceinline__ int64_t late_pos(int S, int Wq, int T, int stream, int row, int f) {
-    return S ? ((int64_t)(stream / S) * T + row) * S * Wq + (int64_t)(stream % S) * Wq + f
-             : ((int64_t)stream * T + row) * Wq + f;
-}
 
 template <int CGP, int NP>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a) {
@@ -371,7 +369,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
     constexpr int W_TERM = 3 * CGP * NP * 16;
     constexpr int W_BYTES = 2 * W_TERM;
     uint8_t* w_smem = smem;
-    const int half_bytes = CGP * a.rows * 16;
+    const int units = a.lay.units;
+    const int half_bytes = CGP * units * 16;
     uint8_t* a_smem = smem + W_BYTES;                                      // slot 0: hi half, slot 1: lo half
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_smem + 2 * half_bytes);
     // bars: full[2], empty[2], tmem_full[A], tmem_empty[A], w_full
@@ -393,15 +392,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
         mbar_init(wfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // pad planes (cg_in odd) and the rows behind the block are never written by the bulk copies: zero them once
-    for (int h = 0; h < 2; ++h) {
-        uint4* base = reinterpret_cast<uint4*>(a_smem + h * half_bytes);
-        const int used = a.T * a.S * a.W;
-        for (int i = threadIdx.x; i < CGP * a.rows; i += kTcThreads) {
-            const int g = i / a.rows, r = i - g * a.rows;
-            if (g >= a.cg_in || r >= used) base[i] = make_uint4(0, 0, 0, 0);
+    // pad planes (odd cg_in) are never written by the bulk copies: zero them once
+    if (a.cg_in < CGP)
+        for (int h = 0; h < 2; ++h) {
+            uint4* pz = reinterpret_cast<uint4*>(a_smem + h * half_bytes + a.cg_in * units * 16);
+            for (int i = threadIdx.x; i < (CGP - a.cg_in) * units; i += kTcThreads) pz[i] = make_uint4(0, 0, 0, 0);
         }
-    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
@@ -411,23 +407,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int blk_units = a.T * a.S * a.W;
 
     if (warp == 0) {
-        // ===================== producer: weights once, then hi half / lo half of one block per tile =====================
+        // ===================== producer: weights once, then the hi half and the lo half of one block per tile ==========
         if (lane == 0) {
             mbar_expect_tx(wfull_bar, W_BYTES);
             bulk_g2s(smem_u32(w_smem), a.w, W_BYTES, wfull_bar);
             uint32_t phase = 0;
-            const uint32_t plane_bytes = (uint32_t)blk_units * 16u, pitch = (uint32_t)a.rows * 16u;
+            const uint32_t bytes = (uint32_t)(a.cg_in * units) * 16u;
+            const uint4* in = reinterpret_cast<const uint4*>(a.in);
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                const int64_t u0 = kGuard + (int64_t)tile * blk_units;
                 for (int h = 0; h < 2; ++h) {
                     mbar_wait(empty_bar(h), phase ^ 1);
-                    mbar_expect_tx(full_bar(h), plane_bytes * a.cg_in);
-                    for (int g = 0; g < a.cg_in; ++g)
-                        bulk_g2s(smem_u32(a_smem + h * half_bytes + g * pitch),
-                                 reinterpret_cast<const uint4*>(a.in) + (int64_t)(h * a.cg_in + g) * a.in_plane + u0, plane_bytes, full_bar(h));
+                    mbar_expect_tx(full_bar(h), bytes);
+                    bulk_g2s(smem_u32(a_smem + h * half_bytes), in + (int64_t)tile * a.lay.blk_stride + (int64_t)h * a.cg_in * units, bytes, full_bar(h));
                 }
                 phase ^= 1;
             }
@@ -439,8 +432,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
             tc_warp_wait(wfull_bar, 0, lane);
             uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             const uint32_t w_addr = smem_u32(w_smem), a_addr = smem_u32(a_smem);
-            const uint32_t lbo_a = (uint32_t)a.rows * 16u, rows16 = (uint32_t)a.rows * 16u;
-            const uint32_t tap16 = (uint32_t)(a.S * a.W) * 16u;
+            const uint32_t lbo_a = (uint32_t)units * 16u;
+            const uint32_t tap16 = (uint32_t)a.tap * 16u;
             for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 tc_warp_wait(tempty_bar(acc), acc_phase ^ 1, lane);
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
@@ -456,7 +449,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
 #pragma unroll
                                 for (int wt = 0; wt < (h == 0 ? 2 : 1); ++wt) {      // hi half: (hi,hi), (hi,lo); lo half: (lo,hi)
                                     const uint32_t w_t = w_addr + (wt == 1 ? (uint32_t)W_TERM : 0u);
-                                    const uint64_t ad = make_desc(a_addr + (uint32_t)h * (uint32_t)half_bytes + (uint32_t)(2 * q) * rows16 + (uint32_t)j * tap16,
+                                    const uint64_t ad = make_desc(a_addr + (uint32_t)h * (uint32_t)half_bytes + (uint32_t)(2 * q) * lbo_a + (uint32_t)j * tap16,
                                                                   lbo_a, 128u);
                                     const uint64_t bd = make_desc(w_t + (uint32_t)((j * CGP + 2 * q) * NP) * 16u, NP * 16u, 128u);
                                     tc_mma_f16(d_tmem, ad, bd, idesc, (h | j | q | wt) != 0);
@@ -478,9 +471,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
         constexpr int NP8 = NP / 8, PH = NP8 / 2;
         const int pl0 = half * PH;
         const int row = quarter * 32 + lane;
-        const int SW = a.S * a.W;
-        const int t = row / SW, sl = (row - t * SW) / a.W, f = row - t * SW - sl * a.W;
-        const bool row_ok = row < a.rows_new * SW;
+        // accumulator row -> (stream of the block, output row, column)
+        int t, sl, f;
+        if (a.lay.kh3) { const int SW = a.lay.S * a.W; t = row / SW; sl = (row - t * SW) / a.W; f = row - t * SW - sl * a.W; }
+        else { const int per = a.lay.T * a.lay.Wq; sl = row / per; t = (row - sl * per) / a.lay.Wq; f = row - sl * per - t * a.lay.Wq; }
+        const bool row_ok = row < a.m_valid && f < a.W;                 // (1,3): the pad column computes nothing that is kept
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -495,9 +490,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
-            const int n = tile * a.S + sl;
+            const int n = tile * a.lay.S + sl;
             if (!row_ok || n >= a.n) continue;
             if (a.out_f32) {
+                if (f != 0) continue;
                 float* o = a.out_f32 + ((int64_t)n * a.rows_new + t) * 96;
 #pragma unroll
                 for (int k = 0; k < PH; ++k) {
@@ -517,6 +513,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
                 }
                 continue;
             }
+            // unit of this position in the destination(s), plane 0
+            int64_t dst[3];
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk)
+                dst[kk] = a.out_lay.S ? late_unit(a.out_lay, 0, n, t + a.out_toff[kk], f)
+                                      : kGuard + ((int64_t)n * a.rows_new + t) * (a.W + 1) + f;
+            const int64_t pstride = a.out_lay.S ? (int64_t)a.out_lay.units : a.out_plane;
 #pragma unroll
             for (int k = 0; k < PH; ++k) {
                 const int g = pl0 + k;
@@ -535,9 +538,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk)
                     if (a.out[kk]) {
-                        uint4* o = reinterpret_cast<uint4*>(a.out[kk]) + kGuard + late_pos(a.out_S, a.out_Wq, a.out_T, n, t + a.out_toff[kk], f);
-                        o[(int64_t)g * a.out_plane] = *reinterpret_cast<uint4*>(h);
-                        o[(int64_t)(a.cg_out + g) * a.out_plane] = *reinterpret_cast<uint4*>(l);
+                        uint4* o = reinterpret_cast<uint4*>(a.out[kk]) + dst[kk];
+                        o[(int64_t)g * pstride] = *reinterpret_cast<uint4*>(h);
+                        o[(int64_t)(a.cg_out + g) * pstride] = *reinterpret_cast<uint4*>(l);
                     }
             }
         }
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
 // ---------------------------------------------------------------- max-pool on fp16 planes
 // split != 0: planes [0, cg) hold hi parts and [cg, 2cg) lo parts of the same values; the pooled element is the one
 // with the largest hi + lo, i.e. the lexicographic maximum of (hi, lo) since |lo| <= ulp(hi)/2.
-struct PoolOut { __half* p[3]; int toff[3]; int out_T; int S = 0; };     // out_T == 0: plain [n][t_out][wp_out] into p[0]; S > 0: blocked dense destination [block][out_T][S][w_out]
+struct PoolOut { __half* p[3]; int toff[3]; int out_T; LateLay lay = {0, 0, 0, 0, 0, 0}; };   // out_T == 0: plain [n][t_out][wp_out] into p[0]; lay.S > 0: block-major destination
 __global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t in_plane, PoolOut po, int64_t out_plane,
                                                       int n, int t_in, int w_in, int cg, int pt, int pf, int split) {
     __half* const out = po.p[0];
@@ -601,9 +604,13 @@ __global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t 
 #pragma unroll
             for (int k = 0; k < 3; ++k)
                 if (po.p[k]) {
-                    if (po.S && f >= w_out) continue;                   // dense destination: no pad column
-                    const int64_t q = po.S ? kGuard + ((s / po.S) * po.out_T + t + po.toff[k]) * po.S * w_out + (s % po.S) * w_out + f
-                                           : kGuard + (s * po.out_T + t + po.toff[k]) * wp_out + f;
+                    if (po.lay.S) {                                     // block-major: pad column untouched (zero since allocation)
+                        if (f >= w_out) continue;
+                        reinterpret_cast<uint4*>(po.p[k])[late_unit(po.lay, g, (int)s, t + po.toff[k], f)] = res;
+                        if (split) reinterpret_cast<uint4*>(po.p[k])[late_unit(po.lay, cg + g, (int)s, t + po.toff[k], f)] = res_lo;
+                        continue;
+                    }
+                    const int64_t q = kGuard + (s * po.out_T + t + po.toff[k]) * wp_out + f;
                     reinterpret_cast<uint4*>(po.p[k])[(int64_t)g * out_plane + q] = res;
                     if (split) reinterpret_cast<uint4*>(po.p[k])[(int64_t)(cg + g) * out_plane + q] = res_lo;
                 }
@@ -652,11 +659,12 @@ int launch_tc(oww_ctx* ctx, const TcConvArgs& a, cudaStream_t s) {
 
 template <int CGP, int NP>
 int launch_tc_blk(oww_ctx* ctx, const TcBlkArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)2 * 3 * CGP * NP * 16 + (size_t)2 * CGP * a.rows * 16 + 8 * (4 + 2 * kAccStages + 1) + 16 + 2 * NP * sizeof(float);
+    const size_t smem = (size_t)2 * 3 * CGP * NP * 16 + (size_t)2 * CGP * a.lay.units * 16 + 8 * (4 + 2 * kAccStages + 1) + 16 + 2 * NP * sizeof(float);
     if (smem > 227 * 1024) return oww_fail(ctx, OWW_EUNSUPPORTED, "blocked late conv tile does not fit shared memory (%zu bytes)", smem);
-    if (!ctx->tc_blk_attr_set) {
+    const uint32_t bit = 1u << (CGP / 2);
+    if (!(ctx->tc_blk_attr_mask & bit)) {
         OWW_CUDA(ctx, cudaFuncSetAttribute(tc_conv_blk_kernel<CGP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ctx->tc_blk_attr_set = true;
+        ctx->tc_blk_attr_mask |= bit;
     }
     const int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
     tc_conv_blk_kernel<CGP, NP><<<grid, kTcThreads, smem, s>>>(a);
@@ -902,9 +910,9 @@ int oww_late_alloc(oww_ctx* ctx) {
     int rows = 8, W = 32;
     for (int l = 0; l < L0; ++l) if (ctx->conv[l].pool_t) { rows /= ctx->conv[l].pool_t; W /= ctx->conv[l].pool_f; }
     size_t tmpl_units = 0, tmp_units = 0;
-    // the blocked kernel is instantiated for 96 -> 96 channels (every (3,1) layer from 11 on)
+    // the block-major kernel is instantiated for 72 / 96 -> 96 channels (every layer from 11 on)
     bool blocked = ctx->late_blocked_ok;
-    for (int l = L0; l < OWW_N_CONV; ++l) if (ctx->conv[l].kh == 3 && (ctx->conv[l].cin != 96 || ctx->conv[l].cout != 96)) blocked = false;
+    for (int l = L0; l < OWW_N_CONV; ++l) if ((ctx->conv[l].cin != 96 && ctx->conv[l].cin != 72) || ctx->conv[l].cout != 96) blocked = false;
     for (int l = L0; l < OWW_N_CONV; ++l) {
         const ConvLayer& C = ctx->conv[l];
         oww_ctx::LateTensor& X = ctx->late_x[l];
@@ -912,22 +920,29 @@ int oww_late_alloc(oww_ctx* ctx) {
         X.rows_new = rows; X.W = W; X.cg = C.cin / 8;
         X.T_buf = rows + (kh3 ? 2 : 0);
         X.n_buf = kh3 ? (rows == 1 ? 3 : 2) : 1;
-        // inputs of (3,1) layers: blocks of S streams, time-major, no pad column (tc_conv_blk_kernel): S*rows*W = 128
-        // accumulator rows where that fits shared memory (one half-block of <= 256 units per plane)
-        X.S = 0; X.Wq = W + 1;
-        if (kh3 && blocked) {
-            X.S = std::max(1, 128 / (rows * W));
-            while (X.S > 1 && X.T_buf * X.S * W > 256) X.S /= 2;
-            X.Wq = W;
+        // block-major layout (tc_conv_blk_kernel): S streams per block so that the block's positions fill the 128
+        // accumulator rows ((3,1): rows*S*W outputs, and the whole [T][S][W] block <= 256 units per plane)
+        X.lay = LateLay{0, 0, 0, 0, 0, 0};
+        size_t buf_units;
+        if (blocked) {
+            LateLay& Y = X.lay;
+            Y.kh3 = kh3 ? 1 : 0; Y.T = X.T_buf; Y.Wq = kh3 ? W : W + 1;
+            Y.S = std::max(1, 128 / (rows * Y.Wq));
+            if (kh3) while (Y.S > 1 && X.T_buf * Y.S * W > 256) Y.S /= 2;
+            const int tap = kh3 ? Y.S * W : 1;
+            Y.units = round8(std::max((kh3 ? 0 : 1) + Y.T * Y.S * Y.Wq, 2 * tap + 128));
+            Y.blk_stride = (int64_t)2 * X.cg * Y.units;
+            buf_units = (size_t)((n + Y.S - 1) / Y.S) * Y.blk_stride;
+            X.plane = 0;
+        } else {
+            X.plane = (int64_t)((kGuard + (int64_t)n * X.T_buf * (W + 1) + kGuardBack + 7) & ~7LL);
+            buf_units = (size_t)2 * X.cg * X.plane;
         }
-        const int64_t per_stream = (int64_t)X.T_buf * X.Wq;
-        const int64_t n_pad = X.S ? (int64_t)((n + X.S - 1) / X.S) * X.S : n;
-        X.plane = (int64_t)((kGuard + n_pad * per_stream + kGuardBack + 7) & ~7LL);
         X.tmpl_off = kh3 ? (int)tmpl_units : -1;
         if (kh3) tmpl_units += (size_t)2 * X.cg * 2 * (W + 1);
         for (int k = 0; k < X.n_buf; ++k) {
-            OWW_CUDA(ctx, cudaMalloc(&X.buf[k], (size_t)2 * X.cg * X.plane * 16));
-            OWW_CUDA(ctx, cudaMemset(X.buf[k], 0, (size_t)2 * X.cg * X.plane * 16));
+            OWW_CUDA(ctx, cudaMalloc(&X.buf[k], buf_units * 16));
+            OWW_CUDA(ctx, cudaMemset(X.buf[k], 0, buf_units * 16));
         }
         if (C.pool_t) {
             const size_t u = (size_t)2 * (C.cout / 8) * ((kGuard + (size_t)n * rows * (W + 1) + kGuardBack + 7) & ~(size_t)7);
@@ -969,31 +984,33 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
         };
         const int64_t tmp_plane = (int64_t)((kGuard + (int64_t)n * T_out * Wp + kGuardBack + 7) & ~7LL);
         int rc;
-        if (X.S) {
-            // (3,1) layer on the blocked dense input: one tile per block of S streams, every accumulator row an output
+        if (X.lay.S) {
+            // block-major input: one tile per block of S streams
             TcBlkArgs b;
             std::memset(&b, 0, sizeof(b));
-            b.in = reinterpret_cast<const __half*>(X.buf[(int)(k % X.n_buf)]);
-            b.in_plane = X.plane;
+            b.in = reinterpret_cast<const __half*>(X.buf[X.n_buf == 1 ? 0 : (int)(k % X.n_buf)]);
+            b.lay = X.lay;
             b.w = reinterpret_cast<const __half*>(ctx->d_tc_w3) + 2 * ctx->tc_w_off[l];
             b.scale = ctx->d_tc_sb3 + ctx->tc_sb_off[l]; b.bias = b.scale + np;
-            b.n = n; b.T = T; b.W = W; b.S = X.S; b.rows_new = T_out;
-            b.rows = round8(std::max(T * X.S * W, 2 * X.S * W + 128));
+            b.n = n; b.W = W; b.rows_new = T_out;
+            b.m_valid = T_out * X.lay.S * X.lay.Wq;
+            b.tap = C.kh == 3 ? X.lay.S * W : 1;
             b.cg_in = cg; b.cg_out = C.cout / 8; b.apply_act = last ? 0 : 1;
-            b.n_tiles = (n + X.S - 1) / X.S;
+            b.n_tiles = (n + X.lay.S - 1) / X.lay.S;
             if (last) {
                 b.out_f32 = d_emb;
             } else if (C.pool_t) {
                 b.out[0] = reinterpret_cast<__half*>(ctx->d_late_tmp[0]);
-                b.out_plane = tmp_plane; b.out_S = 0; b.out_Wq = Wp; b.out_T = T_out;
+                b.out_plane = tmp_plane;
             } else {
                 const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
                 int n_out = 0;
                 route(Y, b.out, b.out_toff, n_out);
-                b.out_plane = Y.plane; b.out_S = Y.S; b.out_Wq = Y.Wq; b.out_T = Y.T_buf;
+                b.out_lay = Y.lay;
             }
             if (cgp == 12 && np == 96) rc = launch_tc_blk<12, 96>(ctx, b, s);
-            else rc = oww_fail(ctx, OWW_EUNSUPPORTED, "no blocked late conv instance for cgp=%d np=%d", cgp, np);
+            else if (cgp == 10 && np == 96) rc = launch_tc_blk<10, 96>(ctx, b, s);
+            else rc = oww_fail(ctx, OWW_EUNSUPPORTED, "no block-major late conv instance for cgp=%d np=%d", cgp, np);
             if (rc) return rc;
         } else {
         TcConvArgs a;
@@ -1021,7 +1038,6 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
             route(Y, p, toff, n_out);
             a.out = p[0]; a.out_plane = Y.plane; a.out_split = 1;
             a.out_T = Y.T_buf; a.out_toff = toff[0];
-            a.out_S = Y.S; a.out_Wq = Y.Wq;
             for (int m = 1; m < n_out; ++m) { a.out_b[m - 1] = p[m]; a.out_b_toff[m - 1] = toff[m]; }
         }
         rc = dispatch_tc<3>(ctx, cgp, np, a, s);
@@ -1030,7 +1046,7 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
         if (C.pool_t && !last) {
             const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
             PoolOut po{{nullptr, nullptr, nullptr}, {0, 0, 0}, Y.T_buf};
-            po.S = Y.S;
+            po.lay = Y.lay;
             int n_out = 0;
             route(Y, po.p, po.toff, n_out);
             const int cgo = C.cout / 8;

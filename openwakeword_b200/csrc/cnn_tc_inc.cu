@@ -67,7 +67,7 @@ struct IncArgs {
     const Gate* gates; int n_gates;                           // conditional verifier pairs, applied after the heads phase
     // cut plan (plan.n_layers < 20): the pooled output of the last fused layer leaves the kernel as fp16 hi/lo planes in
     // the window-mode layout [plane][stream][row][f + pad] - the input of the incremental late layers (cnn_tc.cu)
-    uint4* gx; int64_t gx_plane;
+    uint4* gx; int64_t gx_plane; LateLay gx_lay;     // gx_lay.S > 0: block-major destination (cnn_tc.cu)
 };
 
 // Rows of a later head layer (K x D floats) per ring chunk: a multiple of 4 rows (16-byte chunk starts) that fits a slot.
@@ -564,8 +564,13 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                                 }
                                 if (s_live[g]) {
                                     const int64_t q = kGuard + ((int64_t)(grp * G + g) * T2 + t) * L.nx_Wp + f;
-                                    a.gx[(int64_t)pl * a.gx_plane + q] = res;
-                                    a.gx[(int64_t)(L.cg_out + pl) * a.gx_plane + q] = res_lo;
+                                    if (a.gx_lay.S) {
+                                        a.gx[late_unit(a.gx_lay, pl, grp * G + g, t, f)] = res;
+                                        a.gx[late_unit(a.gx_lay, L.cg_out + pl, grp * G + g, t, f)] = res_lo;
+                                    } else {
+                                        a.gx[(int64_t)pl * a.gx_plane + q] = res;
+                                        a.gx[(int64_t)(L.cg_out + pl) * a.gx_plane + q] = res_lo;
+                                    }
                                 }
                                 continue;
                             }
@@ -1081,6 +1086,7 @@ static void fill_inc_args(oww_ctx* ctx, IncArgs& a) {
     if (ctx->late_active) {
         a.gx = reinterpret_cast<uint4*>(ctx->late_x[ctx->split_from].buf[0]);
         a.gx_plane = ctx->late_x[ctx->split_from].plane;
+        a.gx_lay = ctx->late_x[ctx->split_from].lay;
     }
 }
 

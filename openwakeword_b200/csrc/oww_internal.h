@@ -37,13 +37,30 @@ struct Head {
     std::vector<float> tc_w0_host;   // first-layer matrix [n_in*96][D1] (host copy: the grouped kernel packs it per group)
 };
 
+// Block-major layout of an incremental late tensor (cnn_tc.cu, tc_conv_blk_kernel): streams in blocks of S, a block is
+// [2*cg planes][units] contiguous in HBM (one bulk copy per half), and inside a plane
+//   kh3 (input of a (3,1) layer):  unit (row*S + s)*W + f            - time-major, no pad column
+//   else (input of a (1,3) layer): unit 1 + (s*T + row)*(W+1) + f    - stream-major, pad column, unit 0 = zero guard
+struct LateLay {
+    int S, T, Wq, kh3;           // streams per block, rows per stream, row pitch (W or W+1), orientation
+    int units;                   // units per plane of a block
+    int64_t blk_stride;          // units per block (2*cg*units)
+};
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ int64_t late_unit(const LateLay& L, int plane, int stream, int row, int f) {
+    const int blk = stream / L.S, sl = stream - blk * L.S;
+    const int within = L.kh3 ? (row * L.S + sl) * L.Wq + f : 1 + (sl * L.T + row) * L.Wq + f;
+    return (int64_t)blk * L.blk_stride + (int64_t)plane * L.units + within;
+}
+#endif
+
 // what reset_kernel needs to seed a stream's conv tails (mode 3)
 struct ResetLate {           // one tails-bearing tensor of the incremental late layers
     uint4* now;              // buffer the stream's next step reads: rows 0, 1 <- template rows 0, 1
     uint4* next;             // tensors that gain ONE row per step: the buffer of the step after, row 0 <- template row 1
     const uint4* tmpl;       // [planes][2][Wp]
     int64_t plane; int T_buf, Wp, n_planes;
-    int S, W;                // S > 0: blocked dense destination [block][T_buf][S][W]
+    LateLay lay;             // lay.S > 0: block-major destination
 };
 struct ResetTails { uint4* tails; const uint4* tmpl; int G, tail_units, n_tab; int4 tab[OWW_N_CONV]; int n_late; ResetLate late[6]; };
 
@@ -158,7 +175,7 @@ struct oww_ctx {
     // Incremental late layers (cnn_tc.cu, bottom): tensors X_l = input of conv layer l >= split_from, per stream
     // [tails | new rows], fp16 hi/lo planes in the window-mode layout
     struct LateTensor { void* buf[3] = {nullptr, nullptr, nullptr}; int n_buf = 0, T_buf = 0, rows_new = 0, W = 0, cg = 0, tmpl_off = -1; int64_t plane = 0;
-                        int S = 0, Wq = 0; };      // S > 0: blocked dense layout [block][T_buf][S][W] (input of a (3,1) layer); else [n][T_buf][W + 1]
+                        LateLay lay = {0, 0, 0, 0, 0, 0}; };   // lay.S > 0: block-major (tc_conv_blk_kernel); else plane-major [n][T_buf][W + 1]
     LateTensor late_x[OWW_N_CONV];
     void* d_late_tmp[1] = {nullptr};             // unpooled output of a late layer that is followed by a pool
     void* d_late_template = nullptr;             // tails of the all-ones window per tails-bearing late tensor: [plane][2][Wp]
@@ -203,7 +220,7 @@ struct oww_ctx {
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remembered per handle
     bool heads_attr_set = false;
     bool heads_tc_attr_set = false;
-    bool tc_blk_attr_set = false;
+    uint32_t tc_blk_attr_mask = 0;
     bool mel_clip_attr_set = false;
     uint32_t tc_attr_mask = 0;
     bool tc_heads = true;            // modes 2/3: first head layer on tensor cores when the head allows it (reserved[0] bit 1 disables)
