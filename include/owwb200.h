@@ -75,7 +75,8 @@ typedef struct oww_config {
                               fed from the fp16 mirror of the rings (heads_grp.cu);
                               bit 4: 1 = the incremental late (3,1) layers keep the window-mode tensor layout
                               (per-stream [tails | new rows] x (W+1): most accumulator rows of a tile are not outputs)
-                              instead of the blocked time-major layout of tc_conv_blk_kernel.
+                              instead of the block-major layout of tc_conv_blk_kernel;
+                              bit 5: 1 = no programmatic dependent launches inside the late chain.
                               reserved[1]: first conv layer that takes fp16 hi/lo split operands in the
                               tensor-core modes, 2..20 (0 = default 11; 20 = plain fp16 everywhere)           */
 } oww_config;

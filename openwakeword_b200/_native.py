@@ -127,7 +127,8 @@ class Context:
         self.lib = load_library()
         cfg = Config(device=device, max_chunks=max_chunks, cnn_mode=cnn_mode, window_batch=window_batch)
         cfg.reserved[0] = ((0 if fuse_step else 1) | (0 if tc_heads else 2) | (4 if tc_heads_terms == 1 else 0)
-                           | (0 if group_heads else 8) | (0 if late_blocked else 16))
+                           | (0 if group_heads else 8) | (0 if late_blocked else 16)
+                           | int(os.environ.get("OWW_FLAGS", "0"), 0))      # extra reserved[0] bits for A/B runs (include/owwb200.h)
         if split_from is None:                      # library default (0), or OWW_SPLIT_FROM for experiments
             split_from = int(os.environ.get("OWW_SPLIT_FROM", "0"))
         cfg.reserved[1] = int(split_from)

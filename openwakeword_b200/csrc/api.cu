@@ -336,6 +336,7 @@ int oww_create(const oww_config* cfg, oww_ctx** out) {
     ctx->tc_heads_terms = (cfg->reserved[0] & 4) ? 1 : 3;
     ctx->grp_heads = (cfg->reserved[0] & 8) == 0;
     ctx->late_blocked_ok = (cfg->reserved[0] & 16) == 0;
+    ctx->late_pdl = (cfg->reserved[0] & 32) == 0;
     cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     fill_layer_table(ctx);

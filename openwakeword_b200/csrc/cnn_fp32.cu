@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const float* in, int64_t in_s
 __global__ void __launch_bounds__(256) feat_append_kernel(const float* emb, float* ring, int* count, int n_streams,
                                                           int n_chunks, int rows_mask, int64_t ring_stride, const int* ids) {
     const int64_t total = (int64_t)n_streams * n_chunks * 24;   // float4 units
+    oww_pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int c4 = (int)(i % 24);
         const int64_t j = i / 24;                 // window index = chunk * n_streams + stream
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(256) feat_append_kernel(const float* emb, floa
 }
 __global__ void count_add_kernel(int* count, int n, int add, const int* ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    oww_pdl_sync();
     if (i < n) { const int b = ids ? ids[i] : i; count[b] = oww_wrap_count(count[b] + add); }
 }
 
@@ -405,10 +407,10 @@ int oww_feat_append(oww_ctx* ctx, const float* d_emb, int n_chunks, cudaStream_t
     if (B <= 0) return OWW_OK;
     const int64_t total = (int64_t)B * n_chunks * 24;
     unsigned grid = (unsigned)((total + 255) / 256);
-    feat_append_kernel<<<grid, 256, 0, s>>>(d_emb, ctx->d_feat_ring, ctx->d_feat_count, B, n_chunks,
-                                           ctx->feat_rows - 1, (int64_t)ctx->feat_rows * 96, d_ids);
+    OWW_CUDA(ctx, oww_launch_pdl(ctx->late_pdl, feat_append_kernel, dim3(grid), dim3(256), 0, s, d_emb, ctx->d_feat_ring, ctx->d_feat_count, B,
+                                 n_chunks, ctx->feat_rows - 1, (int64_t)ctx->feat_rows * 96, d_ids));
     OWW_LAUNCH_CHECK(ctx);
-    count_add_kernel<<<(B + 255) / 256, 256, 0, s>>>(ctx->d_feat_count, B, n_chunks, d_ids);
+    OWW_CUDA(ctx, oww_launch_pdl(ctx->late_pdl, count_add_kernel, dim3((B + 255) / 256), dim3(256), 0, s, ctx->d_feat_count, B, n_chunks, d_ids));
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }

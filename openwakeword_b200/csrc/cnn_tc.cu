@@ -407,12 +407,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Chain of dependent launches: the successor may be scheduled from now on (it waits for this grid's completion itself
+    // before it touches a tensor); this CTA's prologue - barriers, TMEM, the weight copy below - ran beside the
+    // predecessor's tail, and only now do we wait for the predecessor's outputs.
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== producer: weights once, then the hi half and the lo half of one block per tile ==========
         if (lane == 0) {
             mbar_expect_tx(wfull_bar, W_BYTES);
             bulk_g2s(smem_u32(w_smem), a.w, W_BYTES, wfull_bar);
+            pdl_wait();
             uint32_t phase = 0;
             const uint32_t bytes = (uint32_t)(a.cg_in * units) * 16u;
             const uint4* in = reinterpret_cast<const uint4*>(a.in);
@@ -476,6 +481,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
         if (a.lay.kh3) { const int SW = a.lay.S * a.W; t = row / SW; sl = (row - t * SW) / a.W; f = row - t * SW - sl * a.W; }
         else { const int per = a.lay.T * a.lay.Wq; sl = row / per; t = (row - sl * per) / a.lay.Wq; f = row - sl * per - t * a.lay.Wq; }
         const bool row_ok = row < a.m_valid && f < a.W;                 // (1,3): the pad column computes nothing that is kept
+        pdl_wait();                                                     // the stores below must follow the predecessor grid
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             mbar_wait(tfull_bar(acc), acc_phase);
@@ -560,6 +566,8 @@ struct PoolOut { __half* p[3]; int toff[3]; int out_T; LateLay lay = {0, 0, 0, 0
 __global__ void __launch_bounds__(256) tc_pool_kernel(const __half* in, int64_t in_plane, PoolOut po, int64_t out_plane,
                                                       int n, int t_in, int w_in, int cg, int pt, int pf, int split) {
     __half* const out = po.p[0];
+    pdl_trigger();
+    pdl_wait();                 // dependent launch inside the late chain (no-op otherwise)
     const int t_out = t_in / pt, w_out = w_in / pf;
     const int wp_in = w_in + 1, wp_out = w_out + 1;
     const int64_t per_out = (int64_t)t_out * wp_out;
@@ -667,7 +675,14 @@ int launch_tc_blk(oww_ctx* ctx, const TcBlkArgs& a, cudaStream_t s) {
         ctx->tc_blk_attr_mask |= bit;
     }
     const int grid = ctx->sm_count < a.n_tiles ? ctx->sm_count : a.n_tiles;
-    tc_conv_blk_kernel<CGP, NP><<<grid, kTcThreads, smem, s>>>(a);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = ctx->late_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    OWW_CUDA(ctx, cudaLaunchKernelEx(&cfg, tc_conv_blk_kernel<CGP, NP>, a));
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }
@@ -1053,8 +1068,15 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
             const int64_t total = (int64_t)n * Y.rows_new * (Y.W + 1) * cgo;
             unsigned grid = (unsigned)((total + 255) / 256);
             if (grid > (unsigned)ctx->sm_count * 16) grid = ctx->sm_count * 16;
-            tc_pool_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(ctx->d_late_tmp[0]), tmp_plane, po, Y.plane, n, T_out, W, cgo,
-                                               C.pool_t, C.pool_f, 1);
+            cudaLaunchConfig_t cfg;
+            std::memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = ctx->late_pdl ? 1 : 0;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            OWW_CUDA(ctx, cudaLaunchKernelEx(&cfg, tc_pool_kernel, reinterpret_cast<const __half*>(ctx->d_late_tmp[0]), tmp_plane, po,
+                                             Y.plane, n, T_out, W, cgo, C.pool_t, C.pool_f, 1));
             OWW_LAUNCH_CHECK(ctx);
         }
     }

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) feat16_sync_kernel(const float* __restric
                                                           const int* __restrict__ count, const int* __restrict__ ids, int n,
                                                           int depth, int pos, int NS, int n_tiles, uint8_t* __restrict__ out) {
     const int64_t total = (int64_t)n * 12 * depth;
+    oww_pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int lb = (int)(i % n);
         const int j = (int)((i / n) % 12);
@@ -204,6 +205,8 @@ __global__ void __launch_bounds__(kHgThreads, 1) heads_grp_kernel(const __grid_c
     const int n_it = G.n_in * 3 / cpr;
     long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg + 8 * blockIdx.y : nullptr;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+    pdl_trigger();              // dependent launch chain of a step (tc_common.cuh): barriers and TMEM are set up, now the
+    pdl_wait();                 // predecessor's feature rows are needed
 
     // Everything the loops below need is copied into registers first: `a` lives in constant memory and is addressed with
     // a run-time index (blockIdx.y), and the asm statements around the barriers are memory clobbers, so a G.field inside
@@ -653,8 +656,9 @@ static int hg_sync(oww_ctx* ctx, const int* d_ids, int n, int depth, cudaStream_
     const int64_t total = (int64_t)n * 12 * depth;
     if (total <= 0) return OWW_OK;
     const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
-    feat16_sync_kernel<<<grid, 256, 0, s>>>(ctx->d_feat_ring, (int64_t)ctx->feat_rows * 96, ctx->feat_rows - 1, ctx->d_feat_count,
-                                           d_ids, n, depth, (int)(g->pos % g->NS), g->NS, g->n_tiles, g->d_f16);
+    OWW_CUDA(ctx, oww_launch_pdl(ctx->late_pdl, feat16_sync_kernel, dim3(grid), dim3(256), 0, s, (const float*)ctx->d_feat_ring,
+                                 (int64_t)ctx->feat_rows * 96, ctx->feat_rows - 1, (const int*)ctx->d_feat_count, d_ids, n, depth,
+                                 (int)(g->pos % g->NS), g->NS, g->n_tiles, g->d_f16));
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }
@@ -710,7 +714,7 @@ int oww_heads_grp_launch(oww_ctx* ctx, int back, int n, float* d_out, int out_st
     a.dbg = g->d_dbg;
     a.steps = 0;
     dim3 grid((n + kHgTile - 1) / kHgTile, g->n_groups);
-    heads_grp_kernel<<<grid, kHgThreads, kHgSmem, s>>>(a);
+    OWW_CUDA(ctx, oww_launch_pdl(ctx->late_pdl, heads_grp_kernel, grid, dim3(kHgThreads), kHgSmem, s, a));
     OWW_LAUNCH_CHECK(ctx);
     return OWW_OK;
 }

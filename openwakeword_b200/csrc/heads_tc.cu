@@ -423,6 +423,7 @@ bool oww_heads_tc_supported(const oww_ctx* ctx, int head_id) {
 namespace {
 __global__ void gate_kernel(float* scores, int n, int stride, const Gate* gates, int n_gates) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    oww_pdl_sync();
     if (i >= n * n_gates) return;
     const int s = i / n_gates;
     const Gate g = gates[i - s * n_gates];
@@ -473,7 +474,8 @@ int oww_heads_all(oww_ctx* ctx, const FeatSrc& src, int n, float* d_out, int out
     if (cc_mask && (rc = oww_heads_launch(ctx, -1, src, n, out, stride, 0, comb, s, cc_mask))) return rc;
     if (!ctx->gates.empty()) {
         const int total = n * (int)ctx->gates.size();
-        gate_kernel<<<(total + 255) / 256, 256, 0, s>>>(out, n, stride, ctx->d_gates, (int)ctx->gates.size());
+        OWW_CUDA(ctx, oww_launch_pdl(ctx->late_pdl, gate_kernel, dim3((total + 255) / 256), dim3(256), 0, s, out, n, stride,
+                                     (const Gate*)ctx->d_gates, (int)ctx->gates.size()));
         OWW_LAUNCH_CHECK(ctx);
     }
     if (via_tmp) {

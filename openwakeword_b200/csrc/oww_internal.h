@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 #include "owwb200.h"
 
@@ -180,6 +181,7 @@ struct oww_ctx {
     void* d_late_tmp[1] = {nullptr};             // unpooled output of a late layer that is followed by a pool
     void* d_late_template = nullptr;             // tails of the all-ones window per tails-bearing late tensor: [plane][2][Wp]
     bool late_active = false;
+    bool late_pdl = true;                        // programmatic dependent launches inside the late chain (reserved[0] bit 5 disables)
     bool late_blocked_ok = true;                 // OWW_LATE_PLAIN=1 keeps the window-mode layout for every late tensor (A/B)
     long late_step = 0;                          // chunks processed since the buffers were allocated (buffer rotation)
 
@@ -241,6 +243,25 @@ int oww_fail(oww_ctx* ctx, int code, const char* fmt, ...);
             return oww_fail((ctx), OWW_ECUDA, "%s failed: %s (%s:%d)", #call,                  \
                             cudaGetErrorString(e__), __FILE__, __LINE__);                      \
     } while (0)
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute (the kernel calls pdl_wait() before it touches anything
+// its predecessor in the stream produced; see tc_common.cuh).  pdl == false: an ordinary launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t oww_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void oww_pdl_sync() {        // trigger the successor, then wait for the predecessor: small kernels
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 #define OWW_LAUNCH_CHECK(ctx)                                                                  \
     do {                                                                                       \
         (ctx)->launches++;                                                                     \

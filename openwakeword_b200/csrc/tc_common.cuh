@@ -69,6 +69,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// Programmatic dependent launch (the incremental late chain): a kernel launched with the programmatic-serialization
+// attribute may start while its predecessor in the stream is still running; pdl_wait() returns once the predecessor grid
+// has completed and its writes are visible (no-op for an ordinary launch); pdl_trigger() lets the successor start.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // One lane of a converged warp: code under `if (tc_elect_one())` runs on the uniform datapath (UTCHMMA takes uniform
 // registers; from a plain `if (lane == 0)` region every MMA pays register -> uniform moves: ~160 instead of ~60 cycles).
 __device__ __forceinline__ bool tc_elect_one() {
