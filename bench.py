@@ -39,7 +39,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_WINDOW = 2 * 41955840          # SURVEY.md Appendix B (reference-algorithmic, per 76x32 window)
-EXEC_FLOPS_PER_FRAME = 2 * 5612544       # what the incremental kernel executes per frame
+EXEC_FLOPS_PER_FRAME = 2 * 5612544       # what the incremental path computes per frame with one MMA term per K step
+# multiply-accumulates per frame of the incremental conv layers 0..19 (8 new mel rows; SURVEY.md Appendix B shapes)
+INC_MACS = [6912, 442368, 442368, 221184, 442368, 442368, 442368, 331776, 497664, 497664, 497664,
+            165888, 221184, 221184, 221184, 110592, 110592, 110592, 110592, 27648]
+
+
+def exec_flops_per_frame(split_from):
+    """FLOPs the tensor pipe issues per frame in cnn_mode 3: layers >= split_from take fp16 hi/lo split operands, i.e.
+    three MMA terms per K step (hi*hi + lo*hi + hi*lo)."""
+    s = 11 if not split_from else split_from
+    return 2 * (sum(INC_MACS[:s]) + 3 * sum(INC_MACS[s:]))
 CHUNK = 1280
 METRIC = "80ms audio-frames/sec (concurrent streams)"
 UNIT = "frames/s"
@@ -419,6 +429,39 @@ def measure(args, wl, rank, world, local, dev, sampler_windows, do_model=True):
     return out
 
 
+def measure_variant(args, wl, local, dev, split_from, sampler_windows):
+    """Device-resident step time and oracle parity of the same workload with another split_from."""
+    import torch
+    from openwakeword_b200.engine import StreamEngine
+    B = WORKLOADS[wl]["streams"]
+    K = min(args.steps, 20)
+    heads = bench_heads(wl)
+    POOL = max(4, int(np.ceil(168e6 / (B * CHUNK * 2))))
+    eng = StreamEngine(list(heads.values()), B, embedding="synthetic:0", device_index=local, max_chunks=1, cnn_mode=3, split_from=split_from)
+    host_pcm = synth_pcm_fast(B, POOL, 1234)
+    dev_steps = [torch.from_numpy(np.ascontiguousarray(host_pcm[:, i * CHUNK:(i + 1) * CHUNK])).to(dev) for i in range(POOL)]
+    out = torch.empty((B, eng.n_cols), dtype=torch.float32, device=dev)
+    for k in range(4):
+        eng.step(dev_steps[k % POOL], 1, out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.perf_counter()
+    e0.record()
+    for k in range(K):
+        eng.step(dev_steps[(4 + k) % POOL], 1, out)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler_windows.append((t_a, time.perf_counter()))
+    ms = e0.elapsed_time(e1) / K
+    par = parity_check(eng, heads, B)
+    del eng
+    torch.cuda.empty_cache()
+    return {"split_from": split_from, "value": B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K,
+            "parity_max_abs_delta": par["max_abs_delta"], "parity_ok": par["ok"],
+            "what": ("conv layers >= %d on fp16 hi/lo split operands" % split_from) if split_from < 20 else
+                    "plain fp16 operands in every conv layer: the whole step in one launch"}
+
+
 def run_own_arm(args):
     import torch
     import torch.distributed as dist
@@ -444,6 +487,12 @@ def run_own_arm(args):
     order = [args.workload] + ([w for w in ("c2",) if w != args.workload] if args.secondary else [])
     for wl in order:
         res[wl] = measure(args, wl, rank, world, local, dev, windows, do_model=(wl == args.workload))
+    # other points of the precision / speed curve of cnn_mode 3 (device-resident timing + the same parity gate), 1 GPU only
+    variants = []
+    if args.variants and world == 1 and args.cnn_mode == 3 and not args.split_from:
+        for sf in (15, 20):
+            v = measure_variant(args, args.workload, local, dev, sf, windows)
+            variants.append(v)
     clocks = sampler.stop(windows) if rank == 0 else None
 
     keys = ["ms_dev", "ms_e2e", "cnn_ms", "heads_ms", "mel_ms"]
@@ -473,15 +522,17 @@ def run_own_arm(args):
     main = res[args.workload]
     B = main["B"]
     n_total = B * world
-    exec_flops = EXEC_FLOPS_PER_FRAME if args.cnn_mode == 3 else FLOPS_PER_WINDOW
+    exec_flops = exec_flops_per_frame(args.split_from) if args.cnn_mode == 3 else FLOPS_PER_WINDOW
     cnn_ms = main["cnn_ms"]
     executed_tf = B * exec_flops / (cnn_ms * 1e-3) / 1e12
     achieved_tf = B * FLOPS_PER_WINDOW / (cnn_ms * 1e-3) / 1e12
     timed_s = main["ms_dev"] * 1e-3
     peak_used = pk_burst if timed_s < 1.0 else pk_sus         # burst figure for a short region at full clocks, sustained for a long one
     fused = args.cnn_mode == 3 and not args.no_fuse
-    kernel_name = ("tc_inc_kernel (cnn_tc_inc.cu): log-mel frontend + 20-layer tcgen05 CNN + ring append of every stream in ONE launch"
-                   + (" (+ heads inside the launch)" if main["heads_ms"] == 0.0 else "; heads_tc_kernel follows as a second launch")
+    sf = args.split_from or 11
+    kernel_name = ((f"tc_inc_kernel<{sf}> (cnn_tc_inc.cu): log-mel frontend + conv layers 0..{sf - 1} of every stream on tcgen05 in ONE persistent launch"
+                    + (f"; layers {sf}..19 follow as tc_conv_blk_kernel launches on fp16 hi/lo split operands (3 MMA terms), then heads_grp_kernel"
+                       if sf < 20 else " + ring append" + (" + heads" if main["heads_ms"] == 0.0 else "; heads_grp_kernel follows")))
                    if fused else "embedding CNN stage (separate launches)")
 
     cpu = None
@@ -512,7 +563,7 @@ def run_own_arm(args):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload]["label"],
                    "streams_per_gpu": B, "heads": main["heads"], "score_columns": main["n_cols"], "cnn_mode": args.cnn_mode,
-                   "split_from": args.split_from,
+                   "split_from": args.split_from or 11,
                    "fused_step": bool(fused),
                    "l2": "inputs larger than L2: distinct PCM batches totalling >= 168 MB cycled",
                    "weights": "synthetic seed 0 (reference shapes); released .onnx weights absent",
@@ -533,10 +584,13 @@ def run_own_arm(args):
                      "traffic": None,
                      "flops_per_unit": FLOPS_PER_WINDOW, "executed_flops_per_unit": exec_flops, "units_per_launch": B,
                      "kernel_ms": cnn_ms, "stage_ms": {"mel": main["mel_ms"], "cnn": main["cnn_ms"], "heads": main["heads_ms"]},
-                     "note": "executed_* = FLOPs the tensor pipe actually issued (the incremental kernel computes only the 8 new mel rows "
-                             "per frame, 11.2 MFLOP, SURVEY.md F10/8d); achieved/frac = reference-algorithmic 83.9 MFLOP per frame "
-                             "delivered per second.  kernel_ms is the fused launch (frontend + CNN + append), CUDA events inside the "
-                             "timed region; ncu summaries of the same command: profiles/"},
+                     "note": "executed_* = FLOPs the tensor pipe actually issued (the incremental path computes only the 8 new mel rows "
+                             "per frame: 11.2 MFLOP with one MMA term per K step, 16.4 MFLOP with the default three-term split operands "
+                             "from layer 11 on; SURVEY.md F10/8d); achieved/frac = reference-algorithmic 83.9 MFLOP per frame delivered per "
+                             "second.  kernel_ms is the CNN stage (frontend + conv layers + ring append), CUDA events inside the timed region. "
+                             "Why the fraction is low by construction: N = Cout is 24..96 and an M128 x N x K16 tcgen05.mma costs ~60-75 cycles "
+                             "for every N <= 128 (scripts/micro/mma_layout.cu, profiles/r2_mma_layout.txt) - at N = 96 the pipe's ceiling is "
+                             "~40 % of its N = 256 rate, and layers 0-2 (N = 24) ~10 %; ncu summaries of the same command: profiles/"},
         "cpu_baseline": cpu,
     }
     if "ms_model" in main:
@@ -546,6 +600,8 @@ def run_own_arm(args):
                                     "D2H, label mapping, first-5 zeroing, history)"}
     if len(order) > 1:
         line["secondary"] = {w: summary(res[w], w) for w in order[1:]}
+    if variants:
+        line["variants"] = variants
     ok = par.get("ok", True) and all((res[w].get("parity") or {}).get("ok", True) for w in order)
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -573,7 +629,9 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="mode 3: keep mel / CNN / append / heads as separate launches (stage breakdown)")
     ap.add_argument("--no-tc-heads", action="store_true", help="heads on CUDA cores (heads.cu)")
     ap.add_argument("--tc-heads-terms", type=int, default=3, choices=[1, 3])
-    ap.add_argument("--split-from", type=int, default=11,
+    ap.add_argument("--no-variants", dest="variants", action="store_false",
+                    help="skip the split_from 15 / 20 variants of the headline workload (N=1, default split only)")
+    ap.add_argument("--split-from", type=int, default=0,
                     help="first conv layer on fp16 hi/lo split operands (11 = default, scores within ~2e-4 of the fp32 graph; "
                          "20 = plain fp16 everywhere and the whole step as one fused launch, ~9e-4)")
     args = ap.parse_args()

@@ -16,5 +16,7 @@ for f in sys.argv[1:]:
     for k, v in (d.get("secondary") or {}).items():
         print("  secondary %s: %.3f M f/s  ms/step %.4f e2e %.3f M parity %.3e stage %s" % (k, v["value"] / 1e6, v["ms_per_step"], v["e2e"] / 1e6,
               v["parity"]["max_abs_delta"], {a: round(b, 4) for a, b in v["stage_ms"].items()}))
+    for v in d.get("variants") or []:
+        print("  variant split_from %d: %.3f M f/s  ms/step %.4f  parity %.3e" % (v["split_from"], v["value"] / 1e6, v["ms_per_step"], v["parity_max_abs_delta"]))
     if d.get("cpu_baseline"):
         print("  cpu", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"], d["cpu_baseline"]["kind"])
