@@ -33,6 +33,9 @@ constexpr int kIncAcc = 4;                                // TMEM accumulator st
 constexpr int kIncMaxG = 7;
 constexpr int kMelNF = 2;                                  // frames a warp of the fused frontend processes at once
 
+__device__ __forceinline__ __half2 u32_as_half2(uint32_t v) {
+    return __halves2half2(__ushort_as_half((unsigned short)(v & 0xFFFFu)), __ushort_as_half((unsigned short)(v >> 16)));
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -209,6 +212,12 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 const uint32_t b_lo0 = (uint32_t)make_desc(0, (uint32_t)L.np * 16u, 128u);
                 const uint32_t a_unit0 = (a_base >> 4) + 1u;
                 const uint32_t b_unit0 = w_addr >> 4;
+                // per-layer geometry in registers: inside the tile loop every L.field would be an indexed constant load
+                // again (P.L[l] with a run-time l, and the barrier asm statements are memory clobbers) - five dependent
+                // LDCUs per tile ahead of the first MMA
+                const uint32_t tap0 = (uint32_t)L.tap[0], tap1 = (uint32_t)L.tap[1], tap2 = (uint32_t)L.tap[2];
+                const uint32_t pitch2 = 2u * (uint32_t)L.in_pitch, np2 = 2u * (uint32_t)L.np, tap_w = (uint32_t)(L.cgp * L.np);
+                const int n_pair = L.cg_in / 2;                   // K steps whose second plane exists
                 for (int tile = 0; tile < n_tiles; ++tile) {
                     mbar_wait(tempty(acc), acc_par ^ 1);
                     tc_fence_after();
@@ -216,14 +225,14 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     // one elect.sync per tile: the elected lane issues the tile's MMAs and the commit back to back
                     if (elect_one()) {
                         uint32_t accumulate = 0;
+                        const uint32_t a_t0 = a_unit0 + (uint32_t)(tile * 128);
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
-                            const uint32_t a_tap = a_unit0 + (uint32_t)(tile * 128 + L.tap[j]);
-                            const uint32_t b_tap = b_unit0 + (uint32_t)(j * L.cgp * L.np);
+                            const uint32_t a_tap = a_t0 + (j == 0 ? tap0 : j == 1 ? tap1 : tap2);
+                            const uint32_t b_tap = b_unit0 + (uint32_t)j * tap_w;
                             for (int q = 0; q < nq; ++q) {
-                                const uint32_t alo = ((2 * q + 1 < L.cg_in) ? a_hi_pair : a_hi_self) |
-                                                     ((a_tap + (uint32_t)(2 * q * L.in_pitch)) & 0x3FFFu);
-                                const uint32_t blo = b_lo0 | ((b_tap + (uint32_t)(2 * q * L.np)) & 0x3FFFu);
+                                const uint32_t alo = (q < n_pair ? a_hi_pair : a_hi_self) | ((a_tap + (uint32_t)q * pitch2) & 0x3FFFu);
+                                const uint32_t blo = b_lo0 | ((b_tap + (uint32_t)q * np2) & 0x3FFFu);
                                 tc_mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | alo, ((uint64_t)desc_hi << 32) | blo, idesc, accumulate);
                                 accumulate = 1;
                             }
@@ -544,23 +553,27 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                                 // pool on (hi, lo) pairs: the element with the largest hi + lo = lexicographic maximum
                                 uint4 res_lo = make_uint4(0, 0, 0, 0);
                                 if (f < L.nx_W) {
-                                    __half mh[8], ml[8];
+                                    // two channels per 32-bit word; mask arithmetic keeps everything in registers
+                                    uint32_t bh[4] = {0, 0, 0, 0}, bl[4] = {0, 0, 0, 0};
                                     bool first = true;
                                     for (int da = 0; da < L.pool_t; ++da)
                                         for (int db = 0; db < L.pool_f; ++db) {
                                             const int at = 1 + ((t * L.pool_t + da) * G + g) * L.Wp + f * L.pool_f + db;
                                             const uint4 q = src[pl * L.tmp_pitch + at], ql = src[(L.cg_out + pl) * L.tmp_pitch + at];
-                                            const __half* hv = reinterpret_cast<const __half*>(&q);
-                                            const __half* lv = reinterpret_cast<const __half*>(&ql);
+                                            const uint32_t qh[4] = {q.x, q.y, q.z, q.w}, qq[4] = {ql.x, ql.y, ql.z, ql.w};
 #pragma unroll
-                                            for (int u = 0; u < 8; ++u) {
-                                                const bool take = first || __hgt(hv[u], mh[u]) || (__heq(hv[u], mh[u]) && __hgt(lv[u], ml[u]));
-                                                if (take) { mh[u] = hv[u]; ml[u] = lv[u]; }
+                                            for (int u = 0; u < 4; ++u) {
+                                                const __half2 h2 = u32_as_half2(qh[u]), l2 = u32_as_half2(qq[u]);
+                                                const __half2 b2 = u32_as_half2(bh[u]), c2 = u32_as_half2(bl[u]);
+                                                const uint32_t m = first ? 0xFFFFFFFFu
+                                                                         : (__hgt2_mask(h2, b2) | (__heq2_mask(h2, b2) & __hgt2_mask(l2, c2)));
+                                                bh[u] = (qh[u] & m) | (bh[u] & ~m);
+                                                bl[u] = (qq[u] & m) | (bl[u] & ~m);
                                             }
                                             first = false;
                                         }
-                                    res = *reinterpret_cast<uint4*>(mh);
-                                    res_lo = *reinterpret_cast<uint4*>(ml);
+                                    res = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+                                    res_lo = make_uint4(bl[0], bl[1], bl[2], bl[3]);
                                 }
                                 if (s_live[g]) {
                                     const int64_t q = kGuard + ((int64_t)(grp * G + g) * T2 + t) * L.nx_Wp + f;
