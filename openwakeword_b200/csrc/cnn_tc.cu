@@ -211,6 +211,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
                 if (tc_elect_one()) {
                     uint32_t accumulate = 0;
+                    if (TERMS == 1 && (a.cg_in & 1)) {
+                        // odd plane count, plain operands: the K octets of the three taps are chained exactly as in the fused
+                        // step kernel (cnn_tc_inc.cu: the last plane of tap 0 shares an MMA with the first plane of tap 1),
+                        // with the weights packed in that order - one MMA per tile less, and the same accumulation order
+                        // as the streaming path (bulk == streaming, bit for bit)
+                        constexpr int CG = CGP - 1, NPAIR = CG / 2;
+                        uint32_t b = w_addr;
+                        constexpr uint32_t np2 = 2u * NP * 16u;
+                        auto mma = [&](uint32_t a_at, uint32_t lbo) {
+                            tc_mma_f16(d_tmem, make_desc(a_at, lbo, 128u), make_desc(b, NP * 16u, 128u), idesc, accumulate);
+                            accumulate = 1; b += np2;
+                        };
+#pragma unroll
+                        for (int k = 0; k < NPAIR; ++k) mma(a_addr + tap16[0] + (uint32_t)(2 * k) * rows16, lbo_a);
+                        mma(a_addr + tap16[1], (uint32_t)CG * rows16 - rows16 + tap16[0] - tap16[1]);
+#pragma unroll
+                        for (int k = 0; k < NPAIR; ++k) mma(a_addr + tap16[1] + (uint32_t)(2 * k + 1) * rows16, lbo_a);
+#pragma unroll
+                        for (int k = 0; k < NPAIR; ++k) mma(a_addr + tap16[2] + (uint32_t)(2 * k) * rows16, lbo_a);
+                        mma(a_addr + tap16[2] + (uint32_t)(CG - 1) * rows16, 0u);
+                    } else {
                     // term order: every K step with the hi activations ((hi,hi), (hi,lo)), then every K step with the lo
                     // activations ((lo,hi)) - the order tc_conv_blk_kernel is bound to (it holds one half at a time), so the
                     // window / clip passes and the incremental late layers accumulate identically (bulk == streaming, bit for bit)
@@ -231,6 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(TcConvArgs a) {
                                 }
                             }
                         }
+                    }
                     }
                     tc_commit(empty_bar(stage));
                     tc_commit(tfull_bar(acc));
@@ -717,6 +739,7 @@ int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob) {
         if (amax > 0.f && std::isfinite(amax)) { int e; std::frexp(amax, &e); sexp = 14 - e; if (sexp > 24) sexp = 24; if (sexp < -8) sexp = -8; }
         const float up = std::ldexp(1.0f, sexp), down = std::ldexp(1.0f, -sexp);
         const size_t term = (size_t)3 * cgp * np * 8;
+        std::fill(hw.begin() + oh, hw.begin() + oh + term, __float2half(0.f));     // pad octets of the chained order stay zero
         for (int j = 0; j < 3; ++j)
             for (int g = 0; g < cgp; ++g)
                 for (int n = 0; n < np; ++n)
@@ -724,7 +747,10 @@ int oww_tc_pack_weights(oww_ctx* ctx, const float* h_blob) {
                         const int c = g * 8 + e;
                         const float v = (c < L.cin && n < L.cout) ? w[((size_t)j * L.cin + c) * L.cout + n] : 0.f;
                         const size_t at = (((size_t)j * cgp + g) * np + n) * 8 + e;
-                        hw[oh + at] = __float2half_rn(v);
+                        // plain weights of a layer with an odd plane count: chained octet order (tc_conv_kernel, TERMS = 1)
+                        int oc = j * cgp + g;
+                        if ((cg & 1) && g < cg) oc = j == 0 ? (g < cg - 1 ? g : cg) : j == 1 ? (g == 0 ? cg - 1 : cg + g) : 2 * cg + g;
+                        if (!(cg & 1) || g < cg) hw[oh + ((size_t)oc * np + n) * 8 + e] = __float2half_rn(v);
                         const __half hi = __float2half_rn(v * up);
                         hw3[2 * oh + at] = hi;
                         hw3[2 * oh + term + at] = __float2half_rn(v * up - __half2float(hi));

@@ -218,14 +218,45 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 const uint32_t tap0 = (uint32_t)L.tap[0], tap1 = (uint32_t)L.tap[1], tap2 = (uint32_t)L.tap[2];
                 const uint32_t pitch2 = 2u * (uint32_t)L.in_pitch, np2 = 2u * (uint32_t)L.np, tap_w = (uint32_t)(L.cgp * L.np);
                 const int n_pair = L.cg_in / 2;                   // K steps whose second plane exists
+                // Odd plane count (24 or 72 channels): instead of padding every tap to an even number of planes (one
+                // half-empty MMA per tap), the K octets of the three taps are chained - the last plane of tap 0 shares an
+                // MMA with the first plane of tap 1 (the LBO field is just the distance of the two octets, whatever tap they
+                // belong to): (3 cg + 1) / 2 MMAs per tile instead of 3 (cg + 1) / 2 (5 instead of 6 at 24 channels).  The
+                // weights of such a layer are packed in the same octet order (oww_inc_setup).
+                const bool chained = (L.cg_in & 1) != 0;
+                const uint32_t a_cross = (uint32_t)make_desc(0, ((uint32_t)(L.cg_in - 1) * (uint32_t)L.in_pitch + tap0 - tap1) * 16u, 128u);
+                const uint32_t last_plane = (uint32_t)(L.cg_in - 1) * (uint32_t)L.in_pitch;
                 for (int tile = 0; tile < n_tiles; ++tile) {
                     mbar_wait(tempty(acc), acc_par ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * 128u;
                     // one elect.sync per tile: the elected lane issues the tile's MMAs and the commit back to back
                     if (elect_one()) {
-                        uint32_t accumulate = 0;
                         const uint32_t a_t0 = a_unit0 + (uint32_t)(tile * 128);
+                        const uint64_t dhi = (uint64_t)desc_hi << 32;
+                        if (chained) {
+                            uint32_t b = b_unit0;
+                            uint32_t accumulate = 0;
+                            for (int k = 0; k < n_pair; ++k) {            // tap 0: planes (0,1) (2,3) ...
+                                tc_mma_f16(d_tmem, dhi | a_hi_pair | ((a_t0 + tap0 + (uint32_t)k * pitch2) & 0x3FFFu), dhi | b_lo0 | (b & 0x3FFFu), idesc, accumulate);
+                                accumulate = 1; b += np2;
+                            }
+                            // (tap 1, plane 0) + (tap 0, last plane): the lower address first
+                            tc_mma_f16(d_tmem, dhi | a_cross | ((a_t0 + tap1) & 0x3FFFu), dhi | b_lo0 | (b & 0x3FFFu), idesc, accumulate);
+                            b += np2;
+                            for (int k = 0; k < n_pair; ++k) {            // tap 1: planes (1,2) (3,4) ...
+                                tc_mma_f16(d_tmem, dhi | a_hi_pair | ((a_t0 + tap1 + (uint32_t)L.in_pitch + (uint32_t)k * pitch2) & 0x3FFFu),
+                                           dhi | b_lo0 | (b & 0x3FFFu), idesc, 1u);
+                                b += np2;
+                            }
+                            for (int k = 0; k < n_pair; ++k) {            // tap 2: planes (0,1) (2,3) ...
+                                tc_mma_f16(d_tmem, dhi | a_hi_pair | ((a_t0 + tap2 + (uint32_t)k * pitch2) & 0x3FFFu), dhi | b_lo0 | (b & 0x3FFFu), idesc, 1u);
+                                b += np2;
+                            }
+                            // tap 2, last plane, paired with itself against a zero weight octet
+                            tc_mma_f16(d_tmem, dhi | a_hi_self | ((a_t0 + tap2 + last_plane) & 0x3FFFu), dhi | b_lo0 | (b & 0x3FFFu), idesc, 1u);
+                        } else {
+                        uint32_t accumulate = 0;
 #pragma unroll
                         for (int j = 0; j < 3; ++j) {
                             const uint32_t a_tap = a_t0 + (j == 0 ? tap0 : j == 1 ? tap1 : tap2);
@@ -233,9 +264,10 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                             for (int q = 0; q < nq; ++q) {
                                 const uint32_t alo = (q < n_pair ? a_hi_pair : a_hi_self) | ((a_tap + (uint32_t)q * pitch2) & 0x3FFFu);
                                 const uint32_t blo = b_lo0 | ((b_tap + (uint32_t)q * np2) & 0x3FFFu);
-                                tc_mma_f16(d_tmem, ((uint64_t)desc_hi << 32) | alo, ((uint64_t)desc_hi << 32) | blo, idesc, accumulate);
+                                tc_mma_f16(d_tmem, dhi | alo, dhi | blo, idesc, accumulate);
                                 accumulate = 1;
                             }
+                        }
                         }
                         tc_commit(tfull(acc));
                     }
@@ -978,13 +1010,23 @@ int oww_inc_setup(oww_ctx* ctx, const float* h_blob) {
         if (li == 0) continue;
         const IncLayer& L = P.L[li];
         __half* hw = reinterpret_cast<__half*>(blob.data() + L.w_off);
+        // octet (tap j, plane g) -> position in the packed block [octet][np][8].  Even plane count: tap-major with the
+        // pad plane zero.  Odd plane count: the chained order of the MMA loop in tc_inc_kernel -
+        //   t0p0 .. t0p(cg-2) | t1p0, t0p(cg-1) | t1p1 .. t1p(cg-1) | t2p0 .. t2p(cg-2) | t2p(cg-1), zero
+        const int cg = L.cg_in;
+        auto octet_at = [&](int j, int g) {
+            if (!(cg & 1)) return j * L.cgp + g;
+            if (j == 0) return g < cg - 1 ? g : cg;
+            if (j == 1) return g == 0 ? cg - 1 : cg + g;
+            return 2 * cg + g;
+        };
         for (int j = 0; j < 3; ++j)
-            for (int g = 0; g < L.cgp; ++g)
+            for (int g = 0; g < cg; ++g)
                 for (int n = 0; n < L.np; ++n)
                     for (int e = 0; e < 8; ++e) {
                         const int c = g * 8 + e;
                         const float v = (c < C.cin && n < C.cout) ? w[((size_t)j * C.cin + c) * C.cout + n] : 0.f;
-                        hw[(((size_t)j * L.cgp + g) * L.np + n) * 8 + e] = __float2half_rn(v);
+                        hw[(((size_t)octet_at(j, g)) * L.np + n) * 8 + e] = __float2half_rn(v);
                     }
         float* sb = reinterpret_cast<float*>(blob.data() + L.w_off + (size_t)3 * L.cgp * L.np * 16);
         for (int n = 0; n < L.np; ++n) { sb[n] = n < C.cout ? sc[n] : 0.f; sb[L.np + n] = n < C.cout ? bi[n] : 0.f; }
