@@ -332,12 +332,14 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                         if (b >= a.B) b = grp * G;
                         tl[i] = a.tail + (int64_t)b * OWW_TAIL; bd[i] = a.pcm + (int64_t)b * a.pcm_stride; fr[i] = fj & 7;
                     }
-                    mel_frames_db<kMelNF>(tl, OWW_TAIL, bd, fr, s_work, s_tw, s_win, a.mel_kmax, my_start, my_len, my_w, lane, db);
+                    long long* st = (a.dbg_clock && blockIdx.x == 0 && grp == 0 && warp == 0 && fi == 0) ? a.dbg_clock + 92 : nullptr;
+                    mel_frames_db<kMelNF>(tl, OWW_TAIL, bd, fr, s_work, s_tw, s_win, a.mel_kmax, my_start, my_len, my_w, lane, db, st);
 #pragma unroll
                     for (int i = 0; i < kMelNF; ++i)
                         if (fi + i < G * 8) s_mel[(fi + i) * 32 + lane] = db[i];
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
+                if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[97] = clock64();
                 if (warp < G) {                                    // per-call (= per stream, this step) maximum -> -80 dB floor
                     float m = -INFINITY;
                     const int j0 = s_live[8 + warp] ? 3 : 0;       // a fresh stream's call holds frames 3..7 only
@@ -358,9 +360,33 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     if (s_live[g] && fr >= skip)
                         a.mel_rw[(int64_t)b * a.mel_stride + (int64_t)((s_cnt[g] + fr - skip) & a.mel_mask) * 32 + (i & 31)] = v;
                 }
-                for (int i = et; i < G * OWW_TAIL; i += kIncEpiWarps * 32) {
-                    const int g = i / OWW_TAIL, k = i - g * OWW_TAIL, b = grp * G + g;
-                    if (s_live[g]) a.tail[(int64_t)b * OWW_TAIL + k] = __ldg(a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + k);
+                {   // the streams' new tails = the last 480 samples of this chunk: 32-bit words, all loads of a thread in flight at once
+                    constexpr int kTW = OWW_TAIL / 2;                                  // words per stream
+                    const bool al = ((size_t)a.pcm & 3) == 0 && (a.pcm_stride & 1) == 0;
+                    uint32_t tv[4]; int ti[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = et + u * kIncEpiWarps * 32;
+                        ti[u] = -1; tv[u] = 0;
+                        if (i < G * kTW) {
+                            const int g = i / kTW, k = i - g * kTW, b = grp * G + g;
+                            if (s_live[g]) {
+                                const int16_t* src = a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + 2 * k;
+                                tv[u] = al ? __ldg(reinterpret_cast<const uint32_t*>(src))
+                                           : ((uint32_t)(unsigned short)__ldg(src) | ((uint32_t)(unsigned short)__ldg(src + 1) << 16));
+                                ti[u] = b * kTW + k;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (ti[u] >= 0) reinterpret_cast<uint32_t*>(a.tail)[ti[u]] = tv[u];
+                    static_assert(kIncMaxG * kTW <= 4 * kIncEpiWarps * 32, "tail copy: four words per thread cover a group");
+                }
+                // the next group's PCM (first touch: HBM) -> L2 while this group's layers run
+                if (grp + (int)gridDim.x < P.n_groups && et < G * 20) {
+                    const int g = et / 20, ln = et - g * 20, b = (grp + (int)gridDim.x) * G + g;
+                    if (b < a.B) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(a.pcm + (int64_t)b * a.pcm_stride) + ln * 128));
                 }
                 if (et < G && s_live[et]) {
                     const int b = grp * G + et;

@@ -108,28 +108,52 @@ constexpr int kMelFrameScratch = 2048 + 2048 + 1280;
 template <int NF>
 __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int prefix, const int16_t* const* body, const int* f,
                                               uint8_t* bufs, const float2* s_tw, const float* s_win, int kmax, int my_start,
-                                              int my_len, const float* my_w, int lane, float* db) {
+                                              int my_len, const float* my_w, int lane, float* db, long long* stamps = nullptr) {
     float2* a[NF]; float2* b[NF]; float* pw[NF];
+    if (stamps && lane == 0) stamps[0] = clock64();
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
         a[i] = reinterpret_cast<float2*>(bufs + i * kMelFrameScratch);
         b[i] = a[i] + 256;
         pw[i] = reinterpret_cast<float*>(b[i] + 256);
     }
+    // sample pairs (x[2n], x[2n+1]) never straddle the tail / body boundary (s0 and prefix are even), so each pair is one
+    // 32-bit load when the clip is 4-byte aligned (it is for every contiguous int16 batch); all 8 x NF loads are in flight
+    // before the first use
+    bool al[NF];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) al[i] = (((size_t)body[i] | (size_t)tail[i]) & 3) == 0 && (prefix & 1) == 0;
+    uint32_t raw[8][NF];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int n = lane + 32 * j;
 #pragma unroll
         for (int i = 0; i < NF; ++i) {
             const int s0 = f[i] * OWW_HOP + 2 * n;
-            float x0, x1;
-            if (s0 + 1 < prefix) { x0 = (float)tail[i][s0]; x1 = (float)tail[i][s0 + 1]; }
-            else if (s0 >= prefix) { x0 = (float)__ldg(body[i] + (s0 - prefix)); x1 = (float)__ldg(body[i] + (s0 + 1 - prefix)); }
-            else { x0 = (float)tail[i][s0]; x1 = (float)__ldg(body[i]); }
-            a[i][fswz(n)] = make_float2(__fmul_rn(x0, s_win[2 * n]), __fmul_rn(x1, s_win[2 * n + 1]));
+            if (al[i]) {
+                raw[j][i] = s0 + 1 < prefix ? *reinterpret_cast<const uint32_t*>(tail[i] + s0)
+                                            : __ldg(reinterpret_cast<const uint32_t*>(body[i] + (s0 - prefix)));
+            } else {
+                unsigned short u0, u1;
+                if (s0 + 1 < prefix) { u0 = (unsigned short)tail[i][s0]; u1 = (unsigned short)tail[i][s0 + 1]; }
+                else if (s0 >= prefix) { u0 = (unsigned short)__ldg(body[i] + (s0 - prefix)); u1 = (unsigned short)__ldg(body[i] + (s0 + 1 - prefix)); }
+                else { u0 = (unsigned short)tail[i][s0]; u1 = (unsigned short)__ldg(body[i]); }
+                raw[j][i] = (uint32_t)u0 | ((uint32_t)u1 << 16);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = lane + 32 * j;
+        const float2 wn = *reinterpret_cast<const float2*>(s_win + 2 * n);
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            const float x0 = (float)(short)(raw[j][i] & 0xFFFFu), x1 = (float)(short)(raw[j][i] >> 16);
+            a[i][fswz(n)] = make_float2(__fmul_rn(x0, wn.x), __fmul_rn(x1, wn.y));
         }
     }
     __syncwarp();
+    if (stamps && lane == 0) stamps[1] = clock64();
 #pragma unroll
     for (int Ns = 1; Ns < 256; Ns *= 4) {
         const int tstep = 128 / Ns;
@@ -160,6 +184,7 @@ __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int pr
 #pragma unroll
         for (int i = 0; i < NF; ++i) { float2* t = a[i]; a[i] = b[i]; b[i] = t; }
     }
+    if (stamps && lane == 0) stamps[2] = clock64();
     for (int k = lane; k < kmax; k += 32) {
 #pragma unroll
         for (int i = 0; i < NF; ++i) {
@@ -181,17 +206,25 @@ __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int pr
         }
     }
     __syncwarp();
+    if (stamps && lane == 0) stamps[3] = clock64();
     float acc[NF];
 #pragma unroll
     for (int i = 0; i < NF; ++i) acc[i] = 0.f;
-    for (int q = 0; q < my_len; ++q) {
-        const float w = my_w[q];
+    // four filter taps per trip: one 16-byte weight load (rows of the table are 128 bytes), the FMA order stays q = 0, 1, 2 ...
+    for (int q = 0; q < my_len; q += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(my_w + q));
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int i = 0; i < NF; ++i) acc[i] = fmaf(pw[i][my_start + q], w, acc[i]);
+        for (int e = 0; e < 4; ++e)
+            if (q + e < my_len) {
+#pragma unroll
+                for (int i = 0; i < NF; ++i) acc[i] = fmaf(pw[i][my_start + q + e], w[e], acc[i]);
+            }
     }
 #pragma unroll
     for (int i = 0; i < NF; ++i) db[i] = 10.0f * logf(fmaxf(acc[i], 1e-10f)) / logf(10.0f);
     __syncwarp();
+    if (stamps && lane == 0) stamps[4] = clock64();
 }
 
 }  // namespace

@@ -22,3 +22,6 @@ for rep in range(2):
     print("  mma issue    :", c[41:41 + NL].tolist())
     print("  to last store:", c[81:81 + NL].tolist())
     print("  frontend:", int(c[0] - c[101]), " heads:", int(c[102] - c[20]) if c[102] else None)
+    if c[92]:
+        print("  frontend detail (warp 0, first frame pair): start +%d | load+window %d | FFT %d | unpack %d | mel+log %d ; all frames done +%d ; floor/affine/ring/tail %d" % (
+            c[92] - c[101], c[93] - c[92], c[94] - c[93], c[95] - c[94], c[96] - c[95], c[97] - c[101], c[0] - c[97]))
