@@ -157,27 +157,33 @@ __device__ __forceinline__ void mel_frames_db(const int16_t* const* tail, int pr
 #pragma unroll
     for (int Ns = 1; Ns < 256; Ns *= 4) {
         const int tstep = 128 / Ns;
+        // k = j & (Ns - 1) does not depend on jj while Ns <= 32: one set of twiddles per pass; in the first pass they are 1
+        // (cmul by (1, 0) returns its argument bit for bit, so skipping it changes nothing)
+        float2 t1 = make_float2(1.f, 0.f), t2 = t1, t3 = t1;
+        if (Ns > 1 && Ns <= 32) { const int k = lane & (Ns - 1); t1 = s_tw[k * tstep]; t2 = s_tw[2 * k * tstep]; t3 = s_tw[3 * k * tstep]; }
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
             const int j = lane + 32 * jj;
             const int k = j & (Ns - 1);
-            const float2 t1 = s_tw[k * tstep], t2 = s_tw[2 * k * tstep], t3 = s_tw[3 * k * tstep];
+            if (Ns > 32) { t1 = s_tw[k * tstep]; t2 = s_tw[2 * k * tstep]; t3 = s_tw[3 * k * tstep]; }
             const int dst = (j / Ns) * Ns * 4 + k;
+            // the swizzle only touches bits 0..3 and reads bits 4..5: adding multiples of 64 commutes with it
+            const int sj = fswz(j);
+            const int d0 = fswz(dst), d1 = fswz(dst + Ns), d2 = fswz(dst + 2 * Ns), d3 = fswz(dst + 3 * Ns);
 #pragma unroll
             for (int i = 0; i < NF; ++i) {
-                float2 v0 = a[i][fswz(j)];
-                float2 v1 = cmul(a[i][fswz(j + 64)], t1);
-                float2 v2 = cmul(a[i][fswz(j + 128)], t2);
-                float2 v3 = cmul(a[i][fswz(j + 192)], t3);
+                const float2 v0 = a[i][sj];
+                float2 v1 = a[i][sj + 64], v2 = a[i][sj + 128], v3 = a[i][sj + 192];
+                if (Ns > 1) { v1 = cmul(v1, t1); v2 = cmul(v2, t2); v3 = cmul(v3, t3); }
                 float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y);
                 float2 a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
                 float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
                 float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
                 float2 a3 = make_float2(d.y, -d.x);
-                b[i][fswz(dst)] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                b[i][fswz(dst + Ns)] = make_float2(a1.x + a3.x, a1.y + a3.y);
-                b[i][fswz(dst + 2 * Ns)] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                b[i][fswz(dst + 3 * Ns)] = make_float2(a1.x - a3.x, a1.y - a3.y);
+                b[i][d0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+                b[i][d1] = make_float2(a1.x + a3.x, a1.y + a3.y);
+                b[i][d2] = make_float2(a0.x - a2.x, a0.y - a2.y);
+                b[i][d3] = make_float2(a1.x - a3.x, a1.y - a3.y);
             }
         }
         __syncwarp();
