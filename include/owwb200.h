@@ -224,8 +224,9 @@ int oww_peer_alloc(oww_ctx* ctx, size_t bytes, void** d_ptr, unsigned char handl
 int oww_peer_free(oww_ctx* ctx, void* d_ptr);
 int oww_peer_open(oww_ctx* ctx, const unsigned char handle[64], void** d_ptr);
 int oww_peer_close(oww_ctx* ctx, void* d_ptr);
-/* stream-ordered block copy into (or out of) a peer mapping: one DMA over NVLink instead of the kernels' scattered
- * 4-byte stores - the way openwakeword_b200.distributed moves a rank's [rows x columns] score block */
+/* stream-ordered block copy into (or out of) a peer mapping (4-byte words, a copy kernel with coalesced 16-byte stores:
+ * full lines over NVLink instead of the step kernels' scattered 4-byte stores) - the way
+ * openwakeword_b200.distributed moves a rank's [rows x columns] score block */
 int oww_peer_copy(oww_ctx* ctx, void* d_dst, const void* d_src, size_t bytes, void* stream);
 int oww_peer_signal(oww_ctx* ctx, uint64_t* d_flag, uint64_t value, void* stream);
 int oww_peer_wait(oww_ctx* ctx, const uint64_t* d_flags, int n, int stride, uint64_t value, double timeout_s, void* stream);
