@@ -378,6 +378,7 @@ struct TcBlkArgs {
     const __half* w; const float* scale; const float* bias;
     int n, W, rows_new;                     // streams, real width, output rows per stream
     int m_valid, tap;                       // accumulator rows that are positions of the block; unit distance of the taps
+    int pool_f;                             // 2: (1,2) max-pool fused into the epilogue (columns f, f^1 sit in adjacent lanes); 0: none
     int cg_in, cg_out, apply_act, n_tiles;
     float* out_f32;                         // final layer: [n][rows_new][96]
     __half* out[3]; int out_toff[3];        // destination buffers (this step / later steps' tails) and their row offsets
@@ -519,9 +520,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
             if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
 
             const int n = tile * a.lay.S + sl;
-            if (!row_ok || n >= a.n) continue;
+            const bool live = row_ok && n < a.n;
             if (a.out_f32) {
-                if (f != 0) continue;
+                if (!live || f != 0) continue;
                 float* o = a.out_f32 + ((int64_t)n * a.rows_new + t) * 96;
 #pragma unroll
                 for (int k = 0; k < PH; ++k) {
@@ -541,17 +542,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
                 }
                 continue;
             }
-            // unit of this position in the destination(s), plane 0
+            // unit of this position in the destination(s), plane 0.  Fused (1,2) pool: columns f and f^1 are adjacent
+            // accumulator rows = adjacent lanes; the even lane writes the maximum to column f/2.  The maximum of the fp32
+            // values, split afterwards, is the element the lexicographic (hi, lo) maximum of the separate pool pass picks.
+            const bool pooled = a.pool_f == 2;
+            const bool writer = live && (!pooled || (f & 1) == 0);
+            const int fo = pooled ? f >> 1 : f;
             int64_t dst[3];
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk)
-                dst[kk] = a.out_lay.S ? late_unit(a.out_lay, 0, n, t + a.out_toff[kk], f)
-                                      : kGuard + ((int64_t)n * a.rows_new + t) * (a.W + 1) + f;
+                dst[kk] = a.out_lay.S ? late_unit(a.out_lay, 0, live ? n : 0, t + a.out_toff[kk], fo)
+                                      : kGuard + ((int64_t)(live ? n : 0) * a.rows_new + t) * (a.W + 1) + f;
             const int64_t pstride = a.out_lay.S ? (int64_t)a.out_lay.units : a.out_plane;
 #pragma unroll
             for (int k = 0; k < PH; ++k) {
                 const int g = pl0 + k;
-                if (g >= a.cg_out) continue;
                 __half2 h[4], l[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -559,10 +564,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_blk_kernel(TcBlkArgs a)
                     float y0 = fmaf(__uint_as_float(v[k * 8 + u * 2]), s_sb[c], s_sb[NP + c]);
                     float y1 = fmaf(__uint_as_float(v[k * 8 + u * 2 + 1]), s_sb[c + 1], s_sb[NP + c + 1]);
                     if (a.apply_act) { y0 = act(y0); y1 = act(y1); }
+                    if (pooled) {
+                        y0 = fmaxf(y0, __shfl_xor_sync(0xffffffffu, y0, 1));
+                        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, 1));
+                    }
                     const __half h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
                     h[u] = __halves2half2(h0, h1);
                     l[u] = __floats2half2_rn(y0 - __half2float(h0), y1 - __half2float(h1));
                 }
+                if (g >= a.cg_out || !writer) continue;
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk)
                     if (a.out[kk]) {
@@ -1025,6 +1035,7 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
         };
         const int64_t tmp_plane = (int64_t)((kGuard + (int64_t)n * T_out * Wp + kGuardBack + 7) & ~7LL);
         int rc;
+        bool pool_fused = false;
         if (X.lay.S) {
             // block-major input: one tile per block of S streams
             TcBlkArgs b;
@@ -1038,8 +1049,17 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
             b.tap = C.kh == 3 ? X.lay.S * W : 1;
             b.cg_in = cg; b.cg_out = C.cout / 8; b.apply_act = last ? 0 : 1;
             b.n_tiles = (n + X.lay.S - 1) / X.lay.S;
+            const bool fuse_pool = !last && C.pool_t == 1 && C.pool_f == 2 && X.lay.kh3 && (W & 1) == 0 && ctx->late_x[l + 1].lay.S > 0;
             if (last) {
                 b.out_f32 = d_emb;
+            } else if (fuse_pool) {
+                // (1,2) max-pool in the epilogue: straight into the next layer's tensor, no temp, no pool launch
+                const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
+                int n_out = 0;
+                route(Y, b.out, b.out_toff, n_out);
+                b.out_lay = Y.lay;
+                b.pool_f = 2;
+                pool_fused = true;
             } else if (C.pool_t) {
                 b.out[0] = reinterpret_cast<__half*>(ctx->d_late_tmp[0]);
                 b.out_plane = tmp_plane;
@@ -1084,7 +1104,7 @@ int oww_late_chain(oww_ctx* ctx, float* d_emb, cudaStream_t s) {
         rc = dispatch_tc<3>(ctx, cgp, np, a, s);
         if (rc) return rc;
         }
-        if (C.pool_t && !last) {
+        if (C.pool_t && !last && !pool_fused) {
             const oww_ctx::LateTensor& Y = ctx->late_x[l + 1];
             PoolOut po{{nullptr, nullptr, nullptr}, {0, 0, 0}, Y.T_buf};
             po.lay = Y.lay;

@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 float* s_win = reinterpret_cast<float*>(sc + 4096);
                 uint8_t* s_work = smem + 2048 + warp * (kMelNF * kMelFrameScratch);   // FFT work buffers: arena base, dead after this phase
                 float* s_floor = s_mel + G * 256;
+                int seen_v = 1;
                 for (int i = et; i < 512; i += kIncEpiWarps * 32) { s_tw[i] = a.mel_twiddle[i]; s_win[i] = a.mel_window[i]; }
                 if (et < G) {
                     const int b = grp * G + et;
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     // fresh stream (first chunk after a reset): only 5 mel frames exist.  Its history is
                     // ones(76,32), which is invariant under a shift in time, so the step is the ordinary 8-row step on
                     // the rows [1, 1, 1, m0..m4] with the tails of the all-ones window (written at reset)
-                    s_live[8 + et] = s_live[et] && a.seen[b] == 0;
+                    seen_v = s_live[et] ? a.seen[b] : 1;
+                    s_live[8 + et] = s_live[et] && seen_v == 0;
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 const int my_start = a.mel_start[lane], my_len = a.mel_len[lane];
@@ -340,6 +342,25 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
                 if (a.dbg_clock && blockIdx.x == 0 && grp == 0 && et == 0) a.dbg_clock[97] = clock64();
+                // the streams' new tails = the last 480 samples of this chunk: 32-bit words, loaded now (every frame has been read)
+                // and stored behind the clamp below, so the L2 latency hides under it
+                constexpr int kTW = OWW_TAIL / 2;                                  // words per stream
+                const bool al = ((size_t)a.pcm & 3) == 0 && (a.pcm_stride & 1) == 0;
+                uint32_t tv[4]; int ti[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = et + u * kIncEpiWarps * 32;
+                    ti[u] = -1; tv[u] = 0;
+                    if (i < G * kTW) {
+                        const int g = i / kTW, k = i - g * kTW, b = grp * G + g;
+                        if (s_live[g]) {
+                            const int16_t* src = a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + 2 * k;
+                            tv[u] = al ? __ldg(reinterpret_cast<const uint32_t*>(src))
+                                       : ((uint32_t)(unsigned short)__ldg(src) | ((uint32_t)(unsigned short)__ldg(src + 1) << 16));
+                            ti[u] = b * kTW + k;
+                        }
+                    }
+                }
                 if (warp < G) {                                    // per-call (= per stream, this step) maximum -> -80 dB floor
                     float m = -INFINITY;
                     const int j0 = s_live[8 + warp] ? 3 : 0;       // a fresh stream's call holds frames 3..7 only
@@ -360,29 +381,10 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                     if (s_live[g] && fr >= skip)
                         a.mel_rw[(int64_t)b * a.mel_stride + (int64_t)((s_cnt[g] + fr - skip) & a.mel_mask) * 32 + (i & 31)] = v;
                 }
-                {   // the streams' new tails = the last 480 samples of this chunk: 32-bit words, all loads of a thread in flight at once
-                    constexpr int kTW = OWW_TAIL / 2;                                  // words per stream
-                    const bool al = ((size_t)a.pcm & 3) == 0 && (a.pcm_stride & 1) == 0;
-                    uint32_t tv[4]; int ti[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = et + u * kIncEpiWarps * 32;
-                        ti[u] = -1; tv[u] = 0;
-                        if (i < G * kTW) {
-                            const int g = i / kTW, k = i - g * kTW, b = grp * G + g;
-                            if (s_live[g]) {
-                                const int16_t* src = a.pcm + (int64_t)b * a.pcm_stride + (OWW_SAMPLES_PER_CHUNK - OWW_TAIL) + 2 * k;
-                                tv[u] = al ? __ldg(reinterpret_cast<const uint32_t*>(src))
-                                           : ((uint32_t)(unsigned short)__ldg(src) | ((uint32_t)(unsigned short)__ldg(src + 1) << 16));
-                                ti[u] = b * kTW + k;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (ti[u] >= 0) reinterpret_cast<uint32_t*>(a.tail)[ti[u]] = tv[u];
-                    static_assert(kIncMaxG * kTW <= 4 * kIncEpiWarps * 32, "tail copy: four words per thread cover a group");
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (ti[u] >= 0) reinterpret_cast<uint32_t*>(a.tail)[ti[u]] = tv[u];
+                static_assert(kIncMaxG * (OWW_TAIL / 2) <= 4 * kIncEpiWarps * 32, "tail copy: four words per thread cover a group");
                 // the next group's PCM (first touch: HBM) -> L2 while this group's layers run
                 if (grp + (int)gridDim.x < P.n_groups && et < G * 20) {
                     const int g = et / 20, ln = et - g * 20, b = (grp + (int)gridDim.x) * G + g;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kIncThreads, 1) tc_inc_kernel(const __grid_con
                 if (et < G && s_live[et]) {
                     const int b = grp * G + et;
                     a.mel_count_rw[b] = oww_wrap_count(s_cnt[et] + (s_live[8 + et] ? 5 : 8));
-                    const int sn = a.seen[b] + 1;
+                    const int sn = seen_v + 1;                     // read when the group started (same thread)
                     a.seen[b] = sn > (1 << 30) ? (1 << 30) : sn;
                 }
                 named_bar_sync(2, kIncEpiWarps * 32);
