@@ -75,3 +75,28 @@ def test_peer_gather_two_gpus(torch_cuda, built_library, n_total):
     want = np.concatenate([local[0], local[1]], axis=1)          # [steps, n_total, n_cols] in stream order
     for k in range(steps):
         np.testing.assert_array_equal(full[k], want[k])
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process(torch_cuda, built_library):
+    """Two handles on two GPUs inside ONE process (the per-device function attributes - dynamic shared memory above
+    48 KB for the conv, heads and step kernels - are tracked per handle): both must run the default path and agree."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from openwakeword_b200.engine import StreamEngine
+    rng = np.random.default_rng(5)
+    hs = [head("alexa_v0.1"), head("timer_v0.1")]
+    B, steps = 200, 6
+    pcm = rng.integers(-3000, 3000, (B, steps * 1280)).astype(np.int16)
+    outs = []
+    for dev in (0, 1):
+        eng = StreamEngine(hs, B, embedding=emb_weights(), device_index=dev, cnn_mode=3)
+        got = []
+        with torch.cuda.device(dev):
+            for k in range(steps):
+                d = torch.from_numpy(np.ascontiguousarray(pcm[:, k * 1280:(k + 1) * 1280])).to(f"cuda:{dev}")
+                got.append(eng.step(d, 1).cpu().numpy())
+        outs.append(np.stack(got))
+        eng.ctx.close()
+    np.testing.assert_array_equal(outs[0], outs[1])

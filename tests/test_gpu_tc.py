@@ -470,3 +470,32 @@ def test_grouped_heads_match_per_head_kernels(torch_cuda, built_library):
     e_grp_tc, e_grp_cc, e_tc_cc = err(outs["grp"], outs["tc"]), err(outs["grp"], outs["cc"]), err(outs["tc"], outs["cc"])
     print(f"grouped vs per-head TC {e_grp_tc:.3e}; grouped vs CUDA cores {e_grp_cc:.3e}; per-head TC vs CUDA cores {e_tc_cc:.3e} ({cols} columns)")
     assert e_grp_tc < 5e-5 and e_grp_cc < 2e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("split_from,tol", [(15, 1e-3), (20, 1e-3)])
+def test_split_from_variants_vs_oracle(torch_cuda, built_library, split_from, tol):
+    """The other points of the precision / speed curve bench.py reports as `variants`: conv layers >= 15 on split operands
+    (tc_inc_kernel<15> + a 5-layer late chain) and plain fp16 everywhere (one launch per step), against the oracle."""
+    from openwakeword_b200.engine import StreamEngine
+    from oracle import streaming, heads as oheads
+    rng = np.random.default_rng(41)
+    B, steps = 300, 12
+    hs = [head("alexa_v0.1"), head("timer_v0.1")]
+    fi = rng.normal(0, 1, (41, 96)).astype(np.float32)
+    pcm = _mixes(rng, B, steps * 1280)
+    eng = StreamEngine(hs, B, embedding=emb_weights(), feature_init=fi, cnn_mode=3, split_from=split_from)
+    got = np.stack([eng.step_host(np.ascontiguousarray(pcm[:, k * 1280:(k + 1) * 1280]), 1).copy() for k in range(steps)])
+    eng.ctx.close()
+    worst = 0.0
+    for b in list(range(0, B, 23)) + [B - 1]:
+        o = streaming.OracleAudioFeatures(emb_weights(), feature_init=fi)
+        for k in range(steps):
+            o(pcm[b, k * 1280:(k + 1) * 1280])
+            col = 0
+            for h in hs:
+                ref = oheads.forward(h, o.get_features(h["n_in"]))[0]
+                worst = max(worst, float(np.abs(ref - got[k, b, col:col + ref.size]).max()))
+                col += ref.size
+    print(f"split_from={split_from}: max |score - oracle| = {worst:.3e}")
+    assert worst < tol
