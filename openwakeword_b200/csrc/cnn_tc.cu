@@ -116,7 +116,8 @@ struct TcConvArgs {
     int n_tiles;
     int out_split;                          // 1: write fp16 hi planes [0, cg_out) and lo planes [cg_out, 2 cg_out) (y = hi + lo)
     int64_t rows_out;                       // final layer: embedding rows per window (T_out valid rows; fully convolutional clips)
-    // incremental late layers (cnn_tc_late.cu): the output rows land at row offset out_toff inside buffers that hold
+    // incremental late layers on plane-major tensors (the reserved[0] bit-4 fallback; the default chain runs
+    // tc_conv_blk_kernel below): the output rows land at row offset out_toff inside buffers that hold
     // out_T rows per stream (tails in front), and are mirrored into up to two further buffers where they will serve as
     // tails of later steps.  out_T == 0: plain layout (out_T = T_out, no offset, no mirrors).
     int out_T, out_toff;

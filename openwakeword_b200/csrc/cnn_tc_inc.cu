@@ -69,7 +69,8 @@ struct IncArgs {
     int hring_off, hslot_bytes, hns;                          // smem ring the producer streams the heads' first-layer weights through
     const Gate* gates; int n_gates;                           // conditional verifier pairs, applied after the heads phase
     // cut plan (plan.n_layers < 20): the pooled output of the last fused layer leaves the kernel as fp16 hi/lo planes in
-    // the window-mode layout [plane][stream][row][f + pad] - the input of the incremental late layers (cnn_tc.cu)
+    // the block-major layout of the first incremental late layer's input (gx_lay, cnn_tc.cu), or - fallback - the
+    // plane-major window layout [plane][stream][row][f + pad]
     uint4* gx; int64_t gx_plane; LateLay gx_lay;     // gx_lay.S > 0: block-major destination (cnn_tc.cu)
 };
 

@@ -1,4 +1,6 @@
-// K3 (tensor-core path): the wake-word heads as a chain of tcgen05 GEMMs, one CTA per (128 streams, head).
+// K3 (tensor-core path, per head): the wake-word heads as a chain of tcgen05 GEMMs, one CTA per (128 samples, head).
+// Streaming steps and bulk clips run heads_grp.cu (all heads of a window in one CTA, A operand from the fp16 mirror); this
+// kernel serves stateless calls on caller-supplied features and the heads no group covers.
 //
 // Same graphs as heads.cu (reference: <head>.onnx sessions, /root/reference/openwakeword/model.py:137-138,153-159,287-302;
 // family /root/reference/openwakeword/train.py:56-83,144-165).  heads.cu tiles 8 or 32 streams per CTA and streams the

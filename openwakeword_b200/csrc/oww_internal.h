@@ -174,7 +174,7 @@ struct oww_ctx {
     void* d_inc_tails[2] = {nullptr, nullptr};   // [n_groups][tail_units] 16-byte units, double-buffered per step
     int inc_cur = 0;                 // tails buffer the next step reads
     // Incremental late layers (cnn_tc.cu, bottom): tensors X_l = input of conv layer l >= split_from, per stream
-    // [tails | new rows], fp16 hi/lo planes in the window-mode layout
+    // [tails | new rows], fp16 hi/lo: block-major (LateLay, the default) or plane-major in the window-mode layout
     struct LateTensor { void* buf[3] = {nullptr, nullptr, nullptr}; int n_buf = 0, T_buf = 0, rows_new = 0, W = 0, cg = 0, tmpl_off = -1; int64_t plane = 0;
                         LateLay lay = {0, 0, 0, 0, 0, 0}; };   // lay.S > 0: block-major (tc_conv_blk_kernel); else plane-major [n][T_buf][W + 1]
     LateTensor late_x[OWW_N_CONV];
@@ -182,7 +182,7 @@ struct oww_ctx {
     void* d_late_template = nullptr;             // tails of the all-ones window per tails-bearing late tensor: [plane][2][Wp]
     bool late_active = false;
     bool late_pdl = true;                        // programmatic dependent launches inside the late chain (reserved[0] bit 5 disables)
-    bool late_blocked_ok = true;                 // OWW_LATE_PLAIN=1 keeps the window-mode layout for every late tensor (A/B)
+    bool late_blocked_ok = true;                 // reserved[0] bit 4 keeps the plane-major window layout for every late tensor (A/B)
     long late_step = 0;                          // chunks processed since the buffers were allocated (buffer rotation)
 
     // Priming.  A reset stream's mel history is ones(76,32) (utils.py:165) and its first chunk yields 5 rows (F8).  A
