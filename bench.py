@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_WINDOW = 2 * 41955840          # SURVEY.md Appendix B (reference-algorithmic, per 76x32 window)
 EXEC_FLOPS_PER_FRAME = 2 * 5612544       # what the incremental path computes per frame with one MMA term per K step
 # multiply-accumulates per frame of the incremental conv layers 0..19 (8 new mel rows; SURVEY.md Appendix B shapes)
-INC_MACS = [6912, 442368, 442368, 221184, 442368, 442368, 442368, 331776, 497664, 497664, 497664,
+INC_MACS = [55296, 442368, 442368, 221184, 442368, 442368, 442368, 331776, 497664, 497664, 497664,
             165888, 221184, 221184, 221184, 110592, 110592, 110592, 110592, 27648]
 
 

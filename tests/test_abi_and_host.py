@@ -303,3 +303,23 @@ def test_custom_verifier_hook(fake_ctx, tmp_path):
     assert kept == base
     with pytest.raises(ValueError):
         _model(c, custom_verifier_models={"not_loaded": path})
+
+
+def test_bench_flop_accounting_matches_survey():
+    """bench.py's executed-FLOP model: SURVEY.md Appendix B gives 5 612 544 MAC per incremental frame; layers from
+    split_from on take three MMA terms per K step (fp16 hi/lo split operands)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    from oracle import embedding as E
+    rows, W, macs = 8, 32, []
+    for kh, kw, cin, cout, pool in E.LAYERS:
+        macs.append(rows * W * kh * kw * cin * cout)
+        if pool:
+            rows = max(1, rows // pool[0]); W //= pool[1]
+    assert macs == b.INC_MACS and sum(macs) == 5612544
+    assert b.exec_flops_per_frame(20) == 2 * 5612544 == b.EXEC_FLOPS_PER_FRAME
+    assert b.exec_flops_per_frame(0) == b.exec_flops_per_frame(11) == 2 * (5612544 + 2 * sum(macs[11:]))
+    assert b.exec_flops_per_frame(15) == 2 * (5612544 + 2 * sum(macs[15:]))
